@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- training interactions/sec of the RankFM hot path (`_fit` epoch loop) on N x B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+A "step" is one full pass of the hot path over the workload: `epochs` SGD epochs over all interactions, starting from
+the same initial weights every step.  Default workload = BASELINE.json configs[1] (MovieLens-1M shape synthetic, 6040 x
+3706, 1M interactions, factors=20, loss='warp', max_samples=20, 20 epochs).
+
+  value   interactions/s (N * epochs * K / device time) with every input already resident in HBM when the timed region
+          starts (CUDA events on the library's stream, max over ranks); the region holds, per step: D2D restore of the
+          initial weights, an L2 flush (512 MB memset), `epochs` SGD kernel launches + per-epoch weight-stat kernels
+  e2e     the same metric through the reference-facing plug-in call `rankfm_b200._rankfm._fit(...)` on HOST buffers:
+          H2D of interactions/CSR/weights, all epochs, D2H of the weights, wall clock
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement"
+
+Multi-GPU (torchrun, one process per GPU): weak scaling -- every rank owns a cfg2-sized block of users (global U =
+6040*N, 1M*N interactions, one shared item catalogue), item-side deltas are summed over NCCL once per epoch.
+torch.distributed (gloo) is only the control plane here (NCCL-id broadcast, barrier, max-reduce of the timings).
+
+--impl reference times the UNMODIFIED reference Cython `_fit` (oracle/_ref, built by oracle/build_ref.py) on the
+host cores, single-threaded by construction (GIL held, no OpenMP), on a bounded slice of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rankfm_b200.synthetic import CONFIGS, init_weights, side_features, zipf_interactions  # noqa: E402
+
+WEIGHTS = ('w_i', 'w_if', 'v_u', 'v_i', 'v_uf', 'v_if')
+HYPER = dict(alpha=0.01, beta=0.1, learning_rate=0.1, learning_schedule='invscaling', learning_exponent=0.25)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes_per_positive(F, S, P=0, Q=0):
+    """4F(S+5) + 4S + 28 (+ 4P + 4Q(1+S) with dense side features)"""
+    return 4.0 * F * (S + 5.0) + 4.0 * S + 28.0 + (4.0 * P + 4.0 * Q * (1.0 + S) if (P or Q) else 0.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def make_workload(name, rank=0, world=1):
+    c = dict(CONFIGS[name])
+    X = zipf_interactions(c["U"], c["I"], c["N"], seed=42 + rank)
+    U_local = int(X[:, 0].max()) + 1
+    c["U_local"] = U_local
+    U_alloc = c["U"]                                       # fixed block per rank so every rank agrees on the global U
+    X[:, 0] += rank * U_alloc
+    c["U_global"] = U_alloc * world
+    c["I_obs"] = c["I"]
+    c["X"] = X
+    c["sw"] = np.ones(len(X), np.float32)
+    c["x_uf"], c["x_if"] = side_features(c["U_global"], c["I"], c["P"], c["Q"])
+    c["w0"] = init_weights(c["U_global"], c["I"], c["F"], c["P"], c["Q"], seed=0)
+    return c
+
+
+def fresh_weights(c):
+    return {k: v.copy() for k, v in c["w0"].items()}
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# -----------------------------------------------------------------------------------------------------------------
+def reference_fit_rate(c, epochs, repeats=1):
+    """interactions/s of the reference's own Cython `_fit` (single host thread) on this workload; None if unavailable"""
+    from oracle import oracle
+    ref = oracle.load_reference(build_if_possible=True)
+    kind = "reference"
+    fit = ref._fit if ref is not None else None
+    if fit is None:
+        kind, fit = "port", oracle._fit
+    X, U = c["X"], c["U_global"]
+    order = np.lexsort((X[:, 1], X[:, 0]))
+    counts = np.bincount(X[:, 0], minlength=U)
+    bounds = np.concatenate([[0], np.cumsum(counts)])
+    items = X[order, 1].astype(np.int32)
+    ui = {u: items[bounds[u]:bounds[u + 1]] for u in range(U)}
+    best = 0.0
+    for _ in range(repeats):
+        w = fresh_weights(c)
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        fit(X, c["sw"], ui, c["x_uf"], c["x_if"], *[w[k] for k in WEIGHTS], HYPER["alpha"], HYPER["beta"], HYPER["learning_rate"],
+            HYPER["learning_schedule"], HYPER["learning_exponent"], c["max_samples"], epochs, False)
+        dt = time.perf_counter() - t0
+        best = max(best, len(X) * epochs / dt)
+    return best, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = make_workload(args.workload)
+    # bounded sample: as many of the workload's epochs per step as fit in ~2 minutes of single-thread CPU time overall
+    per_epoch_s = 1.3 * len(c["X"]) / 1e6 * max(1.0, c["F"] / 20.0)
+    sample_epochs = int(min(c["epochs"], max(2, 120.0 / per_epoch_s / (args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        reference_fit_rate(c, sample_epochs)
+    t0 = time.perf_counter()
+    rates = [reference_fit_rate(c, sample_epochs) for _ in range(args.steps)]
+    dt = time.perf_counter() - t0
+    kind = rates[0][1]
+    value = float(np.mean([r[0] for r in rates]))
+    line = {
+        "impl": "reference", "metric": "training interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": c["label"], "sample": "%d of %d epochs per step, all %d interactions" % (sample_epochs, c["epochs"], len(c["X"]))},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": 1, "kind": kind,
+                         "sample": "%d epochs x %d interactions per step; the reference holds the GIL and has no OpenMP: 1 thread of %d" % (sample_epochs, len(c["X"]), os.cpu_count())},
+        "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# our arm
+# -----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist                 # control plane only (gloo): id broadcast, barrier, max-reduce
+        dist.init_process_group(backend="gloo", init_method="env://")
+    from rankfm_b200 import _lib, _rankfm
+    assert _lib.lib().rfm_device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
+    _rankfm.set_device(local_rank)
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(_rankfm.nccl_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(idt, src=0)
+        _rankfm.set_comm(rank, world, idt.numpy().tobytes())
+
+    c = make_workload(args.workload, rank, world)
+    X, N, epochs = c["X"], len(c["X"]), c["epochs"]
+    ui = _rankfm.UserItems.from_interactions(X, c["U_global"])
+    w = fresh_weights(c)
+    keep = []
+    prob = _rankfm.fit_problem(X, c["sw"], ui, c["x_uf"], c["x_if"], *[w[k] for k in WEIGHTS], HYPER["alpha"], HYPER["beta"],
+                               HYPER["learning_rate"], HYPER["learning_schedule"], HYPER["learning_exponent"], c["max_samples"],
+                               mode="production", seed=1492, keep=keep)
+    sess = _rankfm.Session(prob, keep)
+    sess.snapshot()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def one_step():
+        sess.restore()
+        sess.flush_l2()
+        return sess.train(epochs)
+
+    for _ in range(args.warmup):
+        one_step()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = sess.launch_count()
+    barrier()
+    sess.timer_start()                                   # synchronises the stream, then records the start event
+    all_stats = [one_step() for _ in range(args.steps)]
+    ms = sess.timer_stop()                               # records + synchronises the stop event
+    barrier()
+    launches = sess.launch_count() - launches0
+    clock_info = clocks.stop() if clocks else None
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        ln = torch.tensor([launches], dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln.item())
+    total_interactions = N * epochs * args.steps * world
+    value = total_interactions / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (sgd_epoch_kernel), from the per-launch CUDA events of the timed steps ----
+    flat = [s for step in all_stats for s in step]
+    kern_ms = sum(s["kernel_ms"] for s in flat)
+    alg_bytes = sum(N * algorithmic_bytes_per_positive(c["F"], s["draws"] / N, c["P"], c["Q"]) for s in flat)
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "sgd_epoch_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / len(flat),
+                "launch_ms": kern_ms / len(flat), "kernel_share_of_step": kern_ms / (ms if world == 1 else max(ms, 1e-9)),
+                "mean_draws_per_positive": float(np.mean([s["draws"] / N for s in flat]))}
+
+    line = None
+    if rank == 0:
+        # ---- e2e: the plug-in call on host buffers (H2D + epochs + D2H inside the timed region) ----
+        def e2e_step():
+            ww = fresh_weights(c)
+            t0 = time.perf_counter()
+            _rankfm._fit(X, c["sw"], ui, c["x_uf"], c["x_if"], *[ww[k] for k in WEIGHTS], HYPER["alpha"], HYPER["beta"], HYPER["learning_rate"],
+                         HYPER["learning_schedule"], HYPER["learning_exponent"], c["max_samples"], epochs, False)
+            return time.perf_counter() - t0
+        e2e = None
+        if world == 1:
+            e2e_step()
+            dts = [e2e_step() for _ in range(max(1, min(args.steps, 5)))]
+            h2d = X.nbytes + c["sw"].nbytes + ui.indptr.nbytes + ui.indices.nbytes + sum(v.nbytes for v in c["w0"].values()) + \
+                (c["x_uf"].nbytes if c["P"] else 0) + (c["x_if"].nbytes if c["Q"] else 0)
+            d2h = sum(v.nbytes for v in c["w0"].values())
+            e2e = {"value": N * epochs / float(np.mean(dts)), "unit": "interactions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": 1e3 * float(np.mean(dts)), "call": "rankfm_b200._rankfm._fit(host ndarray buffers) -> ctypes -> rfm_fit"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sample_epochs = 3
+            rate, kind = reference_fit_rate(c, sample_epochs)
+            cpu = {"value": rate, "unit": "interactions/s", "cores": 1, "kind": kind,
+                   "sample": "%d epochs x %d interactions (of %d epochs); single-threaded by construction, %d host cores present" % (sample_epochs, N, epochs, os.cpu_count())}
+        line = {
+            "metric": "training interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c["label"], "interactions_per_gpu": N, "epochs_per_step": epochs, "users": c["U_global"], "items": c["I"],
+                       "l2": "flushed between steps (512 MB memset inside the timed region); tables (<1 MB) are L2-resident within a step by nature of the workload",
+                       "parallelism": "user-sharded x%d, per-epoch NCCL sum of item deltas" % world if world > 1 else "single GPU",
+                       "schedule": "production: Hogwild lane-group per positive, Philox negatives, on-device Feistel order"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
+            "final_log_likelihood": flat[-1]["log_likelihood"],
+        }
+    sess.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/*
+ * rankfm_b200.h -- C ABI of librankfm_b200.so: the B200 (sm_100a) replacement for RankFM's native hot path.
+ *
+ * The reference's native boundary is the Cython module `rankfm/_rankfm.pyx`, imported at `rankfm/rankfm.py:8`
+ * (`from rankfm._rankfm import _fit, _predict, _recommend`).  Each entry point below names the reference
+ * interface it replaces.  Plain pointers and sizes only: no Python objects, no torch types.  All pointers are
+ * HOST pointers unless a name ends in `_dev`.  Every function returns 0 on success or an RFM_ERR_* code;
+ * `rfm_last_error()` then holds a human-readable message (thread-local).
+ *
+ * There is no CPU fallback: with no CUDA device the calls fail with RFM_ERR_NO_DEVICE.
+ *
+ * Layout conventions (identical to what `rankfm.py:140-244` hands to the Cython functions):
+ *   interactions int32 [N,2] C-contiguous (user_idx, item_idx); sample_weight f32 [N];
+ *   user_items as CSR: csr_indptr int64 [U+1], csr_indices int32 [nnz], each user's items sorted ascending;
+ *   x_uf f32 [U,P], x_if f32 [I,Q] (P=Q=1 all-zero when absent, rankfm.py:199,211);
+ *   w_i f32 [I], w_if f32 [Q], v_u f32 [U,F], v_i f32 [I,F], v_uf f32 [P,F], v_if f32 [Q,F].
+ */
+#ifndef RANKFM_B200_H
+#define RANKFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFM_OK              0
+#define RFM_ERR_ARG         1   /* bad argument (message says which) */
+#define RFM_ERR_CUDA        2   /* CUDA runtime error */
+#define RFM_ERR_NO_DEVICE   3   /* no usable CUDA device: this library has no CPU path */
+#define RFM_ERR_NCCL        4   /* NCCL missing or failed */
+#define RFM_ERR_NONFINITE   5   /* weights went non-finite (reference: AssertionError from assert_finite) */
+#define RFM_ERR_UNSUPPORTED 6
+
+/* learning-rate schedules, `_rankfm.pyx:220-225` */
+#define RFM_SCHEDULE_CONSTANT   0
+#define RFM_SCHEDULE_INVSCALING 1
+
+/* row order inside an epoch */
+#define RFM_ORDER_FEISTEL 0     /* on-device keyed permutation (production) */
+#define RFM_ORDER_HOST    1     /* caller supplies the permutation of each epoch (what np.random.shuffle produced,
+                                   `_rankfm.pyx:227`) */
+/* negative sampler */
+#define RFM_SAMPLER_PHILOX 0    /* counter-based, any schedule (production) */
+#define RFM_SAMPLER_MT     1    /* MT19937 stream of the reference (`_rankfm.pyx:182,251`); serial schedule only */
+/* schedule */
+#define RFM_SCHED_PARALLEL 0    /* Hogwild: one lane-group per positive, whole GPU */
+#define RFM_SCHED_SERIAL   1    /* one lane-group, positives strictly in order: reproduces sequential SGD */
+
+typedef struct rfm_session rfm_session;
+
+/* Model + data description.  Mirrors the positional arguments of `_fit` (`_rankfm.pyx:122-142`). */
+typedef struct rfm_problem {
+    /* interaction data (may be NULL / 0 for a scoring-only session) */
+    const int32_t *interactions;
+    const float   *sample_weight;
+    int64_t        n_interactions;
+    const int64_t *csr_indptr;       /* user_items, [U+1] */
+    const int32_t *csr_indices;      /* [csr_indptr[U]] */
+    /* side features */
+    const float *x_uf;               /* [U,P] */
+    const float *x_if;               /* [I,Q] */
+    /* weights: read at session creation, written back by rfm_session_download / rfm_fit */
+    float *w_i, *w_if, *v_u, *v_i, *v_uf, *v_if;
+    int32_t U, I, P, Q, F;
+    /* hyper-parameters */
+    float   alpha, beta, learning_rate, learning_exponent;
+    int32_t schedule;                /* RFM_SCHEDULE_* */
+    int32_t max_samples;             /* 1 for BPR (`rankfm.py:294-295`) */
+    /* execution */
+    int32_t  order;                  /* RFM_ORDER_* */
+    int32_t  sampler;                /* RFM_SAMPLER_* */
+    int32_t  sched;                  /* RFM_SCHED_* */
+    uint32_t mt_seed;                /* 1492 in the reference */
+    uint64_t seed;                   /* Philox / Feistel key */
+    int32_t  max_rejects;            /* rejection-sampling bound per draw (reference: unbounded); 0 -> 64 */
+    int32_t  device;                 /* CUDA device ordinal */
+    /* multi-GPU (one process per GPU).  world==1: single GPU, nccl_id ignored. */
+    int32_t  rank, world;
+    const uint8_t *nccl_id;          /* 128 bytes from rfm_nccl_unique_id() on rank 0, broadcast by the caller */
+} rfm_problem;
+
+/* Per-epoch report, the device-side equivalent of `_rankfm.pyx:328-336` (assert_finite, reg_penalty, log-lik). */
+typedef struct rfm_epoch_stats {
+    double  log_likelihood;          /* sum of log sigma(pairwise utility), measured before each update */
+    double  penalty;                 /* alpha*sum(w_i^2,v_u^2,v_i^2) + beta*sum(w_if^2,v_uf^2,v_if^2) */
+    int64_t draws;                   /* negatives evaluated (sum of `sampled`) */
+    int32_t finite[6];               /* w_i, w_if, v_u, v_i, v_uf, v_if: 1 = finite */
+    float   eta;                     /* learning rate used */
+    float   kernel_ms;               /* CUDA-event time of the SGD kernel launch(es) of this epoch */
+    float   sync_ms;                 /* CUDA-event time of the multi-GPU delta exchange (0 when world==1) */
+} rfm_epoch_stats;
+
+/* ---- library / device ---- */
+const char *rfm_version(void);
+const char *rfm_last_error(void);
+int rfm_device_count(void);                                      /* number of CUDA devices, 0 if none */
+int rfm_nccl_unique_id(uint8_t *out128);                         /* rank 0 calls, caller broadcasts */
+
+/* host-side evaluation of the kernels' RNG definitions (csrc/rfm_rng.cuh), so CPU tests can hold them to the
+ * contract shared with the oracle: Philox4x32-10 block and the per-epoch Feistel permutation of [0,n) */
+int rfm_debug_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4);
+int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_t r0, int64_t count, int64_t *out);
+
+/* ---- one-shot calls on host buffers: the drop-in boundary ---- */
+
+/* replaces `_fit` (`_rankfm.pyx:122-342`): trains `epochs` epochs, updates the six weight arrays in place.
+ * `perms` = int32 [epochs,N] when order==RFM_ORDER_HOST, else NULL.  `stats` = [epochs] or NULL. */
+int rfm_fit(const rfm_problem *p, int32_t epochs, const int32_t *perms, rfm_epoch_stats *stats);
+
+/* replaces `_predict` (`_rankfm.pyx:345-390`): pairs f32 [n,2] hold indexes as floats, NaN = unknown id */
+int rfm_predict(const rfm_problem *p, const float *pairs, int64_t n, float *scores);
+
+/* replaces `_recommend` (`_rankfm.pyx:393-460`): users f32 [n_users] (NaN = unknown), rec_items f32
+ * [n_users,n_items] receives item indexes as floats; rows of unknown users are NaN.  When fewer than n_items
+ * candidates survive `filter_previous` the tail is NaN (the reference leaves it uninitialised). */
+int rfm_recommend(const rfm_problem *p, const float *users, int64_t n_users, int32_t n_items, int32_t filter_previous,
+                  float *rec_items);
+
+/* similar_items / similar_users (`rankfm.py:405-454`): top-n rows of (v + x.v_f) by inner product with row
+ * `index`, the query row itself excluded.  which = 0 items, 1 users.  out int32 [n]. */
+int rfm_similar(const rfm_problem *p, int32_t which, int32_t index, int32_t n, int32_t *out);
+
+/* ---- resident sessions: upload once, train / score many times (bench.py, RankFM class) ---- */
+int rfm_session_create(const rfm_problem *p, rfm_session **out);             /* allocates HBM, copies H2D */
+int rfm_session_train(rfm_session *s, int32_t epochs, const int32_t *perms, rfm_epoch_stats *stats);
+int rfm_session_set_weights(rfm_session *s, const float *w_i, const float *w_if, const float *v_u, const float *v_i,
+                            const float *v_uf, const float *v_if);           /* H2D of the weights only */
+/* device-side copy of the current weights, and restoring it (D2D only): lets a benchmark restart training from
+ * identical weights without a host round trip */
+int rfm_session_snapshot(rfm_session *s);
+int rfm_session_restore(rfm_session *s);
+/* CUDA events on the session's stream: start .. stop brackets whatever was enqueued in between */
+int rfm_session_timer_start(rfm_session *s);
+int rfm_session_timer_stop(rfm_session *s, float *ms_out);
+int rfm_session_download(rfm_session *s, float *w_i, float *w_if, float *v_u, float *v_i, float *v_uf, float *v_if);
+int rfm_session_predict(rfm_session *s, const float *pairs, int64_t n, float *scores);
+int rfm_session_recommend(rfm_session *s, const float *users, int64_t n_users, int32_t n_items, int32_t filter_previous,
+                          float *rec_items);
+/* device-resident timing probes used by bench.py: run the op `iters` times on inputs already in HBM and return
+ * the mean CUDA-event milliseconds per iteration (no host<->device copies inside the timed region) */
+int rfm_session_time_predict(rfm_session *s, const float *pairs, int64_t n, int32_t iters, float *ms_out);
+int rfm_session_time_recommend(rfm_session *s, const float *users, int64_t n_users, int32_t n_items, int32_t filter_previous,
+                               int32_t iters, float *ms_out, float *gemm_ms_out);
+int rfm_session_flush_l2(rfm_session *s);                                    /* overwrite a >L2-sized scratch buffer */
+int rfm_session_launch_count(rfm_session *s, int64_t *launches);             /* kernels launched by this session */
+int rfm_session_destroy(rfm_session *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANKFM_B200_H */

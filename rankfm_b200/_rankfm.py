@@ -1,0 +1,365 @@
+"""Drop-in replacement of the reference's Cython module ``rankfm._rankfm``.
+
+Exports ``_fit``, ``_predict`` and ``_recommend`` with the reference's positional signatures
+(``rankfm/_rankfm.pyx:122-142``, ``:345-355``, ``:393-406``; imported at ``rankfm/rankfm.py:8``) and forwards them
+through ctypes to the hand-written sm_100a kernels in ``librankfm_b200.so``.  Host code stays NumPy; there is no
+PyTorch and no CPU fallback on this path.
+
+Execution modes of ``_fit`` (``set_mode`` / env ``RANKFM_B200_MODE``):
+
+``production`` (default)
+    Hogwild SGD over the whole GPU, Philox negatives, on-device per-epoch permutation.  Statistically equivalent
+    to the reference; not the same trajectory.
+``replay``
+    One lane group walks the positives strictly in the order ``np.random.shuffle`` produces (consuming NumPy's
+    global RNG exactly like ``_rankfm.pyx:227``) and draws negatives from the reference's MT19937 stream seeded
+    1492 (``:182``): the same trajectory as the reference up to float reassociation.  Parity/test mode.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import Problem, EpochStats, as_buffer, check, ptr
+
+_MODE = os.environ.get("RANKFM_B200_MODE", "production")
+_SEED = int(os.environ.get("RANKFM_B200_SEED", "1492"))
+_DEVICE = int(os.environ.get("RANKFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+_COMM = {"rank": 0, "world": 1, "nccl_id": None}
+last_stats = None       # list of per-epoch dicts of the most recent _fit
+
+
+def set_mode(mode):
+    global _MODE
+    assert mode in ("production", "replay"), "[mode] must be in ('production', 'replay')"
+    _MODE = mode
+
+
+def get_mode():
+    return _MODE
+
+
+def set_seed(seed):
+    global _SEED
+    _SEED = int(seed)
+
+
+def set_device(device):
+    global _DEVICE
+    _DEVICE = int(device)
+
+
+def set_comm(rank, world, nccl_id):
+    """multi-GPU: one process per GPU; ``nccl_id`` = the 128 bytes of ``nccl_unique_id()`` made on rank 0 and
+    broadcast by the caller.  Each rank then passes ITS shard of the interactions (see ``shard_by_user``)."""
+    _COMM.update(rank=int(rank), world=int(world), nccl_id=None if nccl_id is None else np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy())
+
+
+def nccl_unique_id():
+    out = np.zeros(128, dtype=np.uint8)
+    check(_lib.lib().rfm_nccl_unique_id(ptr(out)))
+    return out.tobytes()
+
+
+def device_count():
+    return _lib.lib().rfm_device_count()
+
+
+class UserItems(dict):
+    """``user_items`` (``rankfm/rankfm.py:174``: ``{user_idx: sorted int32 array of item_idx}``) backed by one CSR.
+
+    Behaves like the reference's dict (``d[u]``, ``keys()``, ``items()``, ``len``) but the per-user arrays are views
+    created on first access, and ``_fit``/``_recommend`` read ``indptr``/``indices`` directly instead of walking
+    ``U`` Python objects like ``_rankfm.pyx:201-212`` does."""
+
+    def __init__(self, indptr, indices):
+        super().__init__()
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self._n = len(self.indptr) - 1
+
+    def __missing__(self, u):
+        ui = int(u)
+        if ui != u or not 0 <= ui < self._n:
+            raise KeyError(u)
+        view = self.indices[self.indptr[ui]:self.indptr[ui + 1]]
+        dict.__setitem__(self, ui, view)
+        return view
+
+    def __contains__(self, u):
+        try:
+            return 0 <= int(u) < self._n and int(u) == u
+        except (TypeError, ValueError):
+            return False
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        return iter(range(self._n))
+
+    def keys(self):
+        return range(self._n)
+
+    def values(self):
+        return (self[u] for u in range(self._n))
+
+    def items(self):
+        return ((u, self[u]) for u in range(self._n))
+
+    def get(self, u, default=None):
+        return self[u] if u in self else default
+
+    def __reduce__(self):
+        return (UserItems, (self.indptr, self.indices))
+
+    @classmethod
+    def from_interactions(cls, interactions, n_users):
+        """CSR of the items of each user, sorted ascending, duplicates kept (like ``rankfm.py:174``)"""
+        inter = np.asarray(interactions)
+        order = np.lexsort((inter[:, 1], inter[:, 0]))
+        counts = np.bincount(inter[:, 0], minlength=n_users)
+        indptr = np.zeros(n_users + 1, dtype=np.int64)
+        np.cumsum(counts, out=indptr[1:])
+        return cls(indptr, inter[order, 1].astype(np.int32))
+
+
+def user_items_to_csr(user_items, n_users):
+    if hasattr(user_items, "indptr") and hasattr(user_items, "indices"):
+        return user_items.indptr, user_items.indices
+    lens = np.fromiter((len(user_items[u]) for u in range(n_users)), dtype=np.int64, count=n_users)
+    indptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    if n_users:
+        indices = np.ascontiguousarray(np.concatenate([np.asarray(user_items[u], dtype=np.int32) for u in range(n_users)]), dtype=np.int32)
+    else:
+        indices = np.zeros(0, dtype=np.int32)
+    return indptr, indices
+
+
+def _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep):
+    for a, nd, name in ((x_uf, 2, "x_uf"), (x_if, 2, "x_if"), (w_i, 1, "w_i"), (w_if, 1, "w_if"),
+                        (v_u, 2, "v_u"), (v_i, 2, "v_i"), (v_uf, 2, "v_uf"), (v_if, 2, "v_if")):
+        as_buffer(a, np.float32, nd, name)
+    p = Problem()
+    p.x_uf, p.x_if = ptr(x_uf), ptr(x_if)
+    p.w_i, p.w_if, p.v_u, p.v_i, p.v_uf, p.v_if = ptr(w_i), ptr(w_if), ptr(v_u), ptr(v_i), ptr(v_uf), ptr(v_if)
+    p.U, p.F = v_u.shape
+    p.I, p.P, p.Q = v_i.shape[0], v_uf.shape[0], v_if.shape[0]
+    p.max_samples = 1
+    p.device = _DEVICE
+    p.rank, p.world = 0, 1
+    keep.extend([x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if])
+    return p
+
+
+def fit_problem(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
+                alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples,
+                mode=None, seed=None, keep=None):
+    """build the ``rfm_problem`` for a training call; ``keep`` collects the arrays whose memory it points into"""
+    keep = [] if keep is None else keep
+    as_buffer(interactions, np.int32, 2, "interactions")
+    as_buffer(sample_weight, np.float32, 1, "sample_weight")
+    if learning_schedule not in _lib.SCHEDULE:
+        raise ValueError('unknown [learning_schedule]')                       # _rankfm.pyx:225
+    p = _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep)
+    indptr, indices = user_items_to_csr(user_items, p.U)
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    keep.extend([interactions, sample_weight, indptr, indices])
+    p.interactions, p.sample_weight, p.n_interactions = ptr(interactions), ptr(sample_weight), interactions.shape[0]
+    p.csr_indptr, p.csr_indices = ptr(indptr), ptr(indices)
+    p.alpha, p.beta, p.learning_rate, p.learning_exponent = alpha, beta, learning_rate, learning_exponent
+    p.schedule = _lib.SCHEDULE[learning_schedule]
+    p.max_samples = max_samples
+    mode = mode or _MODE
+    if mode == "replay":
+        p.order, p.sampler, p.sched = _lib.ORDER_HOST, _lib.SAMPLER_MT, _lib.SCHED_SERIAL
+    else:
+        p.order, p.sampler, p.sched = _lib.ORDER_FEISTEL, _lib.SAMPLER_PHILOX, _lib.SCHED_PARALLEL
+    p.mt_seed = 1492                                                           # _rankfm.pyx:182
+    p.seed = _SEED if seed is None else int(seed)
+    p.max_rejects = 0
+    p.rank, p.world = _COMM["rank"], _COMM["world"]
+    if p.world > 1:
+        keep.append(_COMM["nccl_id"])
+        p.nccl_id = ptr(_COMM["nccl_id"])
+    return p
+
+
+def _stats_list(stats, epochs):
+    return [dict(log_likelihood=s.log_likelihood, penalty=s.penalty, draws=s.draws, finite=list(s.finite), eta=s.eta,
+                 kernel_ms=s.kernel_ms, sync_ms=s.sync_ms) for s in stats[:epochs]]
+
+
+def fit_ex(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
+           alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, epochs,
+           mode=None, perms=None, seed=None, order=None, sampler=None, sched=None, max_rejects=0):
+    """``_fit`` with the execution knobs exposed (tests, bench).  ``perms`` int32 [epochs, N] is required when the
+    order is HOST; ``order``/``sampler``/``sched`` override what ``mode`` selects.  Returns the per-epoch stats;
+    raises like ``_fit``."""
+    keep = []
+    p = fit_problem(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
+                    alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, mode=mode, seed=seed, keep=keep)
+    if order is not None:
+        p.order = order
+    if sampler is not None:
+        p.sampler = sampler
+    if sched is not None:
+        p.sched = sched
+    p.max_rejects = max_rejects
+    if p.order == _lib.ORDER_HOST:
+        perms = np.ascontiguousarray(perms, dtype=np.int32)
+        assert perms.shape == (epochs, interactions.shape[0]), "[perms] must be int32 [epochs, N]"
+    else:
+        perms = None
+    stats = (EpochStats * epochs)()
+    rc = _lib.lib().rfm_fit(C.byref(p), epochs, ptr(perms), C.cast(stats, C.c_void_p))
+    out = _stats_list(stats, epochs)
+    check(rc)
+    return out
+
+
+def _fit(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
+         alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, epochs, verbose):
+    """train in place on the GPU -- same contract as the reference's ``_fit`` (``_rankfm.pyx:122-342``): the six weight
+    arrays are updated in place, nothing is returned, ``AssertionError`` if weights go non-finite."""
+    global last_stats
+    perms = None
+    if _MODE == "replay":
+        N = interactions.shape[0]
+        shuffle_index = np.arange(N, dtype=np.int32)                           # _rankfm.pyx:197
+        perms = np.empty((epochs, N), dtype=np.int32)
+        for e in range(epochs):
+            np.random.shuffle(shuffle_index)                                   # _rankfm.pyx:227 (cumulative)
+            perms[e] = shuffle_index
+    last_stats = fit_ex(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
+                        alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, epochs, perms=perms)
+    if verbose:
+        for e, s in enumerate(last_stats):                                     # _rankfm.pyx:332-336
+            print("\ntraining epoch:", e)
+            print("log likelihood:", round(float(np.float32(s["log_likelihood"] - s["penalty"])), 2))
+
+
+def _predict(pairs, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if):
+    """scores of (user_idx, item_idx) pairs given as float32, NaN = unknown id (``_rankfm.pyx:345-390``)"""
+    as_buffer(pairs, np.float32, 2, "pairs")
+    keep = []
+    p = _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep)
+    scores = np.empty(pairs.shape[0], dtype=np.float32)
+    check(_lib.lib().rfm_predict(C.byref(p), ptr(pairs), pairs.shape[0], ptr(scores)))
+    return scores
+
+
+def _recommend(users, user_items, n_items, filter_previous, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if):
+    """top-``n_items`` item indexes (as float32) per user (``_rankfm.pyx:393-460``)"""
+    as_buffer(users, np.float32, 1, "users")
+    keep = []
+    p = _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep)
+    if filter_previous:
+        indptr, indices = user_items_to_csr(user_items, p.U)
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        keep.extend([indptr, indices])
+        p.csr_indptr, p.csr_indices = ptr(indptr), ptr(indices)
+    rec_items = np.empty((users.shape[0], n_items), dtype=np.float32)
+    check(_lib.lib().rfm_recommend(C.byref(p), ptr(users), users.shape[0], int(n_items), int(bool(filter_previous)), ptr(rec_items)))
+    return rec_items
+
+
+def _similar(which, index, n, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if):
+    """top-n most similar rows by latent inner product (``rankfm.py:405-454``); which=0 items, 1 users"""
+    keep = []
+    p = _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep)
+    out = np.empty(n, dtype=np.int32)
+    check(_lib.lib().rfm_similar(C.byref(p), int(which), int(index), int(n), ptr(out)))
+    return out
+
+
+def shard_by_user(interactions, sample_weight, n_users, rank, world):
+    """user-range partition with ~equal interaction counts: rank r gets the rows of users in [b_r, b_{r+1})"""
+    counts = np.bincount(interactions[:, 0], minlength=n_users)
+    cum = np.cumsum(counts)
+    bounds = np.searchsorted(cum, cum[-1] * np.arange(1, world) / world, side="left")
+    bounds = np.concatenate([[0], bounds + 1, [n_users]])
+    lo, hi = bounds[rank], bounds[rank + 1]
+    sel = (interactions[:, 0] >= lo) & (interactions[:, 0] < hi)
+    return np.ascontiguousarray(interactions[sel]), np.ascontiguousarray(sample_weight[sel]), (int(lo), int(hi))
+
+
+class Session:
+    """resident-HBM session used by ``bench.py`` and the ``RankFM`` class: upload once, train/score many times"""
+
+    def __init__(self, problem, keep):
+        self._keep = keep
+        self._p = problem
+        h = C.c_void_p()
+        check(_lib.lib().rfm_session_create(C.byref(problem), C.byref(h)))
+        self._h = h
+
+    def train(self, epochs, perms=None):
+        stats = (EpochStats * epochs)()
+        rc = _lib.lib().rfm_session_train(self._h, epochs, ptr(perms), C.cast(stats, C.c_void_p))
+        out = _stats_list(stats, epochs)
+        check(rc)
+        return out
+
+    def set_weights(self, w_i, w_if, v_u, v_i, v_uf, v_if):
+        check(_lib.lib().rfm_session_set_weights(self._h, *[ptr(a) for a in (w_i, w_if, v_u, v_i, v_uf, v_if)]))
+
+    def download(self, w_i, w_if, v_u, v_i, v_uf, v_if):
+        check(_lib.lib().rfm_session_download(self._h, *[ptr(a) for a in (w_i, w_if, v_u, v_i, v_uf, v_if)]))
+
+    def snapshot(self):
+        check(_lib.lib().rfm_session_snapshot(self._h))
+
+    def restore(self):
+        check(_lib.lib().rfm_session_restore(self._h))
+
+    def timer_start(self):
+        check(_lib.lib().rfm_session_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(_lib.lib().rfm_session_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def predict(self, pairs):
+        scores = np.empty(pairs.shape[0], dtype=np.float32)
+        check(_lib.lib().rfm_session_predict(self._h, ptr(pairs), pairs.shape[0], ptr(scores)))
+        return scores
+
+    def recommend(self, users, n_items, filter_previous=False):
+        rec = np.empty((users.shape[0], n_items), dtype=np.float32)
+        check(_lib.lib().rfm_session_recommend(self._h, ptr(users), users.shape[0], n_items, int(filter_previous), ptr(rec)))
+        return rec
+
+    def time_predict(self, pairs, iters=10):
+        ms = C.c_float()
+        check(_lib.lib().rfm_session_time_predict(self._h, ptr(pairs), pairs.shape[0], iters, C.byref(ms)))
+        return ms.value
+
+    def time_recommend(self, users, n_items, filter_previous=False, iters=3):
+        ms, gemm = C.c_float(), C.c_float()
+        check(_lib.lib().rfm_session_time_recommend(self._h, ptr(users), users.shape[0], n_items, int(filter_previous), iters, C.byref(ms), C.byref(gemm)))
+        return ms.value, gemm.value
+
+    def flush_l2(self):
+        check(_lib.lib().rfm_session_flush_l2(self._h))
+
+    def launch_count(self):
+        n = C.c_int64()
+        check(_lib.lib().rfm_session_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self._h:
+            _lib.lib().rfm_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,818 @@
+// rfm_api.cu -- the C ABI (include/rankfm_b200.h): sessions, H2D/D2H, epoch loop, multi-GPU delta exchange.
+//
+// Host-side driver of the kernels; replaces the Python/Cython set-up and epoch loop of `_fit`
+// (rankfm/_rankfm.pyx:182-228, 328-342), `_predict` (:345-390) and `_recommend` (:393-460).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rankfm_b200.h"
+#include "rfm_kernels.h"
+
+using namespace rfm;
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(RFM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* rfm_version(void) { return "rankfm_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* rfm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int rfm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU use has no NCCL dependency
+// ---------------------------------------------------------------------------------------------------------------
+struct Id128 { char b[128]; };   // ncclUniqueId is 128 opaque bytes, passed by value
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.h) return RFM_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return fail(RFM_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(RFM_ERR_NCCL, "libnccl.so.2 lacks required symbols");
+    g_nccl.h = h;
+    return RFM_OK;
+}
+#define NC(call)                                                                                        \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != 0) return fail(RFM_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+constexpr int kNcclFloat = 7, kNcclSum = 0;   // ncclFloat32, ncclSum (nccl.h enum values, stable across 2.x)
+
+extern "C" int rfm_nccl_unique_id(uint8_t* out128)
+{
+    if (!out128) return fail(RFM_ERR_ARG, "out128 is NULL");
+    int rc = nccl_load();
+    if (rc) return rc;
+    NC(g_nccl.GetUniqueId(out128));
+    return RFM_OK;
+}
+
+extern "C" int rfm_debug_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4)
+{
+    if (!out4) return fail(RFM_ERR_ARG, "out4 is NULL");
+    const Philox4 b = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    out4[0] = b.x; out4[1] = b.y; out4[2] = b.z; out4[3] = b.w;
+    return RFM_OK;
+}
+
+extern "C" int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_t r0, int64_t count, int64_t* out)
+{
+    if (!out || n < 1 || r0 < 0 || r0 + count > n) return fail(RFM_ERR_ARG, "bad feistel range");
+    const Feistel f = make_feistel(n, seed, epoch);
+    for (int64_t k = 0; k < count; ++k) out[k] = feistel_perm(f, r0 + k);
+    return RFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// session
+// ---------------------------------------------------------------------------------------------------------------
+struct rfm_session {
+    rfm_problem p{};            // host pointers are NOT retained past create (copied fields only)
+    Tables T{};
+    int device = 0, n_sm = 148;
+    cudaStream_t st = nullptr;
+    // data
+    int2* d_inter = nullptr; float* d_sw = nullptr; int64_t* d_indptr = nullptr; int32_t* d_indices = nullptr;
+    int64_t N = 0, nnz = 0;
+    int32_t* d_perm = nullptr;
+    float* d_mult = nullptr;
+    MtState* d_mt = nullptr;
+    EpochAcc* d_acc = nullptr; int acc_cap = 0;
+    size_t gp_floats = 0;
+    int epochs_done = 0;
+    int grid = 148;
+    int64_t launches = 0;
+    // multi-GPU
+    void* comm = nullptr;
+    float *d_it_snap = nullptr, *d_gp_snap = nullptr, *d_ut_init = nullptr;
+    // scratch
+    float *d_snap_ut = nullptr, *d_snap_it = nullptr, *d_snap_gp = nullptr; int snap_epochs = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    float* d_flush = nullptr; size_t flush_bytes = 0;
+    std::vector<cudaEvent_t> ev;
+};
+
+static size_t round4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+static bool any_nonzero(const float* x, size_t n)
+{
+    for (size_t k = 0; k < n; ++k) if (x[k] != 0.0f) return true;
+    return false;
+}
+
+template <typename T>
+static int dev_alloc(T** out, size_t n)
+{
+    *out = nullptr;
+    if (n == 0) n = 1;
+    CU(cudaMalloc((void**)out, n * sizeof(T)));
+    return RFM_OK;
+}
+
+static int upload_weights(rfm_session* s, const float* w_i, const float* w_if, const float* v_u, const float* v_i,
+                          const float* v_uf, const float* v_if, const float* x_uf, const float* x_if, bool features_too)
+{
+    const Tables& T = s->T;
+    float *st_vu = nullptr, *st_vi = nullptr, *st_wi = nullptr, *st_xu = nullptr, *st_xi = nullptr, *st_g = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&st_vu, (size_t)T.U * T.F))) return rc;
+    if ((rc = dev_alloc(&st_vi, (size_t)T.I * T.F))) return rc;
+    if ((rc = dev_alloc(&st_wi, (size_t)T.I))) return rc;
+    CU(cudaMemcpyAsync(st_vu, v_u, (size_t)T.U * T.F * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(st_vi, v_i, (size_t)T.I * T.F * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(st_wi, w_i, (size_t)T.I * 4, cudaMemcpyHostToDevice, s->st));
+    if (T.Pp) { if ((rc = dev_alloc(&st_xu, (size_t)T.U * T.P))) return rc; CU(cudaMemcpyAsync(st_xu, x_uf, (size_t)T.U * T.P * 4, cudaMemcpyHostToDevice, s->st)); }
+    if (T.Qp) { if ((rc = dev_alloc(&st_xi, (size_t)T.I * T.Q))) return rc; CU(cudaMemcpyAsync(st_xi, x_if, (size_t)T.I * T.Q * 4, cudaMemcpyHostToDevice, s->st)); }
+    (void)features_too;
+    CU(launch_pack_users(T, st_vu, st_xu, s->st));
+    CU(launch_pack_items(T, st_vi, st_wi, st_xi, s->st));
+    s->launches += 2;
+    // globals
+    const size_t n_wif = (size_t)T.Q, n_vuf = (size_t)T.P * T.F, n_vif = (size_t)T.Q * T.F;
+    if ((rc = dev_alloc(&st_g, n_wif + n_vuf + n_vif))) return rc;
+    CU(cudaMemcpyAsync(st_g, w_if, n_wif * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(st_g + n_wif, v_uf, n_vuf * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(st_g + n_wif + n_vuf, v_if, n_vif * 4, cudaMemcpyHostToDevice, s->st));
+    CU(launch_pack_globals(T, st_g, st_g + n_wif, st_g + n_wif + n_vuf, (int)s->gp_floats, s->st));
+    s->launches += 1;
+    CU(cudaStreamSynchronize(s->st));
+    cudaFree(st_vu); cudaFree(st_vi); cudaFree(st_wi); cudaFree(st_xu); cudaFree(st_xi); cudaFree(st_g);
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_destroy(rfm_session* s)
+{
+    if (!s) return RFM_OK;
+    cudaSetDevice(s->device);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    for (auto e : s->ev) cudaEventDestroy(e);
+    cudaFree(s->T.UT); cudaFree(s->T.IT); cudaFree(s->T.GP);
+    cudaFree(s->d_inter); cudaFree(s->d_sw); cudaFree(s->d_indptr); cudaFree(s->d_indices);
+    cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
+    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush);
+    cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp);
+    if (s->t0) cudaEventDestroy(s->t0);
+    if (s->t1) cudaEventDestroy(s->t1);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
+{
+    if (!p || !out) return fail(RFM_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (p->U <= 0 || p->I <= 0 || p->F <= 0 || p->P <= 0 || p->Q <= 0) return fail(RFM_ERR_ARG, "U, I, P, Q, F must be positive");
+    if (!p->w_i || !p->w_if || !p->v_u || !p->v_i || !p->v_uf || !p->v_if || !p->x_uf || !p->x_if) return fail(RFM_ERR_ARG, "weight / feature pointer is NULL");
+    if (p->n_interactions < 0) return fail(RFM_ERR_ARG, "n_interactions < 0");
+    if (p->n_interactions > 0 && (!p->interactions || !p->sample_weight || !p->csr_indptr || !p->csr_indices))
+        return fail(RFM_ERR_ARG, "interaction data pointer is NULL");
+    if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return fail(RFM_ERR_ARG, "bad rank/world %d/%d", p->rank, p->world);
+    if (p->sampler == RFM_SAMPLER_MT && p->sched != RFM_SCHED_SERIAL) return fail(RFM_ERR_ARG, "the MT19937 sampler needs the serial schedule");
+    if (p->max_samples < 1) return fail(RFM_ERR_ARG, "max_samples must be >= 1");
+    const int ndev = rfm_device_count();
+    if (ndev == 0) return fail(RFM_ERR_NO_DEVICE, "no CUDA device: rankfm_b200 has no CPU fallback");
+    if (p->device < 0 || p->device >= ndev) return fail(RFM_ERR_ARG, "device %d out of range (%d devices)", p->device, ndev);
+
+    rfm_session* s = new rfm_session();
+    s->p = *p;
+    s->device = p->device;
+    int rc = RFM_OK;
+    auto bail = [&](int code) { rfm_session_destroy(s); return code; };
+#define TRY(x) do { rc = (x); if (rc) return bail(rc); } while (0)
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(RFM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+    CUB(cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    CUB(cudaGetDeviceProperties(&prop, s->device));
+    s->n_sm = prop.multiProcessorCount;
+    CUB(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+
+    Tables& T = s->T;
+    T.U = p->U; T.I = p->I; T.F = p->F; T.P = p->P; T.Q = p->Q;
+    T.x_uf_any = any_nonzero(p->x_uf, (size_t)p->U * p->P) ? 1 : 0;     // _rankfm.pyx:193-194
+    T.x_if_any = any_nonzero(p->x_if, (size_t)p->I * p->Q) ? 1 : 0;
+    T.Fp = (int)round4(p->F); T.NQ = T.Fp / 4;
+    T.Pp = T.x_uf_any ? (int)round4(p->P) : 0;
+    T.Qp = T.x_if_any ? (int)round4(p->Q) : 0;
+    T.ldu = T.Fp + T.Pp;
+    T.ldi = T.Fp + 4 + T.Qp;
+    const size_t wif_p = round4(p->Q);
+    T.gp_vuf = (int)wif_p;
+    T.gp_vif = T.gp_vuf + p->P * T.Fp;
+    s->gp_floats = (size_t)T.gp_vif + (size_t)p->Q * T.Fp;
+    {
+        int qpl = 1;
+        const int G = train_group_size(T, &qpl);
+        if (std::max(T.Pp, T.Qp) > 4 * G || qpl > 4)
+            return bail(fail(RFM_ERR_UNSUPPORTED, "unsupported shape: factors=%d (max 512), active user/item features %d/%d (max 128)", p->F, T.Pp ? p->P : 0, T.Qp ? p->Q : 0));
+    }
+    TRY(dev_alloc(&T.UT, (size_t)T.U * T.ldu));
+    TRY(dev_alloc(&T.IT, (size_t)T.I * T.ldi));
+    TRY(dev_alloc(&T.GP, s->gp_floats));
+    TRY(upload_weights(s, p->w_i, p->w_if, p->v_u, p->v_i, p->v_uf, p->v_if, p->x_uf, p->x_if, true));
+
+    s->N = p->n_interactions;
+    if (s->N > 0) {
+        s->nnz = p->csr_indptr[p->U];
+        TRY(dev_alloc(&s->d_inter, (size_t)s->N));
+        TRY(dev_alloc(&s->d_sw, (size_t)s->N));
+        TRY(dev_alloc(&s->d_indptr, (size_t)p->U + 1));
+        TRY(dev_alloc(&s->d_indices, (size_t)s->nnz));
+        CUB(cudaMemcpyAsync(s->d_inter, p->interactions, (size_t)s->N * 8, cudaMemcpyHostToDevice, s->st));
+        CUB(cudaMemcpyAsync(s->d_sw, p->sample_weight, (size_t)s->N * 4, cudaMemcpyHostToDevice, s->st));
+        CUB(cudaMemcpyAsync(s->d_indptr, p->csr_indptr, ((size_t)p->U + 1) * 8, cudaMemcpyHostToDevice, s->st));
+        CUB(cudaMemcpyAsync(s->d_indices, p->csr_indices, (size_t)s->nnz * 4, cudaMemcpyHostToDevice, s->st));
+        // WARP multiplier by number of draws: log((I-1)//sampled)/log(I)  (_rankfm.pyx:269, integer quotient)
+        std::vector<float> mult((size_t)p->max_samples + 1, 0.f);
+        for (int k = 1; k <= p->max_samples; ++k)
+            mult[k] = (float)(std::log((double)((long)(p->I - 1) / (long)k)) / std::log((double)p->I));
+        TRY(dev_alloc(&s->d_mult, mult.size()));
+        CUB(cudaMemcpyAsync(s->d_mult, mult.data(), mult.size() * 4, cudaMemcpyHostToDevice, s->st));
+        if (p->sampler == RFM_SAMPLER_MT) {
+            // seed on the host exactly like init_genrand (mt19937ar.c:60-73), pos = N -> first draw twists
+            MtState h;
+            uint32_t prev = p->mt_seed;
+            h.s[0] = prev;
+            for (int k = 1; k < kMtN; ++k) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)k; h.s[k] = prev; }
+            h.pos = kMtN;
+            TRY(dev_alloc(&s->d_mt, 1));
+            CUB(cudaMemcpyAsync(s->d_mt, &h, sizeof h, cudaMemcpyHostToDevice, s->st));
+        }
+        if (p->order == RFM_ORDER_HOST) TRY(dev_alloc(&s->d_perm, (size_t)s->N));
+        CUB(cudaStreamSynchronize(s->st));
+    }
+    {
+        TrainParams tp{};
+        tp.T = T;
+        const int per_sm = std::max(1, sgd_epoch_blocks_per_sm(tp));
+        s->grid = s->n_sm * per_sm;
+    }
+    if (p->world > 1) {
+        TRY(nccl_load());
+        if (!p->nccl_id) return bail(fail(RFM_ERR_ARG, "world>1 needs nccl_id"));
+        Id128 id;
+        memcpy(id.b, p->nccl_id, 128);
+        int r = g_nccl.CommInitRank(&s->comm, p->world, id, p->rank);
+        if (r != 0) return bail(fail(RFM_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+        TRY(dev_alloc(&s->d_it_snap, (size_t)T.I * T.ldi));
+        TRY(dev_alloc(&s->d_gp_snap, s->gp_floats));
+        TRY(dev_alloc(&s->d_ut_init, (size_t)T.U * T.ldu));
+        CUB(cudaMemcpyAsync(s->d_ut_init, T.UT, (size_t)T.U * T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
+        CUB(cudaStreamSynchronize(s->st));
+    }
+#undef TRY
+#undef CUB
+    *out = s;
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_set_weights(rfm_session* s, const float* w_i, const float* w_if, const float* v_u, const float* v_i,
+                                       const float* v_uf, const float* v_if)
+{
+    if (!s) return fail(RFM_ERR_ARG, "NULL session");
+    CU(cudaSetDevice(s->device));
+    // feature blocks of the fat rows are rewritten from the staging copy of x_uf / x_if kept by the caller
+    if (s->T.Pp || s->T.Qp) {
+        if (!s->p.x_uf || !s->p.x_if) return fail(RFM_ERR_ARG, "set_weights with features needs the original x_uf/x_if pointers to be alive");
+    }
+    int rc = upload_weights(s, w_i, w_if, v_u, v_i, v_uf, v_if, s->p.x_uf, s->p.x_if, false);
+    if (rc) return rc;
+    if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->T.UT, (size_t)s->T.U * s->T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
+    s->epochs_done = 0;
+    if (s->d_mt) {
+        MtState h;
+        uint32_t prev = s->p.mt_seed;
+        h.s[0] = prev;
+        for (int k = 1; k < kMtN; ++k) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)k; h.s[k] = prev; }
+        h.pos = kMtN;
+        CU(cudaMemcpyAsync(s->d_mt, &h, sizeof h, cudaMemcpyHostToDevice, s->st));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_snapshot(rfm_session* s)
+{
+    if (!s) return fail(RFM_ERR_ARG, "NULL session");
+    CU(cudaSetDevice(s->device));
+    const size_t nu = (size_t)s->T.U * s->T.ldu, ni = (size_t)s->T.I * s->T.ldi;
+    int rc;
+    if (!s->d_snap_ut) {
+        if ((rc = dev_alloc(&s->d_snap_ut, nu))) return rc;
+        if ((rc = dev_alloc(&s->d_snap_it, ni))) return rc;
+        if ((rc = dev_alloc(&s->d_snap_gp, s->gp_floats))) return rc;
+    }
+    CU(cudaMemcpyAsync(s->d_snap_ut, s->T.UT, nu * 4, cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_snap_it, s->T.IT, ni * 4, cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_snap_gp, s->T.GP, s->gp_floats * 4, cudaMemcpyDeviceToDevice, s->st));
+    s->snap_epochs = s->epochs_done;
+    CU(cudaStreamSynchronize(s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_restore(rfm_session* s)
+{
+    if (!s || !s->d_snap_ut) return fail(RFM_ERR_ARG, "no snapshot to restore");
+    CU(cudaSetDevice(s->device));
+    const size_t nu = (size_t)s->T.U * s->T.ldu, ni = (size_t)s->T.I * s->T.ldi;
+    CU(cudaMemcpyAsync(s->T.UT, s->d_snap_ut, nu * 4, cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaMemcpyAsync(s->T.IT, s->d_snap_it, ni * 4, cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaMemcpyAsync(s->T.GP, s->d_snap_gp, s->gp_floats * 4, cudaMemcpyDeviceToDevice, s->st));
+    if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->d_snap_ut, nu * 4, cudaMemcpyDeviceToDevice, s->st));
+    s->epochs_done = s->snap_epochs;
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_timer_start(rfm_session* s)
+{
+    if (!s) return fail(RFM_ERR_ARG, "NULL session");
+    CU(cudaSetDevice(s->device));
+    if (!s->t0) { CU(cudaEventCreate(&s->t0)); CU(cudaEventCreate(&s->t1)); }
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaEventRecord(s->t0, s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_timer_stop(rfm_session* s, float* ms_out)
+{
+    if (!s || !ms_out || !s->t0) return fail(RFM_ERR_ARG, "timer not started");
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventRecord(s->t1, s->st));
+    CU(cudaEventSynchronize(s->t1));
+    CU(cudaEventElapsedTime(ms_out, s->t0, s->t1));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_download(rfm_session* s, float* w_i, float* w_if, float* v_u, float* v_i, float* v_uf, float* v_if)
+{
+    if (!s) return fail(RFM_ERR_ARG, "NULL session");
+    CU(cudaSetDevice(s->device));
+    const Tables& T = s->T;
+    float *st_vu = nullptr, *st_vi = nullptr, *st_wi = nullptr, *st_g = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&st_vu, (size_t)T.U * T.F))) return rc;
+    if ((rc = dev_alloc(&st_vi, (size_t)T.I * T.F))) return rc;
+    if ((rc = dev_alloc(&st_wi, (size_t)T.I))) return rc;
+    const size_t n_wif = (size_t)T.Q, n_vuf = (size_t)T.P * T.F, n_vif = (size_t)T.Q * T.F;
+    if ((rc = dev_alloc(&st_g, n_wif + n_vuf + n_vif))) return rc;
+    CU(launch_unpack_users(T, st_vu, s->st));
+    CU(launch_unpack_items(T, st_vi, st_wi, s->st));
+    CU(launch_unpack_globals(T, st_g, st_g + n_wif, st_g + n_wif + n_vuf, s->st));
+    s->launches += 3;
+    CU(cudaMemcpyAsync(v_u, st_vu, (size_t)T.U * T.F * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(v_i, st_vi, (size_t)T.I * T.F * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(w_i, st_wi, (size_t)T.I * 4, cudaMemcpyDeviceToHost, s->st));
+    if (T.x_if_any) CU(cudaMemcpyAsync(w_if, st_g, n_wif * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(v_uf, st_g + n_wif, n_vuf * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(v_if, st_g + n_wif + n_vuf, n_vif * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    cudaFree(st_vu); cudaFree(st_vi); cudaFree(st_wi); cudaFree(st_g);
+    return RFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi-GPU: replicated item table / globals, per-epoch sum of deltas (see DESIGN.md, section multi-GPU)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void delta_kernel(float* __restrict__ cur, const float* __restrict__ snap, size_t n)     // cur <- cur - snap
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) cur[e] -= snap[e];
+}
+__global__ void apply_kernel(float* __restrict__ cur, float* __restrict__ snap, size_t n)           // cur <- snap + cur ; snap <- cur
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const float v = snap[e] + cur[e];
+        cur[e] = v; snap[e] = v;
+    }
+}
+
+static int exchange_deltas(rfm_session* s, float* cur, float* snap, size_t n)
+{
+    const int grid = s->n_sm * 4;
+    delta_kernel<<<grid, 256, 0, s->st>>>(cur, snap, n);
+    NC(g_nccl.AllReduce(cur, cur, n, kNcclFloat, kNcclSum, s->comm, s->st));
+    apply_kernel<<<grid, 256, 0, s->st>>>(cur, snap, n);
+    s->launches += 2;
+    CU(cudaGetLastError());
+    return RFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// training
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* perms, rfm_epoch_stats* stats)
+{
+    if (!s) return fail(RFM_ERR_ARG, "NULL session");
+    if (epochs < 1) return fail(RFM_ERR_ARG, "epochs must be >= 1");
+    if (s->N <= 0) return fail(RFM_ERR_ARG, "session holds no interactions");
+    const rfm_problem& p = s->p;
+    if (p.order == RFM_ORDER_HOST && !perms) return fail(RFM_ERR_ARG, "order=HOST needs perms [epochs,N]");
+    if (p.schedule != RFM_SCHEDULE_CONSTANT && p.schedule != RFM_SCHEDULE_INVSCALING) return fail(RFM_ERR_ARG, "unknown [learning_schedule]");
+    CU(cudaSetDevice(s->device));
+    if (s->acc_cap < epochs) {
+        cudaFree(s->d_acc);
+        int rc = dev_alloc(&s->d_acc, (size_t)epochs);
+        if (rc) return rc;
+        s->acc_cap = epochs;
+    }
+    CU(cudaMemsetAsync(s->d_acc, 0, (size_t)epochs * sizeof(EpochAcc), s->st));
+    while ((int)s->ev.size() < 4 * epochs) { cudaEvent_t e; CU(cudaEventCreate(&e)); s->ev.push_back(e); }
+    if (s->comm) {
+        CU(cudaMemcpyAsync(s->d_it_snap, s->T.IT, (size_t)s->T.I * s->T.ldi * 4, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaMemcpyAsync(s->d_gp_snap, s->T.GP, s->gp_floats * 4, cudaMemcpyDeviceToDevice, s->st));
+    }
+
+    TrainParams tp{};
+    tp.T = s->T;
+    tp.interactions = s->d_inter; tp.sample_weight = s->d_sw; tp.indptr = s->d_indptr; tp.indices = s->d_indices;
+    tp.mult = s->d_mult;
+    tp.N = s->N;
+    tp.reg_a = (float)(2.0 * p.alpha);                      // d_reg_a / d_reg_b, _rankfm.pyx:171-172
+    tp.reg_b = (float)(2.0 * p.beta);
+    tp.max_samples = p.max_samples;
+    tp.max_rejects = p.max_rejects > 0 ? p.max_rejects : (p.sampler == RFM_SAMPLER_MT ? 0x7fffffff : 64);
+    tp.serial = p.sched == RFM_SCHED_SERIAL ? 1 : 0;
+    tp.k0 = (uint32_t)p.seed; tp.k1 = (uint32_t)(p.seed >> 32);
+    tp.mt = p.sampler == RFM_SAMPLER_MT ? s->d_mt : nullptr;
+    std::vector<float> etas((size_t)epochs);
+
+    for (int e = 0; e < epochs; ++e) {
+        const int epoch = s->epochs_done + e;               // LR schedule restarts per call, like the reference's per-_fit epoch counter
+        (void)epoch;
+        float eta = p.learning_rate;                        // _rankfm.pyx:220-223
+        if (p.schedule == RFM_SCHEDULE_INVSCALING) eta = (float)(((double)p.learning_rate) / std::pow((double)(e + 1), (double)p.learning_exponent));
+        etas[e] = eta;
+        tp.eta = eta;
+        tp.epoch_key = (uint32_t)(s->epochs_done + e);
+        tp.acc = s->d_acc + e;
+        if (p.order == RFM_ORDER_HOST) {
+            CU(cudaMemcpyAsync(s->d_perm, perms + (size_t)e * s->N, (size_t)s->N * 4, cudaMemcpyHostToDevice, s->st));
+            tp.perm = s->d_perm;
+        } else {
+            tp.perm = nullptr;
+            tp.feistel = make_feistel(s->N, p.seed, s->epochs_done + e);
+        }
+        CU(cudaEventRecord(s->ev[4 * e + 0], s->st));
+        cudaError_t le = launch_sgd_epoch(tp, s->grid, s->st);
+        if (le != cudaSuccess) return fail(RFM_ERR_CUDA, "sgd_epoch launch failed: %s", cudaGetErrorString(le));
+        CU(cudaEventRecord(s->ev[4 * e + 1], s->st));
+        s->launches += 1;
+        CU(cudaEventRecord(s->ev[4 * e + 2], s->st));
+        if (s->comm) {
+            int rc = exchange_deltas(s, s->T.IT, s->d_it_snap, (size_t)s->T.I * s->T.ldi);
+            if (rc) return rc;
+            if (s->T.x_uf_any || s->T.x_if_any) { rc = exchange_deltas(s, s->T.GP, s->d_gp_snap, s->gp_floats); if (rc) return rc; }
+        }
+        CU(cudaEventRecord(s->ev[4 * e + 3], s->st));
+        CU(launch_weight_stats(s->T, (s->d_acc + e)->wstats, s->n_sm * 2, s->st));
+        s->launches += 1;
+    }
+    s->epochs_done += epochs;
+    if (s->comm) {
+        // user rows are owned by exactly one rank: the sum over ranks of (UT - UT_at_start) restores the full table
+        const size_t n = (size_t)s->T.U * s->T.ldu;
+        int rc = exchange_deltas(s, s->T.UT, s->d_ut_init, n);
+        if (rc) return rc;
+    }
+    std::vector<EpochAcc> acc((size_t)epochs);
+    CU(cudaMemcpyAsync(acc.data(), s->d_acc, (size_t)epochs * sizeof(EpochAcc), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    int status = RFM_OK;
+    for (int e = 0; e < epochs; ++e) {
+        const EpochAcc& a = acc[e];
+        rfm_epoch_stats st{};
+        st.log_likelihood = a.ll;
+        st.draws = a.draws;
+        st.eta = etas[e];
+        st.penalty = (double)p.alpha * (a.wstats[6 + 0] + a.wstats[6 + 2] + a.wstats[6 + 3]) + (double)p.beta * (a.wstats[6 + 1] + a.wstats[6 + 4] + a.wstats[6 + 5]);
+        for (int k = 0; k < 6; ++k) st.finite[k] = std::isfinite(a.wstats[k]) ? 1 : 0;
+        cudaEventElapsedTime(&st.kernel_ms, s->ev[4 * e + 0], s->ev[4 * e + 1]);
+        cudaEventElapsedTime(&st.sync_ms, s->ev[4 * e + 2], s->ev[4 * e + 3]);
+        if (stats) stats[e] = st;
+        if (status == RFM_OK) {
+            static const char* names[6] = {"item weights [w_i]", "item feature weights [w_if]", "user factors [v_u]", "item factors [v_i]",
+                                           "user-feature factors [v_uf]", "item-feature factors [v_if]"};
+            for (int k = 0; k < 6; ++k)
+                if (!st.finite[k]) { status = fail(RFM_ERR_NONFINITE, "%s are not finite - try decreasing feature/sample_weight magnitudes", names[k]); break; }
+            if (status == RFM_OK && a.bad) status = fail(RFM_ERR_NONFINITE, "pairwise utilities are not finite - try decreasing feature/sample_weight magnitudes");
+        }
+    }
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------------------------
+static int predict_dev(rfm_session* s, const float2* d_pairs, int64_t n, float* d_scores)
+{
+    cudaError_t e = launch_predict(s->T, d_pairs, n, d_scores, s->n_sm * 8, s->st);
+    if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "predict launch failed: %s", cudaGetErrorString(e));
+    s->launches += 1;
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_predict(rfm_session* s, const float* pairs, int64_t n, float* scores)
+{
+    if (!s || (n > 0 && (!pairs || !scores))) return fail(RFM_ERR_ARG, "NULL argument");
+    if (n == 0) return RFM_OK;
+    CU(cudaSetDevice(s->device));
+    float2* d_pairs = nullptr; float* d_scores = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_pairs, (size_t)n))) return rc;
+    if ((rc = dev_alloc(&d_scores, (size_t)n))) return rc;
+    CU(cudaMemcpyAsync(d_pairs, pairs, (size_t)n * 8, cudaMemcpyHostToDevice, s->st));
+    if ((rc = predict_dev(s, d_pairs, n, d_scores))) return rc;
+    CU(cudaMemcpyAsync(scores, d_scores, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    cudaFree(d_pairs); cudaFree(d_scores);
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_time_predict(rfm_session* s, const float* pairs, int64_t n, int32_t iters, float* ms_out)
+{
+    if (!s || !pairs || !ms_out || n <= 0 || iters < 1) return fail(RFM_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    float2* d_pairs = nullptr; float* d_scores = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_pairs, (size_t)n))) return rc;
+    if ((rc = dev_alloc(&d_scores, (size_t)n))) return rc;
+    CU(cudaMemcpyAsync(d_pairs, pairs, (size_t)n * 8, cudaMemcpyHostToDevice, s->st));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    if ((rc = predict_dev(s, d_pairs, n, d_scores))) return rc;      // warm-up
+    CU(cudaEventRecord(a, s->st));
+    for (int k = 0; k < iters; ++k) if ((rc = predict_dev(s, d_pairs, n, d_scores))) return rc;
+    CU(cudaEventRecord(b, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms / iters;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d_pairs); cudaFree(d_scores);
+    return RFM_OK;
+}
+
+// users as float32 indexes (NaN = unknown) -> int32 (-1 = unknown)
+static void users_to_int(const float* users, int64_t n, std::vector<int32_t>& out)
+{
+    out.resize((size_t)n);
+    for (int64_t k = 0; k < n; ++k) out[(size_t)k] = std::isnan(users[k]) ? -1 : (int32_t)users[k];
+}
+
+static int recommend_dev(rfm_session* s, const int32_t* d_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
+                         float* d_rec, float* gemm_ms)
+{
+    const Tables& T = s->T;
+    // batch users so the score matrix stays under ~8 GB
+    const int64_t max_batch = std::max<int64_t>(1, std::min<int64_t>(n_users, ((int64_t)2 << 30) / std::max(1, T.I)));
+    float* S = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&S, (size_t)max_batch * T.I))) return rc;
+    const int chunks = std::max(1, std::min(64, (T.I + 2047) / 2048));
+    cudaEvent_t a = nullptr, b = nullptr;
+    float acc_ms = 0.f;
+    if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
+    for (int64_t off = 0; off < n_users; off += max_batch) {
+        const int nb = (int)std::min<int64_t>(max_batch, n_users - off);
+        if (gemm_ms) CU(cudaEventRecord(a, s->st));
+        for (int y0 = 0; y0 < nb; y0 += 32768) {   // gridDim.y limit is 65535
+            const int ny = std::min(32768, nb - y0);
+            cudaError_t e = launch_score_users(T, d_users + off + y0, ny, S + (size_t)y0 * T.I, chunks, s->st);
+            if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_users launch failed: %s", cudaGetErrorString(e));
+            s->launches += 1;
+        }
+        if (gemm_ms) { CU(cudaEventRecord(b, s->st)); }
+        cudaError_t e = launch_topn_select(S, T.I, d_users + off, nb, s->d_indptr, s->d_indices, filter_previous, n_items,
+                                           d_rec + (size_t)off * n_items, nullptr, s->st);
+        if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "topn_select launch failed: %s", cudaGetErrorString(e));
+        s->launches += 1;
+        if (gemm_ms) { CU(cudaStreamSynchronize(s->st)); float ms = 0.f; cudaEventElapsedTime(&ms, a, b); acc_ms += ms; }
+    }
+    CU(cudaStreamSynchronize(s->st));
+    if (gemm_ms) { *gemm_ms = acc_ms; cudaEventDestroy(a); cudaEventDestroy(b); }
+    cudaFree(S);
+    return RFM_OK;
+}
+
+static int recommend_checks(rfm_session* s, int64_t n_users, int32_t n_items, int32_t filter_previous)
+{
+    if (n_items < 1) return fail(RFM_ERR_ARG, "n_items must be >= 1");
+    if (n_items > 16384) return fail(RFM_ERR_UNSUPPORTED, "n_items > 16384 is not supported");
+    if (filter_previous && !s->d_indptr) return fail(RFM_ERR_ARG, "filter_previous needs a session created with user_items (CSR)");
+    (void)n_users;
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t n_users, int32_t n_items, int32_t filter_previous, float* rec_items)
+{
+    if (!s || (n_users > 0 && (!users || !rec_items))) return fail(RFM_ERR_ARG, "NULL argument");
+    if (n_users == 0) return RFM_OK;
+    int rc = recommend_checks(s, n_users, n_items, filter_previous);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    std::vector<int32_t> hu;
+    users_to_int(users, n_users, hu);
+    for (auto u : hu) if (u >= s->T.U) return fail(RFM_ERR_ARG, "user index %d out of range", u);
+    int32_t* d_users = nullptr; float* d_rec = nullptr;
+    if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
+    if ((rc = dev_alloc(&d_rec, (size_t)n_users * n_items))) return rc;
+    CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
+    if ((rc = recommend_dev(s, d_users, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
+    CU(cudaMemcpyAsync(rec_items, d_rec, (size_t)n_users * n_items * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    cudaFree(d_users); cudaFree(d_rec);
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, int64_t n_users, int32_t n_items, int32_t filter_previous,
+                                          int32_t iters, float* ms_out, float* gemm_ms_out)
+{
+    if (!s || !users || !ms_out || n_users <= 0 || iters < 1) return fail(RFM_ERR_ARG, "bad argument");
+    int rc = recommend_checks(s, n_users, n_items, filter_previous);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    std::vector<int32_t> hu;
+    users_to_int(users, n_users, hu);
+    int32_t* d_users = nullptr; float* d_rec = nullptr;
+    if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
+    if ((rc = dev_alloc(&d_rec, (size_t)n_users * n_items))) return rc;
+    CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
+    if ((rc = recommend_dev(s, d_users, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;   // warm-up
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    float gemm_total = 0.f;
+    CU(cudaEventRecord(a, s->st));
+    for (int k = 0; k < iters; ++k) {
+        float g = 0.f;
+        if ((rc = recommend_dev(s, d_users, n_users, n_items, filter_previous, d_rec, gemm_ms_out ? &g : nullptr))) return rc;
+        gemm_total += g;
+    }
+    CU(cudaEventRecord(b, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms / iters;
+    if (gemm_ms_out) *gemm_ms_out = gemm_total / iters;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d_users); cudaFree(d_rec);
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_flush_l2(rfm_session* s)
+{
+    if (!s) return fail(RFM_ERR_ARG, "NULL session");
+    CU(cudaSetDevice(s->device));
+    if (!s->d_flush) {
+        s->flush_bytes = (size_t)512 << 20;   // 4x the 126 MB L2
+        CU(cudaMalloc((void**)&s->d_flush, s->flush_bytes));
+    }
+    CU(cudaMemsetAsync(s->d_flush, 0x5a, s->flush_bytes, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_launch_count(rfm_session* s, int64_t* launches)
+{
+    if (!s || !launches) return fail(RFM_ERR_ARG, "NULL argument");
+    *launches = s->launches;
+    return RFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one-shot entry points on host buffers
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int rfm_fit(const rfm_problem* p, int32_t epochs, const int32_t* perms, rfm_epoch_stats* stats)
+{
+    rfm_session* s = nullptr;
+    int rc = rfm_session_create(p, &s);
+    if (rc) return rc;
+    rc = rfm_session_train(s, epochs, perms, stats);
+    // like the reference, weights are written back even when they went non-finite (_rankfm.pyx:329 raises after mutation)
+    if (rc == RFM_OK || rc == RFM_ERR_NONFINITE) {
+        const std::string keep = g_err;
+        int rc2 = rfm_session_download(s, p->w_i, p->w_if, p->v_u, p->v_i, p->v_uf, p->v_if);
+        if (rc2) rc = rc2; else g_err = keep;
+    }
+    rfm_session_destroy(s);
+    return rc;
+}
+
+extern "C" int rfm_predict(const rfm_problem* p, const float* pairs, int64_t n, float* scores)
+{
+    rfm_problem q = *p;
+    q.n_interactions = 0;
+    rfm_session* s = nullptr;
+    int rc = rfm_session_create(&q, &s);
+    if (rc) return rc;
+    rc = rfm_session_predict(s, pairs, n, scores);
+    rfm_session_destroy(s);
+    return rc;
+}
+
+static int attach_csr(rfm_session* s, const rfm_problem* p)
+{
+    if (!p->csr_indptr || !p->csr_indices) return fail(RFM_ERR_ARG, "filter_previous needs csr_indptr / csr_indices");
+    const int64_t nnz = p->csr_indptr[p->U];
+    int rc;
+    if ((rc = dev_alloc(&s->d_indptr, (size_t)p->U + 1))) return rc;
+    if ((rc = dev_alloc(&s->d_indices, (size_t)nnz))) return rc;
+    CU(cudaMemcpyAsync(s->d_indptr, p->csr_indptr, ((size_t)p->U + 1) * 8, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_indices, p->csr_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_recommend(const rfm_problem* p, const float* users, int64_t n_users, int32_t n_items, int32_t filter_previous, float* rec_items)
+{
+    rfm_problem q = *p;
+    q.n_interactions = 0;
+    rfm_session* s = nullptr;
+    int rc = rfm_session_create(&q, &s);
+    if (rc) return rc;
+    if (filter_previous) rc = attach_csr(s, p);
+    if (!rc) rc = rfm_session_recommend(s, users, n_users, n_items, filter_previous, rec_items);
+    rfm_session_destroy(s);
+    return rc;
+}
+
+extern "C" int rfm_similar(const rfm_problem* p, int32_t which, int32_t index, int32_t n, int32_t* out)
+{
+    if (!p || !out) return fail(RFM_ERR_ARG, "NULL argument");
+    const int rows = which == 0 ? p->I : p->U;
+    if (which != 0 && which != 1) return fail(RFM_ERR_ARG, "which must be 0 (items) or 1 (users)");
+    if (index < 0 || index >= rows) return fail(RFM_ERR_ARG, "index out of range");
+    if (n < 1 || n > 16384) return fail(RFM_ERR_ARG, "n out of range");
+    rfm_problem q = *p;
+    q.n_interactions = 0;
+    rfm_session* s = nullptr;
+    int rc = rfm_session_create(&q, &s);
+    if (rc) return rc;
+    float *qvec = nullptr, *S = nullptr, *d_rec = nullptr;
+    int32_t *d_one = nullptr, *d_ex = nullptr;
+    auto done = [&](int code) { cudaFree(qvec); cudaFree(S); cudaFree(d_rec); cudaFree(d_one); cudaFree(d_ex); rfm_session_destroy(s); return code; };
+    if ((rc = dev_alloc(&qvec, (size_t)s->T.Fp))) return done(rc);
+    if ((rc = dev_alloc(&S, (size_t)rows))) return done(rc);
+    if ((rc = dev_alloc(&d_rec, (size_t)n))) return done(rc);
+    if ((rc = dev_alloc(&d_one, 1))) return done(rc);
+    if ((rc = dev_alloc(&d_ex, 1))) return done(rc);
+    const int32_t zero = 0;
+    cudaMemcpyAsync(d_one, &zero, 4, cudaMemcpyHostToDevice, s->st);
+    cudaMemcpyAsync(d_ex, &index, 4, cudaMemcpyHostToDevice, s->st);
+    cudaError_t e = launch_latent_scores(s->T, which, index, qvec, S, s->st);
+    if (e == cudaSuccess) e = launch_topn_select(S, rows, d_one, 1, nullptr, nullptr, 0, n, d_rec, d_ex, s->st);
+    if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "similar launch failed: %s", cudaGetErrorString(e)));
+    std::vector<float> rec((size_t)n);
+    cudaMemcpyAsync(rec.data(), d_rec, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st);
+    e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "similar failed: %s", cudaGetErrorString(e)));
+    for (int k = 0; k < n; ++k) out[k] = std::isnan(rec[(size_t)k]) ? -1 : (int32_t)rec[(size_t)k];
+    return done(RFM_OK);
+}

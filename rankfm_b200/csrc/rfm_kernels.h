@@ -1,0 +1,58 @@
+// rfm_kernels.h -- host-visible declarations of the kernel launchers (internal; the public ABI is include/rankfm_b200.h)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "rfm_common.cuh"
+#include "rfm_rng.cuh"
+
+namespace rfm {
+
+constexpr int kTrainThreads = 256;
+
+struct EpochAcc {            // zeroed before each epoch, read back after
+    double ll;
+    long long draws;
+    int bad;
+    int pad;
+    double wstats[12];       // weight_stats_kernel output
+};
+
+struct TrainParams {
+    Tables T;
+    const int2* interactions;
+    const float* sample_weight;
+    const int64_t* indptr;
+    const int32_t* indices;
+    const int32_t* perm;     // this epoch's order, or nullptr -> Feistel
+    const float* mult;       // [max_samples+1]  WARP multiplier by number of draws
+    Feistel feistel;
+    long long N;
+    float eta, reg_a, reg_b;
+    int32_t max_samples, max_rejects, serial;
+    uint32_t k0, k1, epoch_key;
+    MtState* mt;             // non-null -> MT19937 sampler (serial only)
+    EpochAcc* acc;
+};
+
+int train_group_size(const Tables& T, int* qpl_out);
+cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st);
+cudaError_t launch_weight_stats(const Tables& T, double* out12, int grid, cudaStream_t st);
+
+// scoring (rfm_score.cu)
+cudaError_t launch_predict(const Tables& T, const float2* pairs, long long n, float* scores, int grid, cudaStream_t st);
+
+cudaError_t launch_score_users(const Tables& T, const int32_t* users, int n_users, float* S, int chunks, cudaStream_t st);
+cudaError_t launch_topn_select(float* S, int I, const int32_t* users, int n_users, const int64_t* indptr, const int32_t* indices,
+                               int filter_previous, int n_items, float* rec, const int32_t* exclude, cudaStream_t st);
+cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);
+int sgd_epoch_blocks_per_sm(const TrainParams& p);
+
+// packing between the reference's array layout and the fat-row tables (rfm_pack.cu)
+cudaError_t launch_pack_users(const Tables& T, const float* v_u, const float* x_uf, cudaStream_t st);
+cudaError_t launch_pack_items(const Tables& T, const float* v_i, const float* w_i, const float* x_if, cudaStream_t st);
+cudaError_t launch_unpack_users(const Tables& T, float* v_u, cudaStream_t st);
+cudaError_t launch_unpack_items(const Tables& T, float* v_i, float* w_i, cudaStream_t st);
+cudaError_t launch_pack_globals(const Tables& T, const float* w_if, const float* v_uf, const float* v_if, int n_total, cudaStream_t st);
+cudaError_t launch_unpack_globals(const Tables& T, float* w_if, float* v_uf, float* v_if, cudaStream_t st);
+
+}  // namespace rfm

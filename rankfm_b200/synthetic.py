@@ -1,0 +1,62 @@
+"""Synthetic workloads of the shapes BASELINE.json names (no datasets are reachable offline).
+
+(user, item) pairs with Zipf-distributed popularity on both sides, de-duplicated, ids permuted so popularity is not
+index-ordered, then re-indexed to the observed uniques like ``rankfm.py:115-116``.
+"""
+import numpy as np
+
+CONFIGS = {
+    # name: U, I, N, factors, loss, max_samples, epochs, P, Q
+    "cfg1": dict(U=10_000, I=5_000, N=100_000, F=16, loss="bpr", max_samples=1, epochs=5, P=0, Q=0,
+                 label="synthetic 10k users x 5k items, 100k interactions, factors=16, bpr, 5 epochs"),
+    "cfg2": dict(U=6_040, I=3_706, N=1_000_000, F=20, loss="warp", max_samples=20, epochs=20, P=0, Q=0,
+                 label="MovieLens-1M shape synthetic (6040x3706, 1M interactions), factors=20, warp, max_samples=20, 20 epochs"),
+    "cfg3": dict(U=1_000_000, I=200_000, N=50_000_000, F=64, loss="warp", max_samples=10, epochs=2, P=8, Q=8,
+                 label="1M users x 200k items, 50M Zipf interactions, factors=64, warp, 8+8 side features"),
+    "cfg4s": dict(U=1_250_000, I=1_000_000, N=62_500_000, F=128, loss="bpr", max_samples=1, epochs=2, P=0, Q=0,
+                  label="per-GPU shard of 10M users x 1M items, 500M interactions, factors=128, bpr (1/8 of cfg4)"),
+}
+
+
+def zipf_interactions(U, I, N, seed=42, a_u=0.6, a_i=1.0, oversample=1.0, offset_users=0):
+    """int32 [n,2] unique (user,item) pairs, n ~= N (exactly N when enough unique pairs were drawn)"""
+    rng = np.random.default_rng(seed)
+    pu = 1.0 / np.arange(1, U + 1) ** a_u
+    pi = 1.0 / np.arange(1, I + 1) ** a_i
+    cu, ci = np.cumsum(pu / pu.sum()), np.cumsum(pi / pi.sum())
+    keys = np.zeros(0, dtype=np.int64)
+    want = N
+    draw = int(N * (1.15 + oversample * 0.5)) + 1024
+    for _ in range(8):
+        u = np.minimum(np.searchsorted(cu, rng.random(draw)), U - 1)
+        i = np.minimum(np.searchsorted(ci, rng.random(draw)), I - 1)
+        keys = np.unique(np.concatenate([keys, u.astype(np.int64) * I + i]))
+        if len(keys) >= want:
+            break
+    if len(keys) > want:
+        keys = rng.choice(keys, want, replace=False)
+    u, i = keys // I, keys % I
+    u = rng.permutation(U)[u]
+    i = rng.permutation(I)[i]
+    _, u = np.unique(u, return_inverse=True)
+    _, i = np.unique(i, return_inverse=True)
+    X = np.stack([u + offset_users, i], axis=1).astype(np.int32)
+    rng.shuffle(X)
+    return np.ascontiguousarray(X)
+
+
+def init_weights(U, I, F, P=0, Q=0, seed=0, sigma=0.1, alpha=0.01, beta=0.1):
+    """N(0, sigma) factors like ``rankfm.py:223-244`` (own generator instead of NumPy's global state)"""
+    rng = np.random.default_rng(seed)
+    scale = (alpha / beta) * sigma
+    return dict(w_i=np.zeros(I, np.float32), w_if=np.zeros(max(Q, 1), np.float32),
+                v_u=rng.normal(0, sigma, (U, F)).astype(np.float32), v_i=rng.normal(0, sigma, (I, F)).astype(np.float32),
+                v_uf=(rng.normal(0, scale, (P, F)) if P else np.zeros((1, F))).astype(np.float32),
+                v_if=(rng.normal(0, scale, (Q, F)) if Q else np.zeros((1, F))).astype(np.float32))
+
+
+def side_features(U, I, P, Q, seed=0):
+    rng = np.random.default_rng(seed + 1000)
+    x_uf = rng.random((U, P), dtype=np.float32) if P else np.zeros((U, 1), np.float32)
+    x_if = rng.random((I, Q), dtype=np.float32) if Q else np.zeros((I, 1), np.float32)
+    return x_uf, x_if

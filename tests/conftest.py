@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from rankfm_b200 import _lib
+    return _lib.lib()
+
+
+@pytest.fixture(scope="session")
+def gpu_lib(lib):
+    assert lib.rfm_device_count() > 0, "GPU test collected but no CUDA device is visible"
+    return lib

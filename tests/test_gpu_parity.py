@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA hot path (through the C ABI / ctypes shim) against the oracle and the golden vectors
+minted from the unmodified reference.  Tolerances are written next to each comparison.
+
+  * replay schedule (serial, MT19937 negatives, the reference's row order)  -> same trajectory as the reference:
+    trained weights and predict() scores within 1e-4 relative (BASELINE.json north_star tolerance)
+  * serial Philox/Feistel schedule -> same trajectory as the oracle run with the same Philox/Feistel contract
+  * parallel (Hogwild) schedule    -> statistical parity (log-likelihood, ranking quality, draws)
+"""
+import numpy as np
+import pytest
+
+from helpers import (KERNEL_CASES, WEIGHTS, CSRItems, csr_of, features, golden_fit_args, init_weights, load_golden,
+                     rel_err, topk_overlap, zipf_interactions)
+from oracle import oracle
+from rankfm_b200 import _lib, _rankfm
+
+pytestmark = pytest.mark.gpu
+
+PREDICT_RTOL = 1e-4      # north_star: predict() within 1e-4 relative of the reference for identical seeds/epochs
+
+
+def _weights(g, which):
+    return [np.ascontiguousarray(g[k + '_' + which]) for k in WEIGHTS]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training: exact-trajectory modes
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", KERNEL_CASES)
+def test_replay_fit_matches_reference_golden(gpu_lib, case):
+    g = load_golden(case)
+    args, w, _ = golden_fit_args(g)
+    stats = _rankfm.fit_ex(*args, g['epochs'], mode="replay", perms=g['perms'])
+    for k in WEIGHTS:
+        assert rel_err(w[k], g[k + '_ref']) < 1e-4, k
+    # the trained model scores like the reference's
+    scores = _rankfm._predict(np.ascontiguousarray(g['pairs']), g['x_uf'], g['x_if'], *[w[k] for k in WEIGHTS])
+    assert np.array_equal(np.isnan(scores), np.isnan(g['scores']))
+    assert rel_err(scores, g['scores']) < PREDICT_RTOL
+    # and consumed the reference's number of MT19937 draws (same `sampled` per positive)
+    args_o, _, _ = golden_fit_args(g)
+    out = oracle.fit_ex(*args_o, g['epochs'], perms=g['perms'], sampler="mt")
+    assert [s['draws'] for s in stats] == out['draws'].tolist()
+    np.testing.assert_allclose([s['log_likelihood'] for s in stats], out['ll'], rtol=2e-4)
+
+
+@pytest.mark.parametrize("case", KERNEL_CASES)
+def test_serial_philox_fit_matches_oracle(gpu_lib, case):
+    g = load_golden(case)
+    args, w, _ = golden_fit_args(g)
+    stats = _rankfm.fit_ex(*args, g['epochs'], seed=4242, order=_lib.ORDER_FEISTEL, sampler=_lib.SAMPLER_PHILOX,
+                           sched=_lib.SCHED_SERIAL, max_rejects=64)
+    args_o, wo, _ = golden_fit_args(g)
+    out = oracle.fit_ex(*args_o, g['epochs'], perms=None, sampler="philox", seed=4242, max_rejects=64)
+    for k in WEIGHTS:
+        assert rel_err(w[k], wo[k]) < 1e-4, k
+    assert [s['draws'] for s in stats] == out['draws'].tolist()
+
+
+def test_replay_is_deterministic(gpu_lib):
+    g = load_golden('warp_f20')
+    runs = []
+    for _ in range(2):
+        args, w, _ = golden_fit_args(g)
+        _rankfm.fit_ex(*args, 2, mode="replay", perms=g['perms'][:2])
+        runs.append(w)
+    for k in WEIGHTS:
+        assert np.array_equal(runs[0][k], runs[1][k])
+
+
+def test_fit_partial_continues_the_mt_stream_from_1492(gpu_lib):
+    """the reference re-seeds MT19937 at every `_fit` call (_rankfm.pyx:182): two 1-epoch calls == the oracle's two calls"""
+    g = load_golden('bpr_f16')
+    args, w, _ = golden_fit_args(g)
+    _rankfm.fit_ex(*args, 1, mode="replay", perms=g['perms'][:1])
+    _rankfm.fit_ex(*args, 1, mode="replay", perms=g['perms'][1:2])
+    args_o, wo, _ = golden_fit_args(g)
+    oracle.fit_ex(*args_o, 1, perms=g['perms'][:1])
+    oracle.fit_ex(*args_o, 1, perms=g['perms'][1:2])
+    for k in WEIGHTS:
+        assert rel_err(w[k], wo[k]) < 1e-4, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training: production (parallel) schedule -- statistical parity
+# ---------------------------------------------------------------------------------------------------------------
+def _auc(w, X, indptr, indices, n=20000, seed=3):
+    """P(score(u, observed i) > score(u, random unobserved j)) under the trained model"""
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, len(X), n)
+    u, i = X[rows, 0], X[rows, 1]
+    j = rng.integers(0, w['v_i'].shape[0], n)
+    keep = np.array([jj not in set(indices[indptr[uu]:indptr[uu + 1]].tolist()) for uu, jj in zip(u[:2000], j[:2000])])
+    u, i, j = u[:2000][keep], i[:2000][keep], j[:2000][keep]
+    s = lambda it: w['w_i'][it] + np.einsum('nf,nf->n', w['v_u'][u], w['v_i'][it])
+    return float(np.mean(s(i) > s(j)))
+
+
+@pytest.mark.parametrize("loss,max_samples,F", [("bpr", 1, 16), ("warp", 10, 20)])
+def test_parallel_fit_statistical_parity(gpu_lib, loss, max_samples, F):
+    U, I = 2000, 1000
+    X = zipf_interactions(U, I, 60000, seed=42)
+    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    sw = np.ones(len(X), np.float32)
+    x_uf, x_if = features(U, I, 0, 0)
+    epochs = 5
+    hyper = (0.01, 0.1, 0.1, 'invscaling', 0.25, max_samples)
+    wg = init_weights(U, I, F, seed=0)
+    stats = _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[wg[k] for k in WEIGHTS], *hyper, epochs, mode="production", seed=7)
+    wo = init_weights(U, I, F, seed=0)
+    rng = np.random.RandomState(0)
+    perms = np.stack([rng.permutation(len(X)) for _ in range(epochs)]).astype(np.int32)
+    out = oracle.fit_ex(X, sw, ui, x_uf, x_if, *[wo[k] for k in WEIGHTS], *hyper, epochs, perms=perms, sampler="mt")
+    ll_g, ll_o = np.array([s['log_likelihood'] for s in stats]), out['ll'].astype(np.float64)
+    # epoch log-likelihoods track the sequential reference within 3 % and improve over training
+    np.testing.assert_allclose(ll_g, ll_o, rtol=0.03)
+    assert ll_g[-1] > ll_g[0]
+    draws_g, draws_o = np.array([s['draws'] for s in stats], float), out['draws'].astype(float)
+    np.testing.assert_allclose(draws_g, draws_o, rtol=0.05)
+    if loss == "bpr":
+        assert (draws_g == len(X)).all()
+    # ranking quality of the two trained models agrees
+    auc_g, auc_o = _auc(wg, X, indptr, indices), _auc(wo, X, indptr, indices)
+    assert abs(auc_g - auc_o) < 0.02 and auc_g > 0.7
+    # weights have the same scale
+    for k in ('v_u', 'v_i', 'w_i'):
+        assert abs(np.linalg.norm(wg[k]) / np.linalg.norm(wo[k]) - 1) < 0.05, k
+
+
+def test_parallel_fit_with_features_statistical_parity(gpu_lib):
+    U, I, F, P, Q = 1500, 800, 12, 5, 6
+    X = zipf_interactions(U, I, 40000, seed=5)
+    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    sw = np.random.default_rng(1).uniform(0.5, 1.5, len(X)).astype(np.float32)
+    x_uf, x_if = features(U, I, P, Q)
+    hyper = (0.01, 0.1, 0.05, 'constant', 0.25, 5)
+    wg = init_weights(U, I, F, P, Q, seed=2)
+    stats = _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[wg[k] for k in WEIGHTS], *hyper, 4, mode="production", seed=9)
+    wo = init_weights(U, I, F, P, Q, seed=2)
+    perms = np.stack([np.random.RandomState(e).permutation(len(X)) for e in range(4)]).astype(np.int32)
+    out = oracle.fit_ex(X, sw, ui, x_uf, x_if, *[wo[k] for k in WEIGHTS], *hyper, 4, perms=perms, sampler="mt")
+    np.testing.assert_allclose([s['log_likelihood'] for s in stats], out['ll'].astype(np.float64), rtol=0.03)
+    for k in WEIGHTS:
+        assert abs(np.linalg.norm(wg[k]) / np.linalg.norm(wo[k]) - 1) < 0.10, k
+
+
+def test_fit_size_independent_properties_at_cfg2_shape(gpu_lib):
+    """BASELINE.json configs[1] at full size: MovieLens-1M shape, factors=20, warp, max_samples=20"""
+    X = zipf_interactions(6040, 3706, 1_600_000, seed=42, a_u=0.6, a_i=1.0)[:1_000_000]
+    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    sw = np.ones(len(X), np.float32)
+    x_uf, x_if = features(U, I, 0, 0)
+    w = init_weights(U, I, 20, seed=0)
+    w0 = {k: v.copy() for k, v in w.items()}
+    stats = _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[w[k] for k in WEIGHTS], 0.01, 0.1, 0.1, 'invscaling', 0.25, 20, 4, mode="production", seed=1)
+    N = len(X)
+    for s in stats:
+        assert N <= s['draws'] <= 20 * N and all(s['finite']) and np.isfinite(s['log_likelihood'])
+    ll = [s['log_likelihood'] for s in stats]
+    assert ll[-1] > ll[0] and -N * 0.8 < ll[0] < -N * 0.3          # starts near N*log(0.5)
+    assert stats[1]['eta'] == np.float32(0.1 / 2 ** 0.25)
+    for k in ('w_i', 'v_u', 'v_i'):
+        assert np.isfinite(w[k]).all() and not np.array_equal(w[k], w0[k])
+    assert np.array_equal(w['v_uf'], w0['v_uf']) and np.array_equal(w['w_if'], w0['w_if'])
+    # every user row moved (each user has >= 1 interaction): the epoch permutation visits every row
+    moved = np.abs(w['v_u'] - w0['v_u']).max(axis=1) > 0
+    assert moved.all()
+    # a zero-learning-rate-like run leaves weights (almost) untouched: linearity in eta
+    w2 = {k: v.copy() for k, v in w0.items()}
+    _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[w2[k] for k in WEIGHTS], 0.01, 0.1, 1e-9, 'constant', 0.25, 20, 1, mode="production", seed=1)
+    assert np.abs(w2['v_u'] - w0['v_u']).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F", [1, 2, 3, 10, 33, 64, 128, 130, 300])
+def test_replay_fit_any_factor_count(gpu_lib, F):
+    U, I = 40, 30
+    X = zipf_interactions(U, I, 400, seed=F)
+    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    sw = np.ones(len(X), np.float32)
+    x_uf, x_if = features(U, I, 0, 0)
+    perms = np.stack([np.random.RandomState(e).permutation(len(X)) for e in range(2)]).astype(np.int32)
+    wg, wo = init_weights(U, I, F, seed=1), init_weights(U, I, F, seed=1)
+    hyper = (0.01, 0.1, 0.1, 'constant', 0.25, 4)
+    _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[wg[k] for k in WEIGHTS], *hyper, 2, mode="replay", perms=perms)
+    oracle.fit_ex(X, sw, ui, x_uf, x_if, *[wo[k] for k in WEIGHTS], *hyper, 2, perms=perms)
+    for k in WEIGHTS:
+        assert rel_err(wg[k], wo[k]) < 1e-4, k
+
+
+def test_tiny_and_ragged_inputs(gpu_lib):
+    # one interaction, a user who has seen every item but one, duplicate interactions
+    X = np.array([[0, 0], [1, 0], [1, 1], [1, 2], [1, 3], [2, 4], [2, 4]], np.int32)
+    U, I, F = 3, 5, 4
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    sw = np.ones(len(X), np.float32)
+    x_uf, x_if = features(U, I, 0, 0)
+    perms = np.stack([np.random.RandomState(e).permutation(len(X)) for e in range(3)]).astype(np.int32)
+    wg, wo = init_weights(U, I, F, seed=1), init_weights(U, I, F, seed=1)
+    hyper = (0.01, 0.1, 0.1, 'constant', 0.25, 3)
+    _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[wg[k] for k in WEIGHTS], *hyper, 3, mode="replay", perms=perms)
+    oracle.fit_ex(X, sw, ui, x_uf, x_if, *[wo[k] for k in WEIGHTS], *hyper, 3, perms=perms)
+    for k in WEIGHTS:
+        assert rel_err(wg[k], wo[k]) < 1e-4, k
+    # production mode on the same tiny problem just has to run and stay finite
+    wp = init_weights(U, I, F, seed=1)
+    stats = _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[wp[k] for k in WEIGHTS], *hyper, 3, mode="production")
+    assert all(all(s['finite']) for s in stats)
+    # user 1 can only ever draw item 4
+    X1 = X[1:5]
+    w1 = init_weights(U, I, F, seed=1)
+    before = w1['v_i'].copy()
+    _rankfm.fit_ex(X1, np.ones(4, np.float32), ui, x_uf, x_if, *[w1[k] for k in WEIGHTS], *hyper, 1, mode="production")
+    assert np.abs(w1['v_i'][4] - before[4]).max() > 0
+
+
+def test_nonfinite_weights_raise_like_the_reference(gpu_lib):
+    g = load_golden('bpr_f16')
+    args, w, _ = golden_fit_args(g)
+    args = list(args)
+    args[1] = np.full_like(g['sample_weight'], 1e30)
+    args[13] = 1e10      # learning_rate
+    with pytest.raises(AssertionError, match="are not finite - try decreasing feature/sample_weight magnitudes"):
+        _rankfm.fit_ex(*args, 2, mode="production")
+    assert not np.isfinite(w['v_i']).all()        # weights are written back in the non-finite state, like the reference
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# predict / recommend / similar
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", KERNEL_CASES)
+def test_predict_matches_reference_golden(gpu_lib, case):
+    g = load_golden(case)
+    scores = _rankfm._predict(np.ascontiguousarray(g['pairs']), g['x_uf'], g['x_if'], *_weights(g, 'ref'))
+    assert scores.dtype == np.float32 and scores.shape == g['scores'].shape
+    assert np.array_equal(np.isnan(scores), np.isnan(g['scores']))
+    assert rel_err(scores, g['scores']) < 1e-5
+    assert _rankfm._predict(np.zeros((0, 2), np.float32), g['x_uf'], g['x_if'], *_weights(g, 'ref')).shape == (0,)
+
+
+@pytest.mark.parametrize("case", KERNEL_CASES)
+@pytest.mark.parametrize("filt", [False, True])
+def test_recommend_matches_reference_golden(gpu_lib, case, filt):
+    g = load_golden(case)
+    _, _, ui = golden_fit_args(g)
+    rec = _rankfm._recommend(g['users'], ui, 10, filt, g['x_uf'], g['x_if'], *_weights(g, 'ref'))
+    want = g['rec_filtered'] if filt else g['rec']
+    assert rec.dtype == np.float32 and rec.shape == want.shape
+    assert np.array_equal(np.isnan(rec), np.isnan(want))
+    assert topk_overlap(rec, want) >= 0.99                       # north_star: top-k set overlap >= 0.99
+    assert np.mean(rec[~np.isnan(want)] == want[~np.isnan(want)]) >= 0.98      # and (ties aside) the same order
+    if filt:
+        for row, u in zip(rec, g['users']):
+            if not np.isnan(u):
+                assert not set(row.astype(int).tolist()) & set(ui[int(u)].tolist())
+
+
+def test_recommend_more_than_available_and_large_n(gpu_lib):
+    g = load_golden('bpr_f16')
+    _, _, ui = golden_fit_args(g)
+    I = g['v_i_ref'].shape[0]
+    users = np.array([0, 1, np.nan, 2], np.float32)
+    rec = _rankfm._recommend(users, ui, I, True, g['x_uf'], g['x_if'], *_weights(g, 'ref'))
+    for row, u in zip(rec, users):
+        if np.isnan(u):
+            assert np.isnan(row).all()
+            continue
+        seen = len(set(ui[int(u)].tolist()))
+        assert np.isnan(row[I - seen:]).all() and not np.isnan(row[:I - seen]).any()
+        assert len(set(row[:I - seen].tolist())) == I - seen
+    full = _rankfm._recommend(users[:1], ui, I, False, g['x_uf'], g['x_if'], *_weights(g, 'ref'))
+    scores = oracle.scores_user(0, g['x_uf'], g['x_if'], *_weights(g, 'ref'))
+    assert np.all(np.diff(scores[full[0].astype(int)]) <= 1e-6)       # sorted by score, descending
+
+
+def test_similar_items_and_users(gpu_lib):
+    g = load_golden('warp_feat')
+    w = dict(zip(WEIGHTS, _weights(g, 'ref')))
+    for which, v, x, vf in ((0, w['v_i'], g['x_if'], w['v_if']), (1, w['v_u'], g['x_uf'], w['v_uf'])):
+        rep = v + x @ vf
+        for idx in (0, 7, len(v) - 1):
+            sims = rep @ rep[idx]
+            sims[idx] = -np.inf
+            want = np.argsort(-sims, kind='stable')[:8]
+            got = _rankfm._similar(which, idx, 8, g['x_uf'], g['x_if'], *w.values())
+            assert len(set(got.tolist()) & set(want.tolist())) >= 7 and idx not in got
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the public class, end to end, against the reference's class (golden minted through rankfm.rankfm.RankFM)
+# ---------------------------------------------------------------------------------------------------------------
+def test_rankfm_class_replay_matches_reference_class(gpu_lib):
+    from rankfm_b200 import RankFM
+    g = load_golden('api_warp_feat')
+    _rankfm.set_mode("replay")
+    try:
+        model = RankFM(factors=5, loss='warp', max_samples=6, learning_schedule='invscaling')
+        np.random.seed(int(g['seed']))
+        model.fit(g['interactions'], user_features=g['user_features'], item_features=g['item_features'],
+                  sample_weight=g['sample_weight'], epochs=3)
+    finally:
+        _rankfm.set_mode("production")
+    for k in WEIGHTS:
+        assert rel_err(getattr(model, k), g[k + '_ref']) < 1e-4, k
+    scores = model.predict(g['pairs'])
+    assert np.array_equal(np.isnan(scores), np.isnan(g['scores'])) and rel_err(scores, g['scores']) < PREDICT_RTOL
+    rec = model.recommend(g['users'], n_items=7).values.astype(np.float64)
+    assert np.array_equal(np.isnan(rec), np.isnan(g['rec'])) and topk_overlap(rec, g['rec']) >= 0.99
+    rec_f = model.recommend(g['users'], n_items=7, filter_previous=True).values.astype(np.float64)
+    assert topk_overlap(rec_f, g['rec_filtered']) >= 0.99
+    iid = np.unique(g['interactions'][:, 1]); uid = np.unique(g['interactions'][:, 0])
+    assert len(set(model.similar_items(iid[3], 5).tolist()) & set(g['sim_items'].tolist())) >= 4
+    assert len(set(model.similar_users(uid[7], 5).tolist()) & set(g['sim_users'].tolist())) >= 4
