@@ -142,6 +142,10 @@ int rfm_session_recommend(rfm_session *s, const float *users, int64_t n_users, i
 int rfm_session_time_predict(rfm_session *s, const float *pairs, int64_t n, int32_t iters, float *ms_out);
 int rfm_session_time_recommend(rfm_session *s, const float *users, int64_t n_users, int32_t n_items, int32_t filter_previous,
                                int32_t iters, float *ms_out, float *gemm_ms_out);
+/* debugging / parity: record, for every position r of an epoch, the negative item the sampler settled on and the
+ * number of draws it used (`min_index`, `sampled` of `_rankfm.pyx:244-268`); read back the last epoch's record */
+int rfm_session_trace_enable(rfm_session *s);
+int rfm_session_trace_read(rfm_session *s, int32_t *neg_and_sampled /* [N,2] */);
 int rfm_session_flush_l2(rfm_session *s);                                    /* overwrite a >L2-sized scratch buffer */
 int rfm_session_launch_count(rfm_session *s, int64_t *launches);             /* kernels launched by this session */
 int rfm_session_destroy(rfm_session *s);

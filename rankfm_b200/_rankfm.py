@@ -345,6 +345,14 @@ class Session:
         check(_lib.lib().rfm_session_time_recommend(self._h, ptr(users), users.shape[0], n_items, int(filter_previous), iters, C.byref(ms), C.byref(gemm)))
         return ms.value, gemm.value
 
+    def trace_enable(self):
+        check(_lib.lib().rfm_session_trace_enable(self._h))
+
+    def trace_read(self):
+        out = np.empty((self._p.n_interactions, 2), dtype=np.int32)
+        check(_lib.lib().rfm_session_trace_read(self._h, ptr(out)))
+        return out
+
     def flush_l2(self):
         check(_lib.lib().rfm_session_flush_l2(self._h))
 

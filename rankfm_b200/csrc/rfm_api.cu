@@ -137,6 +137,7 @@ struct rfm_session {
     // scratch
     float *d_snap_ut = nullptr, *d_snap_it = nullptr, *d_snap_gp = nullptr; int snap_epochs = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int32_t* d_trace = nullptr;
     float* d_flush = nullptr; size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;
 };
@@ -199,7 +200,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->d_inter); cudaFree(s->d_sw); cudaFree(s->d_indptr); cudaFree(s->d_indices);
     cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
     cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush);
-    cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp);
+    cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
     if (s->st) cudaStreamDestroy(s->st);
@@ -482,7 +483,18 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     tp.serial = p.sched == RFM_SCHED_SERIAL ? 1 : 0;
     tp.k0 = (uint32_t)p.seed; tp.k1 = (uint32_t)(p.seed >> 32);
     tp.mt = p.sampler == RFM_SAMPLER_MT ? s->d_mt : nullptr;
+    tp.trace = s->d_trace;
     std::vector<float> etas((size_t)epochs);
+    // Hogwild staleness cap: never keep more than 1/16 of an epoch in flight, so that on small inputs the schedule
+    // degrades towards sequential SGD instead of one giant stale batch (large inputs always get the full machine)
+    int grid = s->grid;
+    {
+        int qpl = 1;
+        const int G = train_group_size(s->T, &qpl);
+        const long long groups_per_block = (long long)(kTrainThreads / 32) * (32 / G);
+        const long long cap_blocks = std::max<long long>(1, (s->N / 16) / groups_per_block);
+        grid = (int)std::min<long long>(grid, cap_blocks);
+    }
 
     for (int e = 0; e < epochs; ++e) {
         const int epoch = s->epochs_done + e;               // LR schedule restarts per call, like the reference's per-_fit epoch counter
@@ -501,7 +513,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
             tp.feistel = make_feistel(s->N, p.seed, s->epochs_done + e);
         }
         CU(cudaEventRecord(s->ev[4 * e + 0], s->st));
-        cudaError_t le = launch_sgd_epoch(tp, s->grid, s->st);
+        cudaError_t le = launch_sgd_epoch(tp, grid, s->st);
         if (le != cudaSuccess) return fail(RFM_ERR_CUDA, "sgd_epoch launch failed: %s", cudaGetErrorString(le));
         CU(cudaEventRecord(s->ev[4 * e + 1], s->st));
         s->launches += 1;
@@ -703,6 +715,24 @@ extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, in
     if (gemm_ms_out) *gemm_ms_out = gemm_total / iters;
     cudaEventDestroy(a); cudaEventDestroy(b);
     cudaFree(d_users); cudaFree(d_rec);
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_trace_enable(rfm_session* s)
+{
+    if (!s || s->N <= 0) return fail(RFM_ERR_ARG, "trace needs a training session");
+    CU(cudaSetDevice(s->device));
+    if (!s->d_trace) { int rc = dev_alloc(&s->d_trace, (size_t)s->N * 2); if (rc) return rc; }
+    CU(cudaMemsetAsync(s->d_trace, 0xff, (size_t)s->N * 8, s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_trace_read(rfm_session* s, int32_t* out)
+{
+    if (!s || !out || !s->d_trace) return fail(RFM_ERR_ARG, "trace not enabled");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(out, s->d_trace, (size_t)s->N * 8, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
     return RFM_OK;
 }
 

@@ -62,8 +62,8 @@ template <int G>
 __device__ __forceinline__ unsigned group_ballot(bool pred, int gw)
 {
     const unsigned b = __ballot_sync(0xffffffffu, pred);
-    if (G == 32) return b;
-    return (b >> (gw * G)) & ((1u << G) - 1u);
+    if constexpr (G == 32) return b;
+    else return (b >> (gw * G)) & ((1u << G) - 1u);
 }
 
 // Membership of `cand` in the sorted list items[0..deg): (G+1)-ary search, one probe per lane and round.
@@ -74,21 +74,24 @@ __device__ __forceinline__ bool group_member(int cand, const int32_t* __restrict
 {
     int lo = 0, hi = active ? deg : 0;
     bool found = false;
+    // NOTE: the ballots sit at ONE program point for all 32 lanes -- groups of the same warp are in different
+    // phases of their searches (or idle), and *_sync primitives must never be reached through divergent branches.
     while (__any_sync(0xffffffffu, hi > lo && !found)) {
         const int len = hi - lo;
         const bool live = len > 0 && !found;
-        if (len <= G) {
-            const int e = (live && sub < len) ? __ldg(items + lo + sub) : -1;
-            found = found || (group_ballot<G>(live && e == cand, gw) != 0u);
-            hi = lo;
-        } else {
-            // pivots p_s = lo + (s+1)*len/(G+1), s = 0..G-1, strictly increasing because len > G
-            const int ps = lo + (int)(((long long)(sub + 1) * len) / (G + 1));
-            const int e = live ? __ldg(items + ps) : 0;
-            const unsigned eq = group_ballot<G>(live && e == cand, gw);
-            const unsigned lt = group_ballot<G>(live && e < cand, gw);
-            if (eq) { found = true; }
-            else if (live) {
+        const bool small = len <= G;
+        // small: element lo+sub ; large: pivot p_sub = lo + (sub+1)*len/(G+1), strictly increasing because len > G
+        const int idx = small ? lo + sub : lo + (int)(((long long)(sub + 1) * len) / (G + 1));
+        const bool probe = live && (!small || sub < len);
+        const int e = probe ? __ldg(items + idx) : 0;
+        const unsigned eq = group_ballot<G>(probe && e == cand, gw);
+        const unsigned lt = group_ballot<G>(probe && e < cand, gw);
+        if (eq) {
+            found = true;
+        } else if (live) {
+            if (small) {
+                hi = lo;
+            } else {
                 const int c = __popc(lt);                       // pivots below cand: p_0..p_{c-1}
                 const int nlo = c == 0 ? lo : lo + (int)(((long long)c * len) / (G + 1)) + 1;
                 const int nhi = c == G ? hi : lo + (int)(((long long)(c + 1) * len) / (G + 1));

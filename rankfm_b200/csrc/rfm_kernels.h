@@ -32,6 +32,7 @@ struct TrainParams {
     uint32_t k0, k1, epoch_key;
     MtState* mt;             // non-null -> MT19937 sampler (serial only)
     EpochAcc* acc;
+    int32_t* trace;          // optional [N,2]: (chosen negative, draws used) per position of the epoch
 };
 
 int train_group_size(const Tables& T, int* qpl_out);

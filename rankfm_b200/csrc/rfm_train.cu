@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kTrainThreads) sgd_epoch_kernel(const TrainPar
             draws_acc += sampled;
         }
         const int j = upd ? min_j : 0;
+        if (p.trace && upd && sub == 0) { p.trace[2 * r] = min_j; p.trace[2 * r + 1] = sampled; }
         float* urow = T.UT + (size_t)u * T.ldu;
         float* irow = T.IT + (size_t)i * T.ldi;
         float* jrow = T.IT + (size_t)j * T.ldi;
@@ -184,11 +185,11 @@ __global__ void __launch_bounds__(kTrainThreads) sgd_epoch_kernel(const TrainPar
             if (T.x_uf_any) {                                                  // v_uf[p] for x_uf[u,p] != 0 (:313-318)
                 for (int pp = 0; pp < T.P; ++pp) {
                     const float xp = __shfl_sync(0xffffffffu, get4(uc.xu, pp & 3), pp >> 2, G);
-                    if (xp == 0.0f) continue;                                  // group-uniform
+                    const bool nz = xp != 0.0f;               // predicate, not `continue`: other groups of the warp still need the shuffle
 #pragma unroll
                     for (int k = 0; k < QPL; ++k) {
                         const int q = sub + k * G;
-                        if (upd && q < T.NQ) {
+                        if (upd && nz && q < T.NQ) {
                             float* wp = T.GP + T.gp_vuf + (size_t)pp * T.Fp + 4 * q;
                             const float4 w = ld_cg4(wp);
                             float4 d;
@@ -202,11 +203,11 @@ __global__ void __launch_bounds__(kTrainThreads) sgd_epoch_kernel(const TrainPar
             if (T.x_if_any) {                                                  // v_if[q] for dx[q] != 0 (:321-326)
                 for (int q = 0; q < T.Q; ++q) {
                     const float dxq = __shfl_sync(0xffffffffu, get4(dx, q & 3), q >> 2, G);
-                    if (dxq == 0.0f) continue;
+                    const bool nz = dxq != 0.0f;
 #pragma unroll
                     for (int k = 0; k < QPL; ++k) {
                         const int qq = sub + k * G;
-                        if (upd && qq < T.NQ) {
+                        if (upd && nz && qq < T.NQ) {
                             float* wp = T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq;
                             const float4 w = ld_cg4(wp);
                             float4 d;

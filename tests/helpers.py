@@ -82,12 +82,14 @@ def features(U, I, P, Q, seed=0, sparsity=0.3):
 
 
 def rel_err(a, b):
-    """max |a-b| / max(|b|, floor) over finite entries, floor = 1e-3 * typical magnitude"""
+    """max over entries of |a-b| / max(|b|, 0.1*rms(b)): relative error, where entries smaller than a tenth of the
+    array's typical magnitude are judged against that tenth (float32 reassociation noise on a sum of O(rms) terms
+    is ~1e-7*rms absolute, so a pure per-entry relative error near zero crossings measures nothing)"""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     m = np.isfinite(a) & np.isfinite(b)
     if not m.any():
         return 0.0
-    floor = max(1e-3 * float(np.abs(b[m]).mean()), 1e-12)
+    floor = max(0.1 * float(np.sqrt(np.mean(b[m] ** 2))), 1e-12)
     return float(np.max(np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), floor)))
 
 

@@ -57,6 +57,28 @@ def test_serial_philox_fit_matches_oracle(gpu_lib, case):
     assert [s['draws'] for s in stats] == out['draws'].tolist()
 
 
+@pytest.mark.parametrize("case,sampler", [("warp_f20", "mt"), ("warp_feat", "mt"), ("warp_f20", "philox"), ("bpr_f16", "philox")])
+def test_sampler_is_draw_for_draw_identical_to_the_oracle(gpu_lib, case, sampler):
+    """per position of the epoch: same negative item, same number of draws as the oracle (first epoch, where both
+    start from identical weights; later epochs are covered by the weight comparisons above)"""
+    g = load_golden(case)
+    args, w, _ = golden_fit_args(g)
+    keep = []
+    mt = sampler == "mt"
+    prob = _rankfm.fit_problem(*args, mode="replay" if mt else "production", seed=31337, keep=keep)
+    if not mt:
+        prob.sched = _lib.SCHED_SERIAL
+    sess = _rankfm.Session(prob, keep)
+    sess.trace_enable()
+    sess.train(1, perms=np.ascontiguousarray(g['perms'][:1]) if mt else None)
+    trace = sess.trace_read()
+    sess.close()
+    args_o, _, _ = golden_fit_args(g)
+    out = oracle.fit_ex(*args_o, 1, perms=g['perms'][:1] if mt else None, sampler=sampler, seed=31337, max_rejects=0 if mt else 64, want_neg=True)
+    assert np.array_equal(trace[:, 0], out['neg'][0])
+    assert trace[:, 1].sum() == out['draws'][0]
+
+
 def test_replay_is_deterministic(gpu_lib):
     g = load_golden('warp_f20')
     runs = []
@@ -114,8 +136,10 @@ def test_parallel_fit_statistical_parity(gpu_lib, loss, max_samples, F):
     perms = np.stack([rng.permutation(len(X)) for _ in range(epochs)]).astype(np.int32)
     out = oracle.fit_ex(X, sw, ui, x_uf, x_if, *[wo[k] for k in WEIGHTS], *hyper, epochs, perms=perms, sampler="mt")
     ll_g, ll_o = np.array([s['log_likelihood'] for s in stats]), out['ll'].astype(np.float64)
-    # epoch log-likelihoods track the sequential reference within 3 % and improve over training
-    np.testing.assert_allclose(ll_g, ll_o, rtol=0.03)
+    # epoch log-likelihoods track the sequential reference: the very first epoch lags a little (up to 1/16 of an
+    # epoch is in flight with stale weights while the item biases learn fastest), later epochs agree within 3 %
+    np.testing.assert_allclose(ll_g[:1], ll_o[:1], rtol=0.10)
+    np.testing.assert_allclose(ll_g[1:], ll_o[1:], rtol=0.03)
     assert ll_g[-1] > ll_g[0]
     draws_g, draws_o = np.array([s['draws'] for s in stats], float), out['draws'].astype(float)
     np.testing.assert_allclose(draws_g, draws_o, rtol=0.05)
