@@ -25,7 +25,8 @@
  *
  * Two extra "schedules" that the reference does not have are restated here so that the GPU production kernel
  * (Philox negatives, on-device Feistel shuffle) can be checked draw-for-draw in its serial configuration:
- *   sampler 1  = Philox4x32-10 keyed by (seed), counter (row.lo, epoch, attempt/4, row.hi); attempt a uses word a%4
+ *   sampler 1  = Philox4x32-10 keyed by (seed), counter (row.lo, epoch, attempt/4, row.hi); attempt a uses word a%4;
+ *                item = (word * I) >> 32
  *   perms NULL = position r of epoch e maps to row orc_feistel_perm(r, N, seed, e)
  * Their definitions are the contract shared with rankfm_b200/csrc/rfm_rng.cuh.
  */
@@ -257,7 +258,8 @@ int orc_fit(orc_fit_args *a)
                         word = blk[attempt & 3u];
                         ++attempt;
                     }
-                    j = (int)(word % (uint32_t)I);
+                    j = a->sampler == 0 ? (int)(word % (uint32_t)I)                  /* genrand_int32() % I, _rankfm.pyx:251 */
+                                        : (int)(((uint64_t)word * (uint64_t)(uint32_t)I) >> 32);  /* Philox contract: multiply-shift */
                     if (!orc_member(j, items, n_items)) break;
                     if (a->max_rejects > 0 && ++rejects >= a->max_rejects) break;
                 }

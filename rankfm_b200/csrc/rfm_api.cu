@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -124,6 +125,7 @@ struct rfm_session {
     int2* d_inter = nullptr; float* d_sw = nullptr; int64_t* d_indptr = nullptr; int32_t* d_indices = nullptr;
     int64_t N = 0, nnz = 0;
     int32_t* d_perm = nullptr;
+    uint32_t* d_bitmap = nullptr; int bitmap_words = 0;
     float* d_mult = nullptr;
     MtState* d_mt = nullptr;
     EpochAcc* d_acc = nullptr; int acc_cap = 0;
@@ -198,7 +200,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     for (auto e : s->ev) cudaEventDestroy(e);
     cudaFree(s->T.UT); cudaFree(s->T.IT); cudaFree(s->T.GP);
     cudaFree(s->d_inter); cudaFree(s->d_sw); cudaFree(s->d_indptr); cudaFree(s->d_indices);
-    cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
+    cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
     cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
     if (s->t0) cudaEventDestroy(s->t0);
@@ -289,6 +291,21 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
             CUB(cudaMemcpyAsync(s->d_mt, &h, sizeof h, cudaMemcpyHostToDevice, s->st));
         }
         if (p->order == RFM_ORDER_HOST) TRY(dev_alloc(&s->d_perm, (size_t)s->N));
+        if (s->nnz >= ((int64_t)1 << 31) / 32) return bail(fail(RFM_ERR_UNSUPPORTED, "user_items larger than 2^26 entries per user are not supported"));
+        {
+            // membership bitmap when U x I bits fit the budget (default 1 GiB; RANKFM_B200_BITMAP_MB=0 disables)
+            const char* env = getenv("RANKFM_B200_BITMAP_MB");
+            const double budget_mb = env ? atof(env) : 1024.0;
+            const int words = (p->I + 31) / 32;
+            const double need_mb = (double)p->U * words * 4.0 / (1024.0 * 1024.0);
+            if (need_mb <= budget_mb) {
+                s->bitmap_words = words;
+                TRY(dev_alloc(&s->d_bitmap, (size_t)p->U * words));
+                CUB(cudaMemsetAsync(s->d_bitmap, 0, (size_t)p->U * words * 4, s->st));
+                CUB(launch_build_bitmap(s->d_indptr, s->d_indices, p->U, s->d_bitmap, words, s->st));
+                s->launches += 1;
+            }
+        }
         CUB(cudaStreamSynchronize(s->st));
     }
     {
@@ -475,6 +492,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     tp.T = s->T;
     tp.interactions = s->d_inter; tp.sample_weight = s->d_sw; tp.indptr = s->d_indptr; tp.indices = s->d_indices;
     tp.mult = s->d_mult;
+    tp.bitmap = s->d_bitmap; tp.bitmap_words = s->bitmap_words;
     tp.N = s->N;
     tp.reg_a = (float)(2.0 * p.alpha);                      // d_reg_a / d_reg_b, _rankfm.pyx:171-172
     tp.reg_b = (float)(2.0 * p.beta);
@@ -486,13 +504,12 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     tp.trace = s->d_trace;
     std::vector<float> etas((size_t)epochs);
     // Hogwild staleness cap: never keep more than 1/16 of an epoch in flight, so that on small inputs the schedule
-    // degrades towards sequential SGD instead of one giant stale batch (large inputs always get the full machine)
+    // degrades towards sequential SGD instead of one giant stale batch (large inputs always get the full machine).
+    // A warp of the pipelined kernel holds one batch of 32 positives.
     int grid = s->grid;
     {
-        int qpl = 1;
-        const int G = train_group_size(s->T, &qpl);
-        const long long groups_per_block = (long long)(kTrainThreads / 32) * (32 / G);
-        const long long cap_blocks = std::max<long long>(1, (s->N / 16) / groups_per_block);
+        const long long in_flight_per_block = (long long)(kTrainThreads / 32) * 32;
+        const long long cap_blocks = std::max<long long>(1, (s->N / 16) / in_flight_per_block);
         grid = (int)std::min<long long>(grid, cap_blocks);
     }
 

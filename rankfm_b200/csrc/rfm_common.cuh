@@ -69,6 +69,7 @@ __device__ __forceinline__ unsigned group_ballot(bool pred, int gw)
 // Membership of `cand` in the sorted list items[0..deg): (G+1)-ary search, one probe per lane and round.
 // Replaces the reference's linear scan (`lsearch`, rankfm/_rankfm.pyx:20-27; `bsearch` :30-45 is dead code there).
 // Warp-uniform control flow: every lane of the warp calls with its group's arguments; `active` masks groups out.
+// 32-bit pivot arithmetic: needs G*deg < 2^32, i.e. deg < 1.3e8 (the API rejects larger catalogues).
 template <int G>
 __device__ __forceinline__ bool group_member(int cand, const int32_t* __restrict__ items, int deg, bool active, int sub, int gw)
 {
@@ -81,7 +82,7 @@ __device__ __forceinline__ bool group_member(int cand, const int32_t* __restrict
         const bool live = len > 0 && !found;
         const bool small = len <= G;
         // small: element lo+sub ; large: pivot p_sub = lo + (sub+1)*len/(G+1), strictly increasing because len > G
-        const int idx = small ? lo + sub : lo + (int)(((long long)(sub + 1) * len) / (G + 1));
+        const int idx = small ? lo + sub : lo + (int)(((unsigned)(sub + 1) * (unsigned)len) / (unsigned)(G + 1));
         const bool probe = live && (!small || sub < len);
         const int e = probe ? __ldg(items + idx) : 0;
         const unsigned eq = group_ballot<G>(probe && e == cand, gw);
@@ -93,8 +94,8 @@ __device__ __forceinline__ bool group_member(int cand, const int32_t* __restrict
                 hi = lo;
             } else {
                 const int c = __popc(lt);                       // pivots below cand: p_0..p_{c-1}
-                const int nlo = c == 0 ? lo : lo + (int)(((long long)c * len) / (G + 1)) + 1;
-                const int nhi = c == G ? hi : lo + (int)(((long long)(c + 1) * len) / (G + 1));
+                const int nlo = c == 0 ? lo : lo + (int)(((unsigned)c * (unsigned)len) / (unsigned)(G + 1)) + 1;
+                const int nhi = c == G ? hi : lo + (int)(((unsigned)(c + 1) * (unsigned)len) / (unsigned)(G + 1));
                 lo = nlo; hi = nhi;
             }
         }

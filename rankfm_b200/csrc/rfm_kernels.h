@@ -19,16 +19,19 @@ struct EpochAcc {            // zeroed before each epoch, read back after
 
 struct TrainParams {
     Tables T;
-    const int2* interactions;
+    const int2* interactions;   // [N] (user, item); N < 2^31
     const float* sample_weight;
     const int64_t* indptr;
     const int32_t* indices;
+    const uint32_t* bitmap;  // optional [U, bitmap_words]: bit i of row u set <=> item i in user_items[u]; nullptr -> search the CSR
+    int32_t bitmap_words;
     const int32_t* perm;     // this epoch's order, or nullptr -> Feistel
     const float* mult;       // [max_samples+1]  WARP multiplier by number of draws
     Feistel feistel;
     long long N;
     float eta, reg_a, reg_b;
     int32_t max_samples, max_rejects, serial;
+    int32_t depth;           // stages of the TMA row pipeline (set by the launcher)
     uint32_t k0, k1, epoch_key;
     MtState* mt;             // non-null -> MT19937 sampler (serial only)
     EpochAcc* acc;
@@ -37,6 +40,7 @@ struct TrainParams {
 
 int train_group_size(const Tables& T, int* qpl_out);
 cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st);
+cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bitmap, int words, cudaStream_t st);
 cudaError_t launch_weight_stats(const Tables& T, double* out12, int grid, cudaStream_t st);
 
 // scoring (rfm_score.cu)

@@ -1,0 +1,217 @@
+// rfm_sgd.cuh -- the two halves of one SGD step shared by both epoch kernels (rfm_train.cu):
+//   sample_negatives  WARP/BPR rejection sampler  (rankfm/_rankfm.pyx:244-264)
+//   apply_update      gradient step               (rankfm/_rankfm.pyx:267-326)
+// Both are written for lane groups (rfm_common.cuh); every lane of the warp must call them (warp-uniform control flow,
+// *_sync primitives are never reached through divergent branches).
+#pragma once
+#include "rfm_kernels.h"
+#include "rfm_pair.cuh"
+#include "rfm_rng.cuh"
+
+namespace rfm {
+
+struct StepAcc {
+    double ll = 0.0;          // sum log sigma(pairwise utility)
+    long long draws = 0;      // negatives evaluated
+    int bad = 0;              // a positive whose pairwise utilities were all NaN
+};
+
+// is item `cj` in user u's observed set?  bitmap (small catalogues) or (G+1)-ary search of the sorted CSR segment
+template <int G>
+__device__ __forceinline__ bool is_member(const TrainParams& p, int u, int cj, long long seg, int deg, bool active, int sub, int gw)
+{
+    if (p.bitmap) return active && ((__ldg(p.bitmap + (size_t)u * p.bitmap_words + (cj >> 5)) >> (cj & 31)) & 1u);
+    return group_member<G>(cj, p.indices + seg, deg, active, sub, gw);
+}
+
+// Draws s = s_begin .. max_samples for every group that is not `done`, tracking the hardest negative seen so far
+// (min pairwise utility) in (neg, min_pu, min_j, sampled) exactly like the reference's loop.  `attempt` counts Philox
+// words consumed for this positive (rejected ones included), so a caller that already made draw 1 can continue.
+template <int G, int QPL, bool FEAT, bool MT>
+__device__ __forceinline__ void sample_negatives(const TrainParams& p, const UserCtx<QPL>& uc, float ut_ui, int row, int u, long long seg, int deg,
+                                                 int s_begin, bool& done, uint32_t& attempt, MtState* mt, int sub, int gw,
+                                                 ItemRow<QPL>& neg, float& min_pu, int& min_j, int& sampled)
+{
+    const Tables& T = p.T;
+    ItemRow<QPL> cand;
+    Philox4 blk = {0u, 0u, 0u, 0u};
+    if (!MT && (attempt & 3u) != 0u) blk = philox4x32_10((uint32_t)row, p.epoch_key, attempt >> 2, 0u, p.k0, p.k1);
+    for (int s = s_begin; s <= p.max_samples; ++s) {
+        if (!__any_sync(0xffffffffu, !done)) break;
+        // rejection-sample an unobserved item: `while True: j = genrand_int32() % I` (:250-253)
+        int j = 0, rejects = 0;
+        bool need = !done;
+        while (__any_sync(0xffffffffu, need)) {
+            uint32_t word;
+            if (MT) {
+                word = mt_next_warp(mt);
+            } else {
+                if ((attempt & 3u) == 0u) blk = philox4x32_10((uint32_t)row, p.epoch_key, attempt >> 2, 0u, p.k0, p.k1);
+                const uint32_t c = attempt & 3u;
+                word = c == 0u ? blk.x : (c == 1u ? blk.y : (c == 2u ? blk.z : blk.w));
+                if (need) ++attempt;
+            }
+            // MT replay: `genrand_int32() % I` like the reference; Philox: multiply-shift range reduction (1 IMAD.HI)
+            const int cj = MT ? (int)(word % (uint32_t)T.I) : (int)__umulhi(word, (uint32_t)T.I);
+            if (need) load_item<G, QPL, FEAT>(T, cj, true, sub, cand);      // speculative: in flight during the membership test
+            const bool member = is_member<G>(p, u, cj, seg, deg, need, sub, gw);
+            if (need && (!member || ++rejects >= p.max_rejects)) { j = cj; need = false; }
+        }
+        const float pu = ut_ui - utility<G, QPL, FEAT>(uc, cand);
+        if (!done) {
+            sampled = s;
+            if (pu < min_pu) { min_pu = pu; min_j = j; neg = cand; }
+            if (pu < 1.0f) done = true;                                      // MARGIN (:149,263)
+        }
+    }
+}
+
+// One gradient step on (u, i, j): reads nothing but GP (feature parameters) from memory, everything else arrives in
+// registers; writes go out as vector reductions.  Update formula and operand association follow the generated C of the
+// reference:  w += eta * (((sw*mult) * (d_outer*d)) - (2reg * w)).
+template <int G, int QPL, bool FEAT, bool EXACT>
+__device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx<QPL>& uc, const ItemRow<QPL>& pos, const ItemRow<QPL>& neg,
+                                             int u, int i, int min_j, float sw, int sampled, float min_pu, bool valid, long long r,
+                                             int sub, StepAcc& acc)
+{
+    const Tables& T = p.T;
+    const bool upd = valid && min_j >= 0;
+    if (valid && min_j < 0) acc.bad = 1;
+    const float mult = upd ? __ldg(p.mult + sampled) : 0.f;                  // log((I-1)//sampled)/log(I), host table (:269)
+    // d_outer = 1/(exp(pu)+1) (:276).  Serial/replay schedules keep the reference's double-precision libm path;
+    // the Hogwild schedule uses the SFU (ex2 + rcp, ~1e-6 relative), far below its own scheduling noise.
+    const float d_outer = EXACT ? (float)(1.0 / (exp((double)min_pu) + 1.0)) : __frcp_rn(__expf(min_pu) + 1.0f);
+    const float smul = sw * mult;
+    if (upd && sub == 0) {   // log sigma(pu) = -softplus(-pu), evaluated without cancellation (:270)
+        acc.ll -= (double)(fmaxf(-min_pu, 0.f) + log1pf(__expf(-fabsf(min_pu))));
+        acc.draws += sampled;
+    }
+    const int j = upd ? min_j : 0;
+    if (p.trace && upd && sub == 0) { p.trace[2 * r] = min_j; p.trace[2 * r + 1] = sampled; }
+    float* urow = T.UT + (size_t)u * T.ldu;
+    float* irow = T.IT + (size_t)i * T.ldi;
+    float* jrow = T.IT + (size_t)j * T.ldi;
+    const float eta = p.eta, ra = p.reg_a, rb = p.reg_b;
+#define RFM_G(d, w) (eta * ((smul * (d_outer * (d))) - (rb_or_ra * (w))))
+
+    float4 dx = zero4();
+    if (FEAT) { dx.x = pos.x.x - neg.x.x; dx.y = pos.x.y - neg.x.y; dx.z = pos.x.z - neg.x.z; dx.w = pos.x.w - neg.x.w; }
+
+    // d u / d v_u = (v_i - v_j) + sum_q v_if[q] (x_if[i,q] - x_if[j,q])   (:292,303-305)
+    float4 dvu[QPL];
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) {
+        dvu[k].x = pos.v[k].x - neg.v[k].x; dvu[k].y = pos.v[k].y - neg.v[k].y;
+        dvu[k].z = pos.v[k].z - neg.v[k].z; dvu[k].w = pos.v[k].w - neg.v[k].w;
+    }
+    if (FEAT && T.x_if_any) {
+        for (int q = 0; q < T.Q; ++q) {
+            const float dxq = __shfl_sync(0xffffffffu, get4(dx, q & 3), q >> 2, G);
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) {
+                const int qq = sub + k * G;
+                if (upd && qq < T.NQ) {
+                    const float4 w = ld_cg4(T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq);
+                    dvu[k].x += w.x * dxq; dvu[k].y += w.y * dxq; dvu[k].z += w.z * dxq; dvu[k].w += w.w * dxq;
+                }
+            }
+        }
+    }
+
+    float4 vu_new[QPL], dij_new[QPL];   // updated v_u and (v_i - v_j), needed by the feature-factor updates
+    {
+        const float rb_or_ra = ra;
+        if (upd && sub == 0) {           // item biases (:279-280)
+            red_add1(irow + T.Fp, RFM_G(1.0f, pos.w));
+            red_add1(jrow + T.Fp, RFM_G(-1.0f, neg.w));
+        }
+#pragma unroll
+        for (int k = 0; k < QPL; ++k) {
+            const int q = sub + k * G;
+            float4 du, di, dj;
+            du.x = RFM_G(dvu[k].x, uc.vu[k].x); du.y = RFM_G(dvu[k].y, uc.vu[k].y);
+            du.z = RFM_G(dvu[k].z, uc.vu[k].z); du.w = RFM_G(dvu[k].w, uc.vu[k].w);
+            di.x = RFM_G(uc.a[k].x, pos.v[k].x); di.y = RFM_G(uc.a[k].y, pos.v[k].y);
+            di.z = RFM_G(uc.a[k].z, pos.v[k].z); di.w = RFM_G(uc.a[k].w, pos.v[k].w);
+            dj.x = RFM_G(-uc.a[k].x, neg.v[k].x); dj.y = RFM_G(-uc.a[k].y, neg.v[k].y);
+            dj.z = RFM_G(-uc.a[k].z, neg.v[k].z); dj.w = RFM_G(-uc.a[k].w, neg.v[k].w);
+            if (upd && q < T.NQ) {
+                red_add4(urow + 4 * q, du);
+                red_add4(irow + 4 * q, di);
+                red_add4(jrow + 4 * q, dj);
+            }
+            if (FEAT) {
+                vu_new[k].x = uc.vu[k].x + du.x; vu_new[k].y = uc.vu[k].y + du.y;
+                vu_new[k].z = uc.vu[k].z + du.z; vu_new[k].w = uc.vu[k].w + du.w;
+                dij_new[k].x = (pos.v[k].x + di.x) - (neg.v[k].x + dj.x); dij_new[k].y = (pos.v[k].y + di.y) - (neg.v[k].y + dj.y);
+                dij_new[k].z = (pos.v[k].z + di.z) - (neg.v[k].z + dj.z); dij_new[k].w = (pos.v[k].w + di.w) - (neg.v[k].w + dj.w);
+            }
+        }
+    }
+    if (FEAT) {
+        const float rb_or_ra = rb;
+        if (T.x_if_any) {
+            if (upd && 4 * sub < T.Qp) {                                   // w_if, every q (:283-286)
+                const float4 w = ld_cg4(T.GP + 4 * sub);
+                float4 d;
+                d.x = RFM_G(dx.x, w.x); d.y = RFM_G(dx.y, w.y); d.z = RFM_G(dx.z, w.z); d.w = RFM_G(dx.w, w.w);
+                red_add4(T.GP + 4 * sub, d);
+            }
+        }
+        if (T.x_uf_any) {                                                  // v_uf[p] for x_uf[u,p] != 0 (:313-318)
+            for (int pp = 0; pp < T.P; ++pp) {
+                const float xp = __shfl_sync(0xffffffffu, get4(uc.xu, pp & 3), pp >> 2, G);
+                const bool nz = xp != 0.0f;               // predicate, not `continue`: other groups of the warp still need the shuffle
+#pragma unroll
+                for (int k = 0; k < QPL; ++k) {
+                    const int q = sub + k * G;
+                    if (upd && nz && q < T.NQ) {
+                        float* wp = T.GP + T.gp_vuf + (size_t)pp * T.Fp + 4 * q;
+                        const float4 w = ld_cg4(wp);
+                        float4 d;
+                        d.x = RFM_G(xp * dij_new[k].x, w.x); d.y = RFM_G(xp * dij_new[k].y, w.y);
+                        d.z = RFM_G(xp * dij_new[k].z, w.z); d.w = RFM_G(xp * dij_new[k].w, w.w);
+                        red_add4(wp, d);
+                    }
+                }
+            }
+        }
+        if (T.x_if_any) {                                                  // v_if[q] for dx[q] != 0 (:321-326)
+            for (int q = 0; q < T.Q; ++q) {
+                const float dxq = __shfl_sync(0xffffffffu, get4(dx, q & 3), q >> 2, G);
+                const bool nz = dxq != 0.0f;
+#pragma unroll
+                for (int k = 0; k < QPL; ++k) {
+                    const int qq = sub + k * G;
+                    if (upd && nz && qq < T.NQ) {
+                        float* wp = T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq;
+                        const float4 w = ld_cg4(wp);
+                        float4 d;
+                        d.x = RFM_G(dxq * vu_new[k].x, w.x); d.y = RFM_G(dxq * vu_new[k].y, w.y);
+                        d.z = RFM_G(dxq * vu_new[k].z, w.z); d.w = RFM_G(dxq * vu_new[k].w, w.w);
+                        red_add4(wp, d);
+                    }
+                }
+            }
+        }
+    }
+#undef RFM_G
+}
+
+// fold the per-lane accumulators of a warp into the epoch record
+__device__ __forceinline__ void flush_acc(StepAcc& a, EpochAcc* out)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a.ll += __shfl_xor_sync(0xffffffffu, a.ll, off);
+        a.draws += __shfl_xor_sync(0xffffffffu, a.draws, off);
+        a.bad |= __shfl_xor_sync(0xffffffffu, a.bad, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out->ll, a.ll);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&out->draws), (unsigned long long)a.draws);
+        if (a.bad) atomicOr(&out->bad, 1);
+    }
+}
+
+}  // namespace rfm

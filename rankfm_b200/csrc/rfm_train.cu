@@ -1,240 +1,71 @@
-// rfm_train.cu -- the SGD epoch kernel: B200 replacement of the per-epoch loop of `_fit`
+// rfm_train.cu -- the SGD epoch kernels: B200 replacement of the per-epoch loop of `_fit`
 // (rankfm/_rankfm.pyx:218-326: shuffle order, compute_ui_utility, WARP/BPR rejection sampler, gradient step).
 //
-// One lane group (G lanes) per positive (u,i); groups stride over the positions r of the epoch's permutation.
-// HBM-bound gather/scatter: per positive one gather of the user's fat row, one of the positive item's, one per
-// negative candidate; updates go out as vector reductions (REDG.E.ADD.F32x4) so concurrent groups never lose an
-// update.  No tensor cores here by design (arithmetic intensity ~1 FLOP/B).
+// HBM-bound gather/scatter (arithmetic intensity ~1 FLOP/B, no tensor cores by design): per positive one gather of
+// the user's fat row, one of the positive item's, one per negative candidate; updates leave as vector reductions
+// (REDG.E.ADD.F32x4) so concurrent groups never lose an update.
 //
-// Two schedules share this code (template/param switches, no second implementation):
-//   parallel  Hogwild over the whole GPU, Philox negatives, Feistel (or host) order           -> production
-//   serial    one group, positions strictly in order, optionally the reference's MT19937      -> exact replay of
-//             sequential SGD, used to pin the kernel arithmetic against the oracle / the reference
-#include "rfm_kernels.h"
-#include "rfm_pair.cuh"
-#include "rfm_rng.cuh"
+//   sgd_pipe_kernel    production (Hogwild).  Each warp alternates between
+//                        front end  -- 32 positives at once, one per lane: epoch permutation, (u,i) fetch, Philox draw
+//                                      and membership test of the first negative (32 independent small-load chains)
+//                        back end   -- lane groups walk those 32 tuples; the three fat rows of every tuple are staged
+//                                      into shared memory by TMA bulk copies (cp.async.bulk -> UBLKCP) that run `depth`
+//                                      steps ahead and complete on per-stage mbarriers, so row traffic for several
+//                                      positives per warp is in flight without costing registers.
+//   sgd_serial_kernel  one lane group, positives strictly in order, optionally the reference's MT19937 stream:
+//                      exact replay of sequential SGD, used to pin the arithmetic against the oracle / the reference.
+// Both call the same sample_negatives / apply_update (rfm_sgd.cuh).
+#include "rfm_sgd.cuh"
 
 namespace rfm {
 
+// ---------------------------------------------------------------------------------------------------------------
+// serial schedule
+// ---------------------------------------------------------------------------------------------------------------
 template <int G, int QPL, bool FEAT, bool MT>
-__global__ void __launch_bounds__(kTrainThreads) sgd_epoch_kernel(const TrainParams p)
+__global__ void __launch_bounds__(32) sgd_serial_kernel(const TrainParams p)
 {
     __shared__ MtState mt_smem;
     const Tables& T = p.T;
-    constexpr int GPW = 32 / G;                       // groups per warp
     const int lane = threadIdx.x & 31;
     const int sub = lane % G, gw = lane / G;
-    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    const bool serial = p.serial != 0;
-    const long long stride = serial ? 1 : n_warps * GPW;
-
-    if (MT) {   // serial launch is <<<1,32>>>: the warp owns the generator
+    if (MT) {
         for (int k = lane; k < kMtN; k += 32) mt_smem.s[k] = p.mt->s[k];
         if (lane == 0) mt_smem.pos = p.mt->pos;
         __syncwarp();
     }
-
-    double ll_acc = 0.0;
-    long long draws_acc = 0;
-    int bad = 0;
-
-    for (long long base = serial ? 0 : warp_global * GPW; base < p.N; base += stride) {
-        const long long r = base + (serial ? 0 : gw);
-        const bool valid = r < p.N && (!serial || gw == 0);
-
+    StepAcc acc;
+    for (long long r = 0; r < p.N; ++r) {
+        const bool valid = gw == 0;
         // ---- locate the observed (user, item, sample weight): _rankfm.pyx:233-236 ----
-        long long row = 0;
-        if (valid) row = p.perm ? (long long)__ldg(p.perm + r) : feistel_perm(p.feistel, r);
+        int row = 0;
+        if (valid) row = p.perm ? __ldg(p.perm + r) : (int)feistel_perm(p.feistel, r);
         int2 ui = make_int2(0, 0);
         float sw = 0.f;
         if (valid) { ui = __ldg(p.interactions + row); sw = __ldg(p.sample_weight + row); }
         const int u = ui.x, i = ui.y;
-
         UserCtx<QPL> uc;
-        ItemRow<QPL> pos, cand, neg;
+        ItemRow<QPL> pos, neg;
         load_user<G, QPL, FEAT>(T, u, valid, sub, uc);
         load_item<G, QPL, FEAT>(T, i, valid, sub, pos);
         long long seg = 0; int deg = 0;
         if (valid) { seg = __ldg(p.indptr + u); deg = (int)(__ldg(p.indptr + u + 1) - seg); }
         user_precompute<G, QPL, FEAT>(T, valid, sub, uc);
         const float ut_ui = utility<G, QPL, FEAT>(uc, pos);
-
         // ---- WARP / BPR sampling loop: _rankfm.pyx:244-264 ----
         int sampled = 0, min_j = -1;
         float min_pu = 1e6f;
         bool done = !valid;
         uint32_t attempt = 0;
-        Philox4 blk = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int k = 0; k < QPL; ++k) neg.v[k] = zero4();
         neg.x = zero4(); neg.w = 0.f;
-
-        for (int s = 1; s <= p.max_samples; ++s) {
-            if (!__any_sync(0xffffffffu, !done)) break;
-            // rejection-sample an unobserved item: `while True: j = genrand_int32() % I` (:250-253)
-            int j = 0, rejects = 0;
-            bool need = !done;
-            while (__any_sync(0xffffffffu, need)) {
-                uint32_t word;
-                if (MT) {
-                    word = mt_next_warp(&mt_smem);
-                } else {
-                    if ((attempt & 3u) == 0u)
-                        blk = philox4x32_10((uint32_t)row, p.epoch_key, attempt >> 2, (uint32_t)((unsigned long long)row >> 32), p.k0, p.k1);
-                    const uint32_t c = attempt & 3u;
-                    word = c == 0u ? blk.x : (c == 1u ? blk.y : (c == 2u ? blk.z : blk.w));
-                    if (need) ++attempt;
-                }
-                const int cj = (int)(word % (uint32_t)T.I);
-                if (need) load_item<G, QPL, FEAT>(T, cj, true, sub, cand);      // speculative: in flight during the search
-                const bool member = group_member<G>(cj, p.indices + seg, deg, need, sub, gw);
-                if (need && (!member || ++rejects >= p.max_rejects)) { j = cj; need = false; }
-            }
-            const float ut_uj = utility<G, QPL, FEAT>(uc, cand);
-            const float pu = ut_ui - ut_uj;
-            if (!done) {
-                sampled = s;
-                if (pu < min_pu) { min_pu = pu; min_j = j; neg = cand; }
-                if (pu < 1.0f) done = true;                                      // MARGIN (:149,263)
-            }
-        }
-
+        sample_negatives<G, QPL, FEAT, MT>(p, uc, ut_ui, row, u, seg, deg, 1, done, attempt, &mt_smem, sub, gw, neg, min_pu, min_j, sampled);
         // ---- gradient step: _rankfm.pyx:267-326 ----
-        const bool upd = valid && min_j >= 0;
-        if (valid && min_j < 0) bad = 1;
-        const float mult = upd ? __ldg(p.mult + sampled) : 0.f;                  // log((I-1)//sampled)/log(I), host table
-        const float d_outer = (float)(1.0 / (exp((double)min_pu) + 1.0));
-        const float smul = sw * mult;
-        if (upd && sub == 0) {   // log sigma(pu) = -softplus(-pu), evaluated without cancellation (:270)
-            ll_acc -= (double)(fmaxf(-min_pu, 0.f) + log1pf(__expf(-fabsf(min_pu))));
-            draws_acc += sampled;
-        }
-        const int j = upd ? min_j : 0;
-        if (p.trace && upd && sub == 0) { p.trace[2 * r] = min_j; p.trace[2 * r + 1] = sampled; }
-        float* urow = T.UT + (size_t)u * T.ldu;
-        float* irow = T.IT + (size_t)i * T.ldi;
-        float* jrow = T.IT + (size_t)j * T.ldi;
-        const float eta = p.eta, ra = p.reg_a, rb = p.reg_b;
-#define RFM_G(d, w) (eta * ((smul * (d_outer * (d))) - (rb_or_ra * (w))))
-
-        float4 dx = zero4();
-        if (FEAT) { dx.x = pos.x.x - neg.x.x; dx.y = pos.x.y - neg.x.y; dx.z = pos.x.z - neg.x.z; dx.w = pos.x.w - neg.x.w; }
-
-        // d u / d v_u = (v_i - v_j) + sum_q v_if[q] (x_if[i,q] - x_if[j,q])   (:292,303-305)
-        float4 dvu[QPL];
-#pragma unroll
-        for (int k = 0; k < QPL; ++k) {
-            dvu[k].x = pos.v[k].x - neg.v[k].x; dvu[k].y = pos.v[k].y - neg.v[k].y;
-            dvu[k].z = pos.v[k].z - neg.v[k].z; dvu[k].w = pos.v[k].w - neg.v[k].w;
-        }
-        if (FEAT && T.x_if_any) {
-            for (int q = 0; q < T.Q; ++q) {
-                const float dxq = __shfl_sync(0xffffffffu, get4(dx, q & 3), q >> 2, G);
-#pragma unroll
-                for (int k = 0; k < QPL; ++k) {
-                    const int qq = sub + k * G;
-                    if (upd && qq < T.NQ) {
-                        const float4 w = ld_cg4(T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq);
-                        dvu[k].x += w.x * dxq; dvu[k].y += w.y * dxq; dvu[k].z += w.z * dxq; dvu[k].w += w.w * dxq;
-                    }
-                }
-            }
-        }
-
-        float4 vu_new[QPL], dij_new[QPL];   // updated v_u and (v_i - v_j), needed by the feature-factor updates
-        {
-            const float rb_or_ra = ra;
-            if (upd && sub == 0) {           // item biases (:279-280)
-                red_add1(irow + T.Fp, RFM_G(1.0f, pos.w));
-                red_add1(jrow + T.Fp, RFM_G(-1.0f, neg.w));
-            }
-#pragma unroll
-            for (int k = 0; k < QPL; ++k) {
-                const int q = sub + k * G;
-                float4 du, di, dj;
-                du.x = RFM_G(dvu[k].x, uc.vu[k].x); du.y = RFM_G(dvu[k].y, uc.vu[k].y);
-                du.z = RFM_G(dvu[k].z, uc.vu[k].z); du.w = RFM_G(dvu[k].w, uc.vu[k].w);
-                di.x = RFM_G(uc.a[k].x, pos.v[k].x); di.y = RFM_G(uc.a[k].y, pos.v[k].y);
-                di.z = RFM_G(uc.a[k].z, pos.v[k].z); di.w = RFM_G(uc.a[k].w, pos.v[k].w);
-                dj.x = RFM_G(-uc.a[k].x, neg.v[k].x); dj.y = RFM_G(-uc.a[k].y, neg.v[k].y);
-                dj.z = RFM_G(-uc.a[k].z, neg.v[k].z); dj.w = RFM_G(-uc.a[k].w, neg.v[k].w);
-                if (upd && q < T.NQ) {
-                    red_add4(urow + 4 * q, du);
-                    red_add4(irow + 4 * q, di);
-                    red_add4(jrow + 4 * q, dj);
-                }
-                if (FEAT) {
-                    vu_new[k].x = uc.vu[k].x + du.x; vu_new[k].y = uc.vu[k].y + du.y;
-                    vu_new[k].z = uc.vu[k].z + du.z; vu_new[k].w = uc.vu[k].w + du.w;
-                    dij_new[k].x = (pos.v[k].x + di.x) - (neg.v[k].x + dj.x); dij_new[k].y = (pos.v[k].y + di.y) - (neg.v[k].y + dj.y);
-                    dij_new[k].z = (pos.v[k].z + di.z) - (neg.v[k].z + dj.z); dij_new[k].w = (pos.v[k].w + di.w) - (neg.v[k].w + dj.w);
-                }
-            }
-        }
-        if (FEAT) {
-            const float rb_or_ra = rb;
-            if (T.x_if_any) {
-                if (upd && 4 * sub < T.Qp) {                                   // w_if, every q (:283-286)
-                    const float4 w = ld_cg4(T.GP + 4 * sub);
-                    float4 d;
-                    d.x = RFM_G(dx.x, w.x); d.y = RFM_G(dx.y, w.y); d.z = RFM_G(dx.z, w.z); d.w = RFM_G(dx.w, w.w);
-                    red_add4(T.GP + 4 * sub, d);
-                }
-            }
-            if (T.x_uf_any) {                                                  // v_uf[p] for x_uf[u,p] != 0 (:313-318)
-                for (int pp = 0; pp < T.P; ++pp) {
-                    const float xp = __shfl_sync(0xffffffffu, get4(uc.xu, pp & 3), pp >> 2, G);
-                    const bool nz = xp != 0.0f;               // predicate, not `continue`: other groups of the warp still need the shuffle
-#pragma unroll
-                    for (int k = 0; k < QPL; ++k) {
-                        const int q = sub + k * G;
-                        if (upd && nz && q < T.NQ) {
-                            float* wp = T.GP + T.gp_vuf + (size_t)pp * T.Fp + 4 * q;
-                            const float4 w = ld_cg4(wp);
-                            float4 d;
-                            d.x = RFM_G(xp * dij_new[k].x, w.x); d.y = RFM_G(xp * dij_new[k].y, w.y);
-                            d.z = RFM_G(xp * dij_new[k].z, w.z); d.w = RFM_G(xp * dij_new[k].w, w.w);
-                            red_add4(wp, d);
-                        }
-                    }
-                }
-            }
-            if (T.x_if_any) {                                                  // v_if[q] for dx[q] != 0 (:321-326)
-                for (int q = 0; q < T.Q; ++q) {
-                    const float dxq = __shfl_sync(0xffffffffu, get4(dx, q & 3), q >> 2, G);
-                    const bool nz = dxq != 0.0f;
-#pragma unroll
-                    for (int k = 0; k < QPL; ++k) {
-                        const int qq = sub + k * G;
-                        if (upd && nz && qq < T.NQ) {
-                            float* wp = T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq;
-                            const float4 w = ld_cg4(wp);
-                            float4 d;
-                            d.x = RFM_G(dxq * vu_new[k].x, w.x); d.y = RFM_G(dxq * vu_new[k].y, w.y);
-                            d.z = RFM_G(dxq * vu_new[k].z, w.z); d.w = RFM_G(dxq * vu_new[k].w, w.w);
-                            red_add4(wp, d);
-                        }
-                    }
-                }
-            }
-        }
-#undef RFM_G
-        if (serial) { __threadfence(); __syncwarp(); }   // next step must observe this step's reductions
+        apply_update<G, QPL, FEAT, true>(p, uc, pos, neg, u, i, min_j, sw, sampled, min_pu, valid, r, sub, acc);
+        __threadfence(); __syncwarp();          // the next step must observe this step's reductions
     }
-
-    // ---- epoch accumulators ----
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        ll_acc += __shfl_xor_sync(0xffffffffu, ll_acc, off);
-        draws_acc += __shfl_xor_sync(0xffffffffu, draws_acc, off);
-        bad |= __shfl_xor_sync(0xffffffffu, bad, off);
-    }
-    if (lane == 0) {
-        atomicAdd(&p.acc->ll, ll_acc);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&p.acc->draws), (unsigned long long)draws_acc);
-        if (bad) atomicOr(&p.acc->bad, 1);
-    }
+    flush_acc(acc, p.acc);
     if (MT) {
         __syncwarp();
         for (int k = lane; k < kMtN; k += 32) p.mt->s[k] = mt_smem.s[k];
@@ -243,29 +74,201 @@ __global__ void __launch_bounds__(kTrainThreads) sgd_epoch_kernel(const TrainPar
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// production schedule: TMA-staged pipeline
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct Tuple {            // one positive with its first negative candidate, produced by the front end (one per lane)
+    int u, i, j, row;     // row < 0: past the end of the epoch
+    float sw;
+    uint32_t attempt;     // Philox words consumed so far for this positive
+};
+
+__device__ __forceinline__ bool lane_member(int cand, const int32_t* __restrict__ items, int deg)
+{
+    int lo = 0, hi = deg - 1;
+    while (lo <= hi) {
+        const int md = (lo + hi) >> 1;
+        const int e = __ldg(items + md);
+        if (e == cand) return true;
+        if (e < cand) lo = md + 1; else hi = md - 1;
+    }
+    return false;
+}
+
+__device__ __forceinline__ Tuple front_end(const TrainParams& p, long long r)
+{
+    Tuple t;
+    t.u = t.i = t.j = 0; t.row = -1; t.sw = 0.f; t.attempt = 0u;
+    if (r < p.N) {
+        const int row = p.perm ? __ldg(p.perm + r) : (int)feistel_perm(p.feistel, r);
+        const int2 ui = __ldg(p.interactions + row);
+        t.row = row; t.u = ui.x; t.i = ui.y;
+        t.sw = __ldg(p.sample_weight + row);
+        long long seg = 0; int deg = 0;
+        if (!p.bitmap) { seg = __ldg(p.indptr + ui.x); deg = (int)(__ldg(p.indptr + ui.x + 1) - seg); }
+        Philox4 blk = {0u, 0u, 0u, 0u};
+        int rejects = 0;
+        for (;;) {                                           // first draw of the positive (:250-253)
+            if ((t.attempt & 3u) == 0u) blk = philox4x32_10((uint32_t)row, p.epoch_key, t.attempt >> 2, 0u, p.k0, p.k1);
+            const uint32_t c = t.attempt & 3u;
+            const uint32_t word = c == 0u ? blk.x : (c == 1u ? blk.y : (c == 2u ? blk.z : blk.w));
+            ++t.attempt;
+            const int cj = (int)__umulhi(word, (uint32_t)p.T.I);
+            const bool member = p.bitmap ? ((__ldg(p.bitmap + (size_t)ui.x * p.bitmap_words + (cj >> 5)) >> (cj & 31)) & 1u) != 0u
+                                         : lane_member(cj, p.indices + seg, deg);
+            t.j = cj;
+            if (!member || ++rejects >= p.max_rejects) break;
+        }
+    }
+    return t;
+}
+
+template <int G, int QPL, bool FEAT>
+__device__ __forceinline__ void smem_user(const Tables& T, const float* s, int sub, UserCtx<QPL>& c)
+{
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) { const int q = sub + k * G; c.vu[k] = q < T.NQ ? s4[q] : zero4(); }
+    if (FEAT) c.xu = 4 * sub < T.Pp ? s4[T.NQ + sub] : zero4();
+}
+template <int G, int QPL, bool FEAT>
+__device__ __forceinline__ void smem_item(const Tables& T, const float* s, int sub, ItemRow<QPL>& r)
+{
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) { const int q = sub + k * G; r.v[k] = q < T.NQ ? s4[q] : zero4(); }
+    r.w = s[T.Fp];
+    if (FEAT) r.x = 4 * sub < T.Qp ? s4[T.NQ + 1 + sub] : zero4();
+}
+
+constexpr int kPipeBarBytes = 128;      // up to 16 mbarriers per warp, keeps the stages 128-byte aligned
+
+template <int G, int QPL, bool FEAT>
+__global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kernel(const TrainParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Tables& T = p.T;
+    constexpr int GPW = 32 / G;                       // tuples processed per step (one per lane group)
+    constexpr int STEPS = 32 / GPW;                   // steps per batch of 32 tuples
+    const int lane = threadIdx.x & 31, sub = lane % G, gw = lane / G;
+    const int D = p.depth;
+    const int tuple_floats = T.ldu + 2 * T.ldi;
+    const uint32_t tuple_bytes = (uint32_t)tuple_floats * 4u;
+    const int stage_floats = GPW * tuple_floats;
+    unsigned char* wbase = smem_raw + (size_t)(threadIdx.x >> 5) * (kPipeBarBytes + (size_t)D * stage_floats * 4);
+    const uint32_t bars = smem_u32(wbase);
+    float* stages = reinterpret_cast<float*>(wbase + kPipeBarBytes);
+    if (lane == 0) {
+        for (int d = 0; d < D; ++d) mbar_init(bars + 8u * d, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long n_batches = (p.N + 31) / 32;
+    StepAcc acc;
+    uint32_t issued = 0, consumed = 0;                // running stage counters: stage = n % D, parity = (n / D) & 1
+
+    // stage the rows of step `step` of the batch held in `cur` (warp-collective)
+    auto issue = [&](const Tuple& cur, int step) {
+        const int k = step * GPW + gw;
+        const int tu = __shfl_sync(0xffffffffu, cur.u, k), ti = __shfl_sync(0xffffffffu, cur.i, k);
+        const int tj = __shfl_sync(0xffffffffu, cur.j, k), trow = __shfl_sync(0xffffffffu, cur.row, k);
+        const bool ok = trow >= 0;
+        const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, ok && sub == 0));
+        const uint32_t st = issued % (uint32_t)D;
+        const uint32_t bar = bars + 8u * st;
+        if (lane == 0) mbar_expect_tx(bar, nvalid * tuple_bytes);
+        __syncwarp();
+        if (ok && sub < 3) {
+            const uint32_t dst = smem_u32(stages + (size_t)st * stage_floats + (size_t)gw * tuple_floats);
+            if (sub == 0)      bulk_g2s(dst, T.UT + (size_t)tu * T.ldu, (uint32_t)T.ldu * 4u, bar);
+            else if (sub == 1) bulk_g2s(dst + (uint32_t)T.ldu * 4u, T.IT + (size_t)ti * T.ldi, (uint32_t)T.ldi * 4u, bar);
+            else               bulk_g2s(dst + (uint32_t)(T.ldu + T.ldi) * 4u, T.IT + (size_t)tj * T.ldi, (uint32_t)T.ldi * 4u, bar);
+        }
+        ++issued;
+    };
+
+    Tuple cur = front_end(p, warp_global * 32 + lane);
+    for (long long b = warp_global; b < n_batches; b += n_warps) {
+        const int ahead = D < STEPS ? D : STEPS;
+        for (int d = 0; d < ahead; ++d) issue(cur, d);
+        // next batch's front end overlaps with the copies just issued
+        const Tuple nxt = front_end(p, (b + n_warps) * 32 + lane);
+
+        for (int step = 0; step < STEPS; ++step) {
+            const int k = step * GPW + gw;
+            const int u = __shfl_sync(0xffffffffu, cur.u, k), i = __shfl_sync(0xffffffffu, cur.i, k);
+            const int j1 = __shfl_sync(0xffffffffu, cur.j, k), row = __shfl_sync(0xffffffffu, cur.row, k);
+            const float sw = __shfl_sync(0xffffffffu, cur.sw, k);
+            uint32_t attempt = __shfl_sync(0xffffffffu, cur.attempt, k);
+            const bool valid = row >= 0;
+            const uint32_t st = consumed % (uint32_t)D, parity = (consumed / (uint32_t)D) & 1u;
+            while (!mbar_try_wait(bars + 8u * st, parity)) { }
+            ++consumed;
+
+            const float* base = stages + (size_t)st * stage_floats + (size_t)gw * tuple_floats;
+            UserCtx<QPL> uc;
+            ItemRow<QPL> pos, neg;
+            if (valid) {
+                smem_user<G, QPL, FEAT>(T, base, sub, uc);
+                smem_item<G, QPL, FEAT>(T, base + T.ldu, sub, pos);
+                smem_item<G, QPL, FEAT>(T, base + T.ldu + T.ldi, sub, neg);
+            } else {
+#pragma unroll
+                for (int q = 0; q < QPL; ++q) { uc.vu[q] = zero4(); pos.v[q] = zero4(); neg.v[q] = zero4(); }
+                uc.xu = zero4(); pos.x = zero4(); neg.x = zero4(); pos.w = 0.f; neg.w = 0.f;
+            }
+            user_precompute<G, QPL, FEAT>(T, valid, sub, uc);
+            const float ut_ui = utility<G, QPL, FEAT>(uc, pos);
+            const float pu1 = ut_ui - utility<G, QPL, FEAT>(uc, neg);   // the group reductions also order every smem read of this stage
+            // draw 1 of the reference's loop (:247-264); NaN leaves min_index at -1 like `pu < 1e6` failing
+            int sampled = 1;
+            float min_pu = 1e6f;
+            int min_j = -1;
+            if (pu1 < min_pu) { min_pu = pu1; min_j = j1; }
+            bool done = !valid || pu1 < 1.0f;
+            __syncwarp();
+            if (step + D < STEPS) issue(cur, step + D);      // refill the stage just drained
+            if (p.max_samples > 1 && __any_sync(0xffffffffu, !done)) {
+                long long seg = 0; int deg = 0;
+                if (!done && !p.bitmap) { seg = __ldg(p.indptr + u); deg = (int)(__ldg(p.indptr + u + 1) - seg); }
+                sample_negatives<G, QPL, FEAT, false>(p, uc, ut_ui, row, u, seg, deg, 2, done, attempt, nullptr, sub, gw, neg, min_pu, min_j, sampled);
+            }
+            apply_update<G, QPL, FEAT, false>(p, uc, pos, neg, u, i, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc);
+        }
+        cur = nxt;
+    }
+    flush_acc(acc, p.acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // launch: pick the group geometry from the widest row section
 // ---------------------------------------------------------------------------------------------------------------
-template <int G, int QPL>
-static cudaError_t launch_gq(const TrainParams& p, int grid, cudaStream_t st)
-{
-    const bool feat = p.T.x_uf_any || p.T.x_if_any;
-    const bool mt = p.mt != nullptr;
-    const dim3 g(p.serial ? 1 : grid), b(p.serial ? 32 : kTrainThreads);
-    if (feat) { if (mt) sgd_epoch_kernel<G, QPL, true, true><<<g, b, 0, st>>>(p); else sgd_epoch_kernel<G, QPL, true, false><<<g, b, 0, st>>>(p); }
-    else      { if (mt) sgd_epoch_kernel<G, QPL, false, true><<<g, b, 0, st>>>(p); else sgd_epoch_kernel<G, QPL, false, false><<<g, b, 0, st>>>(p); }
-    return cudaGetLastError();
-}
-
-template <int G, int QPL>
-static int occ_gq(const TrainParams& p)
-{
-    const bool feat = p.T.x_uf_any || p.T.x_if_any;
-    int n = 0;
-    if (feat) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sgd_epoch_kernel<G, QPL, true, false>, kTrainThreads, 0);
-    else      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sgd_epoch_kernel<G, QPL, false, false>, kTrainThreads, 0);
-    return n;
-}
-
 int train_group_size(const Tables& T, int* qpl_out)
 {
     const int widest = max(T.Fp, max(T.Pp, T.Qp)) / 4;   // quads
@@ -274,6 +277,61 @@ int train_group_size(const Tables& T, int* qpl_out)
     int qpl = (T.NQ + G - 1) / G;
     if (qpl_out) *qpl_out = qpl;
     return G;
+}
+
+// depth of the staging pipeline: ~8 KB of rows in flight per warp, 2..8 stages
+static int pipe_depth(const Tables& T, int G)
+{
+    const int stage_bytes = (32 / G) * (T.ldu + 2 * T.ldi) * 4;
+    int d = 8192 / stage_bytes;
+    return d < 2 ? 2 : (d > 8 ? 8 : d);
+}
+static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
+{
+    const size_t stage_bytes = (size_t)(32 / G) * (T.ldu + 2 * T.ldi) * 4;
+    return (size_t)(kTrainThreads / 32) * (kPipeBarBytes + (size_t)depth * stage_bytes);
+}
+
+template <int G, int QPL>
+static cudaError_t launch_gq(const TrainParams& p0, int grid, cudaStream_t st)
+{
+    TrainParams p = p0;
+    const bool feat = p.T.x_uf_any || p.T.x_if_any;
+    if (p.serial) {
+        const bool mt = p.mt != nullptr;
+        if (feat) { if (mt) sgd_serial_kernel<G, QPL, true, true><<<1, 32, 0, st>>>(p); else sgd_serial_kernel<G, QPL, true, false><<<1, 32, 0, st>>>(p); }
+        else      { if (mt) sgd_serial_kernel<G, QPL, false, true><<<1, 32, 0, st>>>(p); else sgd_serial_kernel<G, QPL, false, false><<<1, 32, 0, st>>>(p); }
+        return cudaGetLastError();
+    }
+    p.depth = pipe_depth(p.T, G);
+    const size_t smem = pipe_smem_bytes(p.T, G, p.depth);
+    cudaError_t e;
+    if (feat) {
+        e = cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sgd_pipe_kernel<G, QPL, true><<<grid, kTrainThreads, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sgd_pipe_kernel<G, QPL, false><<<grid, kTrainThreads, smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+template <int G, int QPL>
+static int occ_gq(const TrainParams& p)
+{
+    const bool feat = p.T.x_uf_any || p.T.x_if_any;
+    const size_t smem = pipe_smem_bytes(p.T, G, pipe_depth(p.T, G));
+    int n = 0;
+    if (feat) {
+        cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sgd_pipe_kernel<G, QPL, true>, kTrainThreads, smem);
+    } else {
+        cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sgd_pipe_kernel<G, QPL, false>, kTrainThreads, smem);
+    }
+    return n;
 }
 
 cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st)
@@ -302,6 +360,26 @@ int sgd_epoch_blocks_per_sm(const TrainParams& p)
         case 16: return occ_gq<16, 1>(p);
         default: return qpl == 1 ? occ_gq<32, 1>(p) : (qpl == 2 ? occ_gq<32, 2>(p) : occ_gq<32, 4>(p));
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-user membership bitmap (small catalogues): replaces the search of user_items by one bit test per draw
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void build_bitmap_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int U, uint32_t* __restrict__ bitmap, int words)
+{
+    const long long nnz = indptr[U];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = U;                                   // owner of CSR slot e: last u with indptr[u] <= e
+        while (hi - lo > 1) { const int md = (lo + hi) >> 1; if (indptr[md] <= e) lo = md; else hi = md; }
+        const int it = indices[e];
+        atomicOr(bitmap + (size_t)lo * words + (it >> 5), 1u << (it & 31));
+    }
+}
+
+cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bitmap, int words, cudaStream_t st)
+{
+    build_bitmap_kernel<<<148 * 4, 256, 0, st>>>(indptr, indices, U, bitmap, words);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

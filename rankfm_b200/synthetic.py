@@ -13,36 +13,40 @@ CONFIGS = {
                  label="MovieLens-1M shape synthetic (6040x3706, 1M interactions), factors=20, warp, max_samples=20, 20 epochs"),
     "cfg3": dict(U=1_000_000, I=200_000, N=50_000_000, F=64, loss="warp", max_samples=10, epochs=2, P=8, Q=8,
                  label="1M users x 200k items, 50M Zipf interactions, factors=64, warp, 8+8 side features"),
+    "cfg4m": dict(U=1_250_000, I=1_000_000, N=16_000_000, F=128, loss="bpr", max_samples=1, epochs=3, P=0, Q=0,
+                  label="DRAM-resident slice of cfg4: 1.25M users x 1M items, 16M interactions, factors=128, bpr (tables 1.2 GB >> L2)"),
     "cfg4s": dict(U=1_250_000, I=1_000_000, N=62_500_000, F=128, loss="bpr", max_samples=1, epochs=2, P=0, Q=0,
                   label="per-GPU shard of 10M users x 1M items, 500M interactions, factors=128, bpr (1/8 of cfg4)"),
 }
 
 
-def zipf_interactions(U, I, N, seed=42, a_u=0.6, a_i=1.0, oversample=1.0, offset_users=0):
-    """int32 [n,2] unique (user,item) pairs, n ~= N (exactly N when enough unique pairs were drawn)"""
+def zipf_interactions(U, I, N, seed=42, a_u=0.6, a_i=1.0, offset_users=0):
+    """int32 [n,2] unique (user,item) pairs in random order, n == N whenever enough unique pairs exist"""
     rng = np.random.default_rng(seed)
     pu = 1.0 / np.arange(1, U + 1) ** a_u
     pi = 1.0 / np.arange(1, I + 1) ** a_i
     cu, ci = np.cumsum(pu / pu.sum()), np.cumsum(pi / pi.sum())
     keys = np.zeros(0, dtype=np.int64)
-    want = N
-    draw = int(N * (1.15 + oversample * 0.5)) + 1024
+    draw = int(N * 1.25) + 1024
     for _ in range(8):
-        u = np.minimum(np.searchsorted(cu, rng.random(draw)), U - 1)
-        i = np.minimum(np.searchsorted(ci, rng.random(draw)), I - 1)
-        keys = np.unique(np.concatenate([keys, u.astype(np.int64) * I + i]))
-        if len(keys) >= want:
+        u = np.minimum(np.searchsorted(cu, rng.random(draw, dtype=np.float32).astype(np.float64)), U - 1)
+        i = np.minimum(np.searchsorted(ci, rng.random(draw, dtype=np.float32).astype(np.float64)), I - 1)
+        k = u.astype(np.int64) * I + i
+        k.sort()
+        k = k[np.concatenate([[True], k[1:] != k[:-1]])]
+        keys = k if len(keys) == 0 else np.union1d(keys, k)
+        if len(keys) >= N:
             break
-    if len(keys) > want:
-        keys = rng.choice(keys, want, replace=False)
+    order = rng.permutation(len(keys))[:N]                 # unbiased trim + final shuffle in one pass
+    keys = keys[order]
     u, i = keys // I, keys % I
-    u = rng.permutation(U)[u]
+    u = rng.permutation(U)[u]                               # popularity must not be index-ordered
     i = rng.permutation(I)[i]
-    _, u = np.unique(u, return_inverse=True)
-    _, i = np.unique(i, return_inverse=True)
-    X = np.stack([u + offset_users, i], axis=1).astype(np.int32)
-    rng.shuffle(X)
-    return np.ascontiguousarray(X)
+    for col, n in ((u, U), (i, I)):                         # re-index to the observed uniques (rankfm.py:115-116)
+        present = np.zeros(n, dtype=bool)
+        present[col] = True
+        col[:] = (np.cumsum(present) - 1)[col]
+    return np.ascontiguousarray(np.stack([u + offset_users, i], axis=1).astype(np.int32))
 
 
 def init_weights(U, I, F, P=0, Q=0, seed=0, sigma=0.1, alpha=0.01, beta=0.1):
