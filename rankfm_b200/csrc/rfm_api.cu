@@ -311,7 +311,9 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
     {
         TrainParams tp{};
         tp.T = T;
-        const int per_sm = std::max(1, sgd_epoch_blocks_per_sm(tp));
+        tp.max_samples = p->max_samples;
+        int per_sm = std::max(1, sgd_epoch_blocks_per_sm(tp));
+        if (const char* e = getenv("RANKFM_B200_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // experiments
         s->grid = s->n_sm * per_sm;
     }
     if (p->world > 1) {
@@ -503,6 +505,8 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     tp.mt = p.sampler == RFM_SAMPLER_MT ? s->d_mt : nullptr;
     tp.trace = s->d_trace;
     std::vector<float> etas((size_t)epochs);
+    const char* spec_s = getenv("RANKFM_B200_SPEC");          // 0 (default) = adaptive, else force 1 / 2 / 4
+    const int spec_env = spec_s ? atoi(spec_s) : 0;
     // Hogwild staleness cap: never keep more than 1/16 of an epoch in flight, so that on small inputs the schedule
     // degrades towards sequential SGD instead of one giant stale batch (large inputs always get the full machine).
     // A warp of the pipelined kernel holds one batch of 32 positives.
@@ -522,6 +526,8 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
         tp.eta = eta;
         tp.epoch_key = (uint32_t)(s->epochs_done + e);
         tp.acc = s->d_acc + e;
+        tp.prev_acc = e > 0 ? s->d_acc + (e - 1) : nullptr;
+        tp.spec = tp.serial ? 4 : spec_env;
         if (p.order == RFM_ORDER_HOST) {
             CU(cudaMemcpyAsync(s->d_perm, perms + (size_t)e * s->N, (size_t)s->N * 4, cudaMemcpyHostToDevice, s->st));
             tp.perm = s->d_perm;

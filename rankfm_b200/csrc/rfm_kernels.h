@@ -32,6 +32,8 @@ struct TrainParams {
     float eta, reg_a, reg_b;
     int32_t max_samples, max_rejects, serial;
     int32_t depth;           // stages of the TMA row pipeline (set by the launcher)
+    int32_t spec;            // WARP sampler look-ahead: 1, 2, 4 attempts per round; 0 = choose from prev_acc
+    const EpochAcc* prev_acc;   // previous epoch's record (device), or nullptr
     uint32_t k0, k1, epoch_key;
     MtState* mt;             // non-null -> MT19937 sampler (serial only)
     EpochAcc* acc;

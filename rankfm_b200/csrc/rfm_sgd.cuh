@@ -12,8 +12,11 @@ namespace rfm {
 
 struct StepAcc {
     double ll = 0.0;          // sum log sigma(pairwise utility)
-    long long draws = 0;      // negatives evaluated
+    float ll_f = 0.f;         // short-run float partial of the same sum, folded into `ll` by fold()
+    int draws = 0;            // negatives evaluated (folded into draws64 by fold())
+    long long draws64 = 0;
     int bad = 0;              // a positive whose pairwise utilities were all NaN
+    __device__ __forceinline__ void fold() { ll += (double)ll_f; ll_f = 0.f; draws64 += draws; draws = 0; }
 };
 
 // is item `cj` in user u's observed set?  bitmap (small catalogues) or (G+1)-ary search of the sorted CSR segment
@@ -66,13 +69,88 @@ __device__ __forceinline__ void sample_negatives(const TrainParams& p, const Use
     }
 }
 
+// Philox-only variant of the loop above with speculative look-ahead: up to `spec` (1, 2 or 4) consecutive attempts of
+// one Philox block are resolved together -- their membership words and candidate rows are all in flight at once, then
+// they are consumed strictly in attempt order, so the accepted draws, their count and the arg-min are exactly those of
+// the sequential loop (attempts past the terminating draw are simply discarded, like unread words of the block).
+// Cuts the dependent-latency chain of a WARP positive from one L2/HBM round trip per draw to one per `spec` draws.
+// `s` = draws already made for this positive (the caller made draw 1 from the prefetched candidate).
+template <int G, int QPL, bool FEAT>
+__device__ __forceinline__ void sample_negatives_spec(const TrainParams& p, const UserCtx<QPL>& uc, float ut_ui, int row, int u, long long seg, int deg,
+                                                      int s, bool& done, uint32_t& attempt, int spec, int sub, int gw,
+                                                      ItemRow<QPL>& neg, float& min_pu, int& min_j, int& sampled)
+{
+    constexpr int KMAX = (QPL == 1) ? 4 : 2;
+    const Tables& T = p.T;
+    int rejects = 0;
+    while (__any_sync(0xffffffffu, !done)) {
+        const Philox4 blk = philox4x32_10((uint32_t)row, p.epoch_key, attempt >> 2, 0u, p.k0, p.k1);
+        const int off = (int)(attempt & 3u);
+        const int navail = min(4 - off, spec);                     // attempts this group resolves in this round
+        ItemRow<QPL> cand[KMAX];
+        int cj[KMAX];
+        uint32_t mword[KMAX];
+#pragma unroll
+        for (int w = 0; w < KMAX; ++w) {
+            if (w >= spec) break;                                  // warp-uniform
+            const bool live = !done && w < navail;
+            const int c = off + w;
+            const uint32_t word = c == 0 ? blk.x : (c == 1 ? blk.y : (c == 2 ? blk.z : blk.w));
+            cj[w] = (int)__umulhi(word, (uint32_t)T.I);
+            load_item<G, QPL, FEAT>(T, cj[w], live, sub, cand[w]);
+            mword[w] = (live && p.bitmap) ? __ldg(p.bitmap + (size_t)u * p.bitmap_words + (cj[w] >> 5)) : 0u;
+        }
+#pragma unroll
+        for (int w = 0; w < KMAX; ++w) {
+            if (w >= spec) break;
+            const bool live = !done && w < navail;
+            bool member;
+            if (p.bitmap) member = ((mword[w] >> (cj[w] & 31)) & 1u) != 0u;
+            else member = group_member<G>(cj[w], p.indices + seg, deg, live, sub, gw);
+            const float pu = ut_ui - utility<G, QPL, FEAT>(uc, cand[w]);
+            if (live) {
+                ++attempt;
+                if (member && ++rejects < p.max_rejects) {
+                    // observed item: rejected, the next attempt belongs to the same draw
+                } else {
+                    rejects = 0;
+                    sampled = ++s;
+                    if (pu < min_pu) { min_pu = pu; min_j = cj[w]; neg = cand[w]; }
+                    if (pu < 1.0f || s >= p.max_samples) done = true;          // MARGIN (:149,263) / loop bound (:247)
+                }
+            }
+        }
+    }
+}
+
+// Where the row deltas of one step go.
+//   RedSink   straight to HBM/L2 as per-lane vector reductions (REDG.E.ADD.F32x4)           -- serial schedule
+//   SmemSink  into the shared-memory slot the rows were staged in; the caller then ships each delta row with ONE TMA
+//             bulk reduction (cp.reduce.async.bulk ... .add.f32 -> UBLKRED) instead of ~33 lane reductions per row
+struct RedSink {
+    float *urow, *irow, *jrow;
+    int Fp;
+    __device__ __forceinline__ void user(int q, float4 d) const { red_add4(urow + 4 * q, d); }
+    __device__ __forceinline__ void item_i(int q, float4 d) const { red_add4(irow + 4 * q, d); }
+    __device__ __forceinline__ void item_j(int q, float4 d) const { red_add4(jrow + 4 * q, d); }
+    __device__ __forceinline__ void bias(float di, float dj) const { red_add1(irow + Fp, di); red_add1(jrow + Fp, dj); }
+};
+struct SmemSink {
+    float4 *su, *si, *sj;     // the tuple's three row slots in shared memory (deltas overwrite the staged rows)
+    int nq;                   // Fp / 4
+    __device__ __forceinline__ void user(int q, float4 d) const { su[q] = d; }
+    __device__ __forceinline__ void item_i(int q, float4 d) const { si[q] = d; }
+    __device__ __forceinline__ void item_j(int q, float4 d) const { sj[q] = d; }
+    __device__ __forceinline__ void bias(float di, float dj) const { si[nq] = make_float4(di, 0.f, 0.f, 0.f); sj[nq] = make_float4(dj, 0.f, 0.f, 0.f); }
+};
+
 // One gradient step on (u, i, j): reads nothing but GP (feature parameters) from memory, everything else arrives in
 // registers; writes go out as vector reductions.  Update formula and operand association follow the generated C of the
 // reference:  w += eta * (((sw*mult) * (d_outer*d)) - (2reg * w)).
-template <int G, int QPL, bool FEAT, bool EXACT>
+template <int G, int QPL, bool FEAT, bool EXACT, typename Sink>
 __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx<QPL>& uc, const ItemRow<QPL>& pos, const ItemRow<QPL>& neg,
-                                             int u, int i, int min_j, float sw, int sampled, float min_pu, bool valid, long long r,
-                                             int sub, StepAcc& acc)
+                                             int min_j, float sw, int sampled, float min_pu, bool valid, long long r,
+                                             int sub, StepAcc& acc, const Sink& sink)
 {
     const Tables& T = p.T;
     const bool upd = valid && min_j >= 0;
@@ -80,19 +158,23 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
     const float mult = upd ? __ldg(p.mult + sampled) : 0.f;                  // log((I-1)//sampled)/log(I), host table (:269)
     // d_outer = 1/(exp(pu)+1) (:276).  Serial/replay schedules keep the reference's double-precision libm path;
     // the Hogwild schedule uses the SFU (ex2 + rcp, ~1e-6 relative), far below its own scheduling noise.
-    const float d_outer = EXACT ? (float)(1.0 / (exp((double)min_pu) + 1.0)) : __frcp_rn(__expf(min_pu) + 1.0f);
-    const float smul = sw * mult;
-    if (upd && sub == 0) {   // log sigma(pu) = -softplus(-pu), evaluated without cancellation (:270)
-        acc.ll -= (double)(fmaxf(-min_pu, 0.f) + log1pf(__expf(-fabsf(min_pu))));
-        acc.draws += sampled;
+    float d_outer, ll_term;
+    if (EXACT) {
+        d_outer = (float)(1.0 / (exp((double)min_pu) + 1.0));
+        ll_term = -(fmaxf(-min_pu, 0.f) + log1pf(__expf(-fabsf(min_pu))));       // log sigma(pu) without cancellation (:270)
+    } else {
+        const float t = __expf(-fabsf(min_pu));               // one ex2 shared by the sigmoid and the log-likelihood
+        const float rcp = __frcp_rn(1.0f + t);
+        d_outer = min_pu > 0.f ? t * rcp : rcp;
+        ll_term = fminf(min_pu, 0.f) - __logf(1.0f + t);
     }
-    const int j = upd ? min_j : 0;
+    const float smul = sw * mult;
+    if (upd) { acc.ll_f += ll_term; acc.draws += sampled; }  // every lane of the group adds the same value; flush_acc keeps lane `sub==0`
     if (p.trace && upd && sub == 0) { p.trace[2 * r] = min_j; p.trace[2 * r + 1] = sampled; }
-    float* urow = T.UT + (size_t)u * T.ldu;
-    float* irow = T.IT + (size_t)i * T.ldi;
-    float* jrow = T.IT + (size_t)j * T.ldi;
     const float eta = p.eta, ra = p.reg_a, rb = p.reg_b;
-#define RFM_G(d, w) (eta * ((smul * (d_outer * (d))) - (rb_or_ra * (w))))
+    // EXACT keeps the reference's operand association; the Hogwild schedule folds it into two FMAs per element
+    const float ec = eta * (smul * d_outer);
+#define RFM_G(d, w) (EXACT ? (eta * ((smul * (d_outer * (d))) - (rb_or_ra * (w)))) : fmaf(ec, (d), -(eta * rb_or_ra) * (w)))
 
     float4 dx = zero4();
     if (FEAT) { dx.x = pos.x.x - neg.x.x; dx.y = pos.x.y - neg.x.y; dx.z = pos.x.z - neg.x.z; dx.w = pos.x.w - neg.x.w; }
@@ -122,8 +204,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
     {
         const float rb_or_ra = ra;
         if (upd && sub == 0) {           // item biases (:279-280)
-            red_add1(irow + T.Fp, RFM_G(1.0f, pos.w));
-            red_add1(jrow + T.Fp, RFM_G(-1.0f, neg.w));
+            sink.bias(RFM_G(1.0f, pos.w), RFM_G(-1.0f, neg.w));
         }
 #pragma unroll
         for (int k = 0; k < QPL; ++k) {
@@ -136,9 +217,9 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
             dj.x = RFM_G(-uc.a[k].x, neg.v[k].x); dj.y = RFM_G(-uc.a[k].y, neg.v[k].y);
             dj.z = RFM_G(-uc.a[k].z, neg.v[k].z); dj.w = RFM_G(-uc.a[k].w, neg.v[k].w);
             if (upd && q < T.NQ) {
-                red_add4(urow + 4 * q, du);
-                red_add4(irow + 4 * q, di);
-                red_add4(jrow + 4 * q, dj);
+                sink.user(q, du);
+                sink.item_i(q, di);
+                sink.item_j(q, dj);
             }
             if (FEAT) {
                 vu_new[k].x = uc.vu[k].x + du.x; vu_new[k].y = uc.vu[k].y + du.y;
@@ -198,18 +279,21 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
 #undef RFM_G
 }
 
-// fold the per-lane accumulators of a warp into the epoch record
+// fold the per-lane accumulators of a warp into the epoch record; lanes with sub != 0 hold copies of their group's sums
+template <int G>
 __device__ __forceinline__ void flush_acc(StepAcc& a, EpochAcc* out)
 {
+    a.fold();
+    if ((threadIdx.x & 31) % G != 0) { a.ll = 0.0; a.draws64 = 0; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         a.ll += __shfl_xor_sync(0xffffffffu, a.ll, off);
-        a.draws += __shfl_xor_sync(0xffffffffu, a.draws, off);
+        a.draws64 += __shfl_xor_sync(0xffffffffu, a.draws64, off);
         a.bad |= __shfl_xor_sync(0xffffffffu, a.bad, off);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&out->ll, a.ll);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&out->draws), (unsigned long long)a.draws);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&out->draws), (unsigned long long)a.draws64);
         if (a.bad) atomicOr(&out->bad, 1);
     }
 }

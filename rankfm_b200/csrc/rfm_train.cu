@@ -15,6 +15,8 @@
 //   sgd_serial_kernel  one lane group, positives strictly in order, optionally the reference's MT19937 stream:
 //                      exact replay of sequential SGD, used to pin the arithmetic against the oracle / the reference.
 // Both call the same sample_negatives / apply_update (rfm_sgd.cuh).
+#include <cstdlib>
+#include <cstring>
 #include "rfm_sgd.cuh"
 
 namespace rfm {
@@ -60,12 +62,15 @@ __global__ void __launch_bounds__(32) sgd_serial_kernel(const TrainParams p)
 #pragma unroll
         for (int k = 0; k < QPL; ++k) neg.v[k] = zero4();
         neg.x = zero4(); neg.w = 0.f;
-        sample_negatives<G, QPL, FEAT, MT>(p, uc, ut_ui, row, u, seg, deg, 1, done, attempt, &mt_smem, sub, gw, neg, min_pu, min_j, sampled);
+        if (MT) sample_negatives<G, QPL, FEAT, true>(p, uc, ut_ui, row, u, seg, deg, 1, done, attempt, &mt_smem, sub, gw, neg, min_pu, min_j, sampled);
+        else    sample_negatives_spec<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, 0, done, attempt, p.spec, sub, gw, neg, min_pu, min_j, sampled);
         // ---- gradient step: _rankfm.pyx:267-326 ----
-        apply_update<G, QPL, FEAT, true>(p, uc, pos, neg, u, i, min_j, sw, sampled, min_pu, valid, r, sub, acc);
+        const RedSink sink{T.UT + (size_t)u * T.ldu, T.IT + (size_t)i * T.ldi, T.IT + (size_t)(min_j >= 0 ? min_j : 0) * T.ldi, T.Fp};
+        apply_update<G, QPL, FEAT, true>(p, uc, pos, neg, min_j, sw, sampled, min_pu, valid, r, sub, acc, sink);
+        acc.fold();
         __threadfence(); __syncwarp();          // the next step must observe this step's reductions
     }
-    flush_acc(acc, p.acc);
+    flush_acc<G>(acc, p.acc);
     if (MT) {
         __syncwarp();
         for (int k = lane; k < kMtN; k += 32) p.mt->s[k] = mt_smem.s[k];
@@ -98,6 +103,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+
+// TMA bulk reduction shared -> global: global[0..bytes) += shared[0..bytes) as f32 (SASS: UBLKRED), bulk-group completion
+__device__ __forceinline__ void bulk_red_add_f32(void* dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct Tuple {            // one positive with its first negative candidate, produced by the front end (one per lane)
     int u, i, j, row;     // row < 0: past the end of the epoch
@@ -165,11 +181,12 @@ __device__ __forceinline__ void smem_item(const Tables& T, const float* s, int s
 
 constexpr int kPipeBarBytes = 128;      // up to 16 mbarriers per warp, keeps the stages 128-byte aligned
 
-template <int G, int QPL, bool FEAT>
-__global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kernel(const TrainParams p)
+template <int G, int QPL, bool FEAT, bool WARP, bool TRED>
+__global__ void __launch_bounds__(kTrainThreads, (QPL == 1 && !FEAT) ? 3 : (QPL <= 2 ? 2 : 1)) sgd_pipe_kernel(const TrainParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Tables& T = p.T;
+    constexpr bool TMA = true;                        // rows are staged by TMA bulk copies (the cp.async path lost: profiles/)
     constexpr int GPW = 32 / G;                       // tuples processed per step (one per lane group)
     constexpr int STEPS = 32 / GPW;                   // steps per batch of 32 tuples
     const int lane = threadIdx.x & 31, sub = lane % G, gw = lane / G;
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kern
     const uint32_t bars = smem_u32(wbase);
     float* stages = reinterpret_cast<float*>(wbase + kPipeBarBytes);
     if (lane == 0) {
-        for (int d = 0; d < D; ++d) mbar_init(bars + 8u * d, 1u);
+        for (int d = 0; d < D; ++d) mbar_init(bars + 8u * d, TMA ? 1u : 32u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -190,8 +207,20 @@ __global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kern
     const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long n_batches = (p.N + 31) / 32;
+    // look-ahead of the WARP sampler: follow the previous epoch's mean number of draws per positive (device-side,
+    // no host round trip); early epochs violate the margin at the first draw and would waste the look-ahead
+    int spec = p.spec;
+    if (spec == 0) {
+        spec = 1;
+        if (p.prev_acc) {
+            const long long prev = p.prev_acc->draws;
+            spec = prev >= 3 * p.N ? 4 : (prev >= 3 * p.N / 2 ? 2 : 1);
+        }
+    }
     StepAcc acc;
-    uint32_t issued = 0, consumed = 0;                // running stage counters: stage = n % D, parity = (n / D) & 1
+    uint32_t st_issue = 0, st_cons = 0, par_cons = 0;   // ring positions of the next stage to fill / to drain, and its parity
+    const uint32_t stage0 = smem_u32(stages);
+    const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
 
     // stage the rows of step `step` of the batch held in `cur` (warp-collective)
     auto issue = [&](const Tuple& cur, int step) {
@@ -199,18 +228,20 @@ __global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kern
         const int tu = __shfl_sync(0xffffffffu, cur.u, k), ti = __shfl_sync(0xffffffffu, cur.i, k);
         const int tj = __shfl_sync(0xffffffffu, cur.j, k), trow = __shfl_sync(0xffffffffu, cur.row, k);
         const bool ok = trow >= 0;
+        const uint32_t bar = bars + 8u * st_issue;
+        const uint32_t dst = stage0 + st_issue * stage_bytes + (uint32_t)gw * tuple_bytes;
+        const float* su = T.UT + (size_t)tu * T.ldu;
+        const float* si = T.IT + (size_t)ti * T.ldi;
+        const float* sj = T.IT + (size_t)tj * T.ldi;
         const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, ok && sub == 0));
-        const uint32_t st = issued % (uint32_t)D;
-        const uint32_t bar = bars + 8u * st;
         if (lane == 0) mbar_expect_tx(bar, nvalid * tuple_bytes);
         __syncwarp();
         if (ok && sub < 3) {
-            const uint32_t dst = smem_u32(stages + (size_t)st * stage_floats + (size_t)gw * tuple_floats);
-            if (sub == 0)      bulk_g2s(dst, T.UT + (size_t)tu * T.ldu, (uint32_t)T.ldu * 4u, bar);
-            else if (sub == 1) bulk_g2s(dst + (uint32_t)T.ldu * 4u, T.IT + (size_t)ti * T.ldi, (uint32_t)T.ldi * 4u, bar);
-            else               bulk_g2s(dst + (uint32_t)(T.ldu + T.ldi) * 4u, T.IT + (size_t)tj * T.ldi, (uint32_t)T.ldi * 4u, bar);
+            if (sub == 0)      bulk_g2s(dst, su, (uint32_t)T.ldu * 4u, bar);
+            else if (sub == 1) bulk_g2s(dst + (uint32_t)T.ldu * 4u, si, (uint32_t)T.ldi * 4u, bar);
+            else               bulk_g2s(dst + (uint32_t)(T.ldu + T.ldi) * 4u, sj, (uint32_t)T.ldi * 4u, bar);
         }
-        ++issued;
+        st_issue = st_issue + 1 == (uint32_t)D ? 0u : st_issue + 1;
     };
 
     Tuple cur = front_end(p, warp_global * 32 + lane);
@@ -227,11 +258,9 @@ __global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kern
             const float sw = __shfl_sync(0xffffffffu, cur.sw, k);
             uint32_t attempt = __shfl_sync(0xffffffffu, cur.attempt, k);
             const bool valid = row >= 0;
-            const uint32_t st = consumed % (uint32_t)D, parity = (consumed / (uint32_t)D) & 1u;
-            while (!mbar_try_wait(bars + 8u * st, parity)) { }
-            ++consumed;
-
-            const float* base = stages + (size_t)st * stage_floats + (size_t)gw * tuple_floats;
+            while (!mbar_try_wait(bars + 8u * st_cons, par_cons)) { }
+            const float* base = stages + (size_t)st_cons * stage_floats + (size_t)gw * tuple_floats;
+            if (++st_cons == (uint32_t)D) { st_cons = 0; par_cons ^= 1u; }
             UserCtx<QPL> uc;
             ItemRow<QPL> pos, neg;
             if (valid) {
@@ -244,8 +273,20 @@ __global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kern
                 uc.xu = zero4(); pos.x = zero4(); neg.x = zero4(); pos.w = 0.f; neg.w = 0.f;
             }
             user_precompute<G, QPL, FEAT>(T, valid, sub, uc);
-            const float ut_ui = utility<G, QPL, FEAT>(uc, pos);
-            const float pu1 = ut_ui - utility<G, QPL, FEAT>(uc, neg);   // the group reductions also order every smem read of this stage
+            float ut_ui = 0.f, pu1;
+            if (!WARP) {                       // BPR: only the difference is needed -> one group reduction instead of two
+                float part = 0.f;
+#pragma unroll
+                for (int q = 0; q < QPL; ++q) {
+                    const float4 d = make_float4(pos.v[q].x - neg.v[q].x, pos.v[q].y - neg.v[q].y, pos.v[q].z - neg.v[q].z, pos.v[q].w - neg.v[q].w);
+                    part = dot4(uc.a[q], d, part);
+                }
+                if (FEAT) part = dot4(uc.b, make_float4(pos.x.x - neg.x.x, pos.x.y - neg.x.y, pos.x.z - neg.x.z, pos.x.w - neg.x.w), part);
+                pu1 = (pos.w - neg.w) + group_sum<G>(part);
+            } else {
+                ut_ui = utility<G, QPL, FEAT>(uc, pos);
+                pu1 = ut_ui - utility<G, QPL, FEAT>(uc, neg);
+            }                                  // the group reductions also order every smem read of this stage
             // draw 1 of the reference's loop (:247-264); NaN leaves min_index at -1 like `pu < 1e6` failing
             int sampled = 1;
             float min_pu = 1e6f;
@@ -253,17 +294,47 @@ __global__ void __launch_bounds__(kTrainThreads, QPL == 1 ? 3 : 1) sgd_pipe_kern
             if (pu1 < min_pu) { min_pu = pu1; min_j = j1; }
             bool done = !valid || pu1 < 1.0f;
             __syncwarp();
-            if (step + D < STEPS) issue(cur, step + D);      // refill the stage just drained
-            if (p.max_samples > 1 && __any_sync(0xffffffffu, !done)) {
+            if (!TRED) { if (step + D < STEPS) issue(cur, step + D); }      // refill the stage just drained
+            if (WARP && __any_sync(0xffffffffu, !done)) {
                 long long seg = 0; int deg = 0;
                 if (!done && !p.bitmap) { seg = __ldg(p.indptr + u); deg = (int)(__ldg(p.indptr + u + 1) - seg); }
-                sample_negatives<G, QPL, FEAT, false>(p, uc, ut_ui, row, u, seg, deg, 2, done, attempt, nullptr, sub, gw, neg, min_pu, min_j, sampled);
+                sample_negatives_spec<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, 1, done, attempt, spec, sub, gw, neg, min_pu, min_j, sampled);
             }
-            apply_update<G, QPL, FEAT, false>(p, uc, pos, neg, u, i, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc);
+            const int jj = min_j >= 0 ? min_j : 0;
+            if (TRED) {
+                // deltas overwrite the staged rows of this tuple, then three bulk reductions ship them (one per row)
+                float4* slot = reinterpret_cast<float4*>(const_cast<float*>(base));
+                const int nu4 = T.ldu >> 2, ni4 = T.ldi >> 2;
+                const SmemSink sink{slot, slot + nu4, slot + nu4 + ni4, T.NQ};
+                if (FEAT && valid) {      // the read-only feature blocks must add 0
+                    if (4 * sub < T.Pp) slot[T.NQ + sub] = zero4();
+                    if (4 * sub < T.Qp) { slot[nu4 + T.NQ + 1 + sub] = zero4(); slot[nu4 + ni4 + T.NQ + 1 + sub] = zero4(); }
+                }
+                apply_update<G, QPL, FEAT, false>(p, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
+                fence_async_smem();
+                __syncwarp();
+                const bool upd = valid && min_j >= 0;
+                if (upd && sub < 3) {
+                    const uint32_t src = smem_u32(slot);
+                    if (sub == 0)      bulk_red_add_f32(T.UT + (size_t)u * T.ldu, src, (uint32_t)T.ldu * 4u);
+                    else if (sub == 1) bulk_red_add_f32(T.IT + (size_t)i * T.ldi, src + (uint32_t)T.ldu * 4u, (uint32_t)T.ldi * 4u);
+                    else               bulk_red_add_f32(T.IT + (size_t)jj * T.ldi, src + (uint32_t)(T.ldu + T.ldi) * 4u, (uint32_t)T.ldi * 4u);
+                }
+                if (sub < 3) bulk_commit();
+                // refill the stage drained one step ago: its reductions (the group before the one just committed) have had
+                // a whole step to read their source; the group just committed may still be reading
+                if (step >= 1 && step - 1 + D < STEPS) { if (sub < 3) bulk_wait_read1(); __syncwarp(); issue(cur, step - 1 + D); }
+            } else {
+                const RedSink sink{T.UT + (size_t)u * T.ldu, T.IT + (size_t)i * T.ldi, T.IT + (size_t)jj * T.ldi, T.Fp};
+                apply_update<G, QPL, FEAT, false>(p, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
+            }
         }
+        if (TRED) { if (sub < 3) bulk_wait_read0(); __syncwarp(); }   // the next batch refills every stage
+        acc.fold();
         cur = nxt;
     }
-    flush_acc(acc, p.acc);
+    if (TRED) bulk_wait_all();
+    flush_acc<G>(acc, p.acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -283,13 +354,51 @@ int train_group_size(const Tables& T, int* qpl_out)
 static int pipe_depth(const Tables& T, int G)
 {
     const int stage_bytes = (32 / G) * (T.ldu + 2 * T.ldi) * 4;
-    int d = 8192 / stage_bytes;
+    int d = 4096 / stage_bytes;                                        // measured: shallow rings win (profiles/r01_depth_sweep.md)
+    if (const char* e = getenv("RANKFM_B200_DEPTH")) d = atoi(e);      // experiments
     return d < 2 ? 2 : (d > 8 ? 8 : d);
 }
 static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
 {
     const size_t stage_bytes = (size_t)(32 / G) * (T.ldu + 2 * T.ldi) * 4;
     return (size_t)(kTrainThreads / 32) * (kPipeBarBytes + (size_t)depth * stage_bytes);
+}
+
+template <typename K>
+static cudaError_t launch_kernel(K kernel, const TrainParams& p, int grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kTrainThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// delta path of the production kernel: TMA bulk reductions (default) or per-lane REDG; RANKFM_B200_UPDATE=redg|tma
+static bool use_tred()
+{
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("RANKFM_B200_UPDATE"); cached = (e && !strcmp(e, "redg")) ? 0 : 1; }
+    return cached == 1;
+}
+
+template <int G, int QPL, typename F>
+static void with_pipe_kernel(bool feat, bool warp, bool tred, F&& f)
+{
+    if (feat) {
+        if (warp) { if (tred) f(sgd_pipe_kernel<G, QPL, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, true, false>); }
+        else      { if (tred) f(sgd_pipe_kernel<G, QPL, true, false, true>); else f(sgd_pipe_kernel<G, QPL, true, false, false>); }
+    } else {
+        if (warp) { if (tred) f(sgd_pipe_kernel<G, QPL, false, true, true>); else f(sgd_pipe_kernel<G, QPL, false, true, false>); }
+        else      { if (tred) f(sgd_pipe_kernel<G, QPL, false, false, true>); else f(sgd_pipe_kernel<G, QPL, false, false, false>); }
+    }
+}
+
+template <int G, int QPL>
+static cudaError_t launch_pipe(const TrainParams& p, bool feat, int grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaSuccess;
+    with_pipe_kernel<G, QPL>(feat, p.max_samples > 1, use_tred(), [&](auto kernel) { e = launch_kernel(kernel, p, grid, smem, st); });
+    return e;
 }
 
 template <int G, int QPL>
@@ -305,17 +414,7 @@ static cudaError_t launch_gq(const TrainParams& p0, int grid, cudaStream_t st)
     }
     p.depth = pipe_depth(p.T, G);
     const size_t smem = pipe_smem_bytes(p.T, G, p.depth);
-    cudaError_t e;
-    if (feat) {
-        e = cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        sgd_pipe_kernel<G, QPL, true><<<grid, kTrainThreads, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        sgd_pipe_kernel<G, QPL, false><<<grid, kTrainThreads, smem, st>>>(p);
-    }
-    return cudaGetLastError();
+    return launch_pipe<G, QPL>(p, feat, grid, smem, st);
 }
 
 template <int G, int QPL>
@@ -324,13 +423,10 @@ static int occ_gq(const TrainParams& p)
     const bool feat = p.T.x_uf_any || p.T.x_if_any;
     const size_t smem = pipe_smem_bytes(p.T, G, pipe_depth(p.T, G));
     int n = 0;
-    if (feat) {
-        cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sgd_pipe_kernel<G, QPL, true>, kTrainThreads, smem);
-    } else {
-        cudaFuncSetAttribute(sgd_pipe_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sgd_pipe_kernel<G, QPL, false>, kTrainThreads, smem);
-    }
+    with_pipe_kernel<G, QPL>(feat, p.max_samples > 1, use_tred(), [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kTrainThreads, smem);
+    });
     return n;
 }
 
