@@ -501,7 +501,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     tp.max_samples = p.max_samples;
     tp.max_rejects = p.max_rejects > 0 ? p.max_rejects : (p.sampler == RFM_SAMPLER_MT ? 0x7fffffff : 64);
     tp.serial = p.sched == RFM_SCHED_SERIAL ? 1 : 0;
-    tp.k0 = (uint32_t)p.seed; tp.k1 = (uint32_t)(p.seed >> 32);
+    tp.k0 = (uint32_t)p.seed; tp.k1 = (uint32_t)(p.seed >> 32) ^ (0x9E3779B9u * (uint32_t)p.rank);   // ranks index their shards locally: decorrelate
     tp.mt = p.sampler == RFM_SAMPLER_MT ? s->d_mt : nullptr;
     tp.trace = s->d_trace;
     std::vector<float> etas((size_t)epochs);

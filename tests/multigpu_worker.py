@@ -1,0 +1,115 @@
+"""Worker for the multi-process tests (launched once per rank by test_multigpu.py or by torchrun).
+
+mode "gloo-oracle" (CPU): every rank trains ITS user shard with the CPU oracle from identical initial weights, the ranks
+  then combine exactly like rfm_session_train does on GPUs -- per epoch a SUM of item-table deltas over the process
+  group, at the end a sum of user-table deltas (user rows are owned by one rank) -- and the result must be identical on
+  every rank and equal to the single-process emulation of the same schedule.
+mode "nccl" (GPU): the real thing: one process per GPU, rfm_fit with world>1 (NCCL loaded by the library), then the same
+  invariants + agreement with a single-GPU fit within Hogwild tolerances.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import WEIGHTS, CSRItems, csr_of, features, init_weights, zipf_interactions  # noqa: E402
+
+
+def problem():
+    X = zipf_interactions(600, 300, 20000, seed=3)
+    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    indptr, indices = csr_of(X, U)
+    return X, U, I, CSRItems(indptr, indices), np.ones(len(X), np.float32)
+
+
+def allreduce_sum(a):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.numpy()
+
+
+def gloo_oracle(rank, world):
+    from oracle import oracle
+    from rankfm_b200 import _rankfm
+    X, U, I, ui, sw = problem()
+    F, epochs = 8, 3
+    x_uf, x_if = features(U, I, 0, 0)
+    Xr, swr, (lo, hi) = _rankfm.shard_by_user(X, sw, U, rank, world)
+    w = init_weights(U, I, F, seed=1)
+    w0_vu = w['v_u'].copy()
+    hyper = (0.01, 0.1, 0.1, 'constant', 0.25, 1)
+    for e in range(epochs):
+        snap = {k: w[k].copy() for k in ('w_i', 'v_i')}
+        oracle.fit_ex(Xr, swr, ui, x_uf, x_if, *[w[k] for k in WEIGHTS], *hyper, 1, perms=None, sampler="philox", seed=5, epoch_offset=e, max_rejects=64)
+        for k in ('w_i', 'v_i'):                       # replicated item side: sum of deltas
+            w[k][...] = snap[k] + allreduce_sum(w[k] - snap[k])
+    w['v_u'][...] = w0_vu + allreduce_sum(w['v_u'] - w0_vu)      # user rows: owned by exactly one rank
+    # every rank must now hold the same model
+    for k in ('w_i', 'v_i', 'v_u'):
+        ref = allreduce_sum(w[k].astype(np.float64)) / world
+        assert np.allclose(w[k], ref, rtol=0, atol=1e-6), k
+    # rows of users outside [lo, hi) were written by their owner, not by us
+    assert not np.array_equal(w['v_u'][lo:hi], w0_vu[lo:hi])
+    if rank == 0:
+        # single-process emulation of the same schedule
+        shards = [_rankfm.shard_by_user(X, sw, U, r, world) for r in range(world)]
+        ws = init_weights(U, I, F, seed=1)
+        for e in range(epochs):
+            base = {k: ws[k].copy() for k in WEIGHTS}
+            acc = {k: np.zeros_like(ws[k]) for k in ('w_i', 'v_i', 'v_u')}
+            for Xs, sws, _ in shards:
+                wr = {k: base[k].copy() for k in WEIGHTS}
+                oracle.fit_ex(Xs, sws, ui, x_uf, x_if, *[wr[k] for k in WEIGHTS], *hyper, 1, perms=None, sampler="philox", seed=5, epoch_offset=e, max_rejects=64)
+                for k in acc:
+                    acc[k] += wr[k] - base[k]
+            for k in acc:
+                ws[k][...] = base[k] + acc[k]
+        for k in ('w_i', 'v_i', 'v_u'):
+            assert np.allclose(w[k], ws[k], rtol=1e-5, atol=1e-6), k
+        print("gloo-oracle ok")
+
+
+def nccl(rank, world):
+    from rankfm_b200 import _rankfm
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    _rankfm.set_device(local)
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(_rankfm.nccl_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(idt, src=0)
+    X, U, I, ui, sw = problem()
+    F, epochs = 8, 4
+    x_uf, x_if = features(U, I, 0, 0)
+    hyper = (0.01, 0.1, 0.1, 'constant', 0.25, 1)
+    Xr, swr, (lo, hi) = _rankfm.shard_by_user(X, sw, U, rank, world)
+    w = init_weights(U, I, F, seed=1)
+    _rankfm.set_comm(rank, world, idt.numpy().tobytes())
+    stats = _rankfm.fit_ex(Xr, swr, ui, x_uf, x_if, *[w[k] for k in WEIGHTS], *hyper, epochs, mode="production", seed=5)
+    _rankfm.set_comm(0, 1, None)
+    for k in ('w_i', 'v_i', 'v_u'):
+        ref = allreduce_sum(w[k].astype(np.float64)) / world
+        assert np.allclose(w[k], ref, rtol=0, atol=1e-6), "ranks disagree on " + k
+    ll = allreduce_sum(np.array([s['log_likelihood'] for s in stats]))
+    assert all(s['sync_ms'] > 0 for s in stats)
+    if rank == 0:
+        w1 = init_weights(U, I, F, seed=1)
+        s1 = _rankfm.fit_ex(X, sw, ui, x_uf, x_if, *[w1[k] for k in WEIGHTS], *hyper, epochs, mode="production", seed=5)
+        ll1 = np.array([s['log_likelihood'] for s in s1])
+        assert np.allclose(ll[1:], ll1[1:], rtol=0.05), (ll, ll1)
+        for k in ('v_u', 'v_i', 'w_i'):
+            assert abs(np.linalg.norm(w[k]) / np.linalg.norm(w1[k]) - 1) < 0.1, k
+        print("nccl ok", ll.tolist(), ll1.tolist())
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1]
+    dist.init_process_group(backend="gloo", init_method="env://")
+    try:
+        (gloo_oracle if mode == "gloo-oracle" else nccl)(dist.get_rank(), dist.get_world_size())
+    finally:
+        dist.destroy_process_group()
