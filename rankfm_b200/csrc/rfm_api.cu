@@ -136,6 +136,7 @@ struct rfm_session {
     // multi-GPU
     void* comm = nullptr;
     float *d_it_snap = nullptr, *d_gp_snap = nullptr, *d_ut_init = nullptr;
+    float* d_gp_acc = nullptr;
     // scratch
     float *d_snap_ut = nullptr, *d_snap_it = nullptr, *d_snap_gp = nullptr; int snap_epochs = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -201,7 +202,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->T.UT); cudaFree(s->T.IT); cudaFree(s->T.GP);
     cudaFree(s->d_inter); cudaFree(s->d_sw); cudaFree(s->d_indptr); cudaFree(s->d_indices);
     cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
-    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush);
+    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
@@ -307,6 +308,13 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
             }
         }
         CUB(cudaStreamSynchronize(s->st));
+    }
+    if (s->N > 0 && (T.x_uf_any || T.x_if_any)) {
+        TRY(dev_alloc(&s->d_gp_acc, s->gp_floats));
+        CUB(cudaMemsetAsync(s->d_gp_acc, 0, s->gp_floats * 4, s->st));
+        if (p->sched == RFM_SCHED_PARALLEL && sgd_pipe_smem_bytes(T) > 200 * 1024)
+            return bail(fail(RFM_ERR_UNSUPPORTED, "side-feature blocks too large for the production schedule (warp-private copies need %zu KiB of shared memory per block); use fewer feature columns/factors or the replay mode",
+                             sgd_pipe_smem_bytes(T) / 1024));
     }
     {
         TrainParams tp{};
@@ -442,9 +450,9 @@ extern "C" int rfm_session_download(rfm_session* s, float* w_i, float* w_if, flo
 // ---------------------------------------------------------------------------------------------------------------
 // multi-GPU: replicated item table / globals, per-epoch sum of deltas (see DESIGN.md, section multi-GPU)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void delta_kernel(float* __restrict__ cur, const float* __restrict__ snap, size_t n)     // cur <- cur - snap
+__global__ void delta_kernel(float* __restrict__ cur, const float* __restrict__ snap, size_t n, float scale)     // cur <- scale*(cur - snap)
 {
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) cur[e] -= snap[e];
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) cur[e] = scale * (cur[e] - snap[e]);
 }
 __global__ void apply_kernel(float* __restrict__ cur, float* __restrict__ snap, size_t n)           // cur <- snap + cur ; snap <- cur
 {
@@ -454,15 +462,26 @@ __global__ void apply_kernel(float* __restrict__ cur, float* __restrict__ snap, 
     }
 }
 
-static int exchange_deltas(rfm_session* s, float* cur, float* snap, size_t n)
+static int exchange_deltas(rfm_session* s, float* cur, float* snap, size_t n, float scale = 1.0f)
 {
     const int grid = s->n_sm * 4;
-    delta_kernel<<<grid, 256, 0, s->st>>>(cur, snap, n);
+    delta_kernel<<<grid, 256, 0, s->st>>>(cur, snap, n, scale);
     NC(g_nccl.AllReduce(cur, cur, n, kNcclFloat, kNcclSum, s->comm, s->st));
     apply_kernel<<<grid, 256, 0, s->st>>>(cur, snap, n);
     s->launches += 2;
     CU(cudaGetLastError());
     return RFM_OK;
+}
+
+// Folding C independent chains of a parameter with per-step decay (1-lambda), each run for n steps from the same start:
+// theta = start + gain * sum_c (theta_c - start).  gain = (1 - d^C) / (C (1 - d)), d = (1-lambda)^n, is exact for the
+// decay part: 1 (sum of deltas) when the chains barely move, 1/C (average) when each chain has forgotten its start.
+static float fold_gain(double lambda, double n, double C)
+{
+    if (C <= 1.0) return 1.0f;
+    const double d = std::pow(std::max(0.0, 1.0 - lambda), n);
+    if (1.0 - d < 1e-12) return 1.0f;
+    return (float)((1.0 - std::pow(d, C)) / (C * (1.0 - d)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -535,16 +554,32 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
             tp.perm = nullptr;
             tp.feistel = make_feistel(s->N, p.seed, s->epochs_done + e);
         }
+        const bool feat_parallel = !tp.serial && (s->T.x_uf_any || s->T.x_if_any);
+        double chains = 1.0, steps_per_chain = (double)s->N;
+        if (feat_parallel) {
+            // warp-private feature-parameter chains: one per warp that owns >= 1 batch
+            const double n_batches = std::ceil((double)s->N / 32.0);
+            chains = std::min((double)grid * (kTrainThreads / 32), n_batches);
+            steps_per_chain = (double)s->N / chains;
+            tp.gp_acc = s->d_gp_acc;
+            tp.gp_gain = fold_gain((double)tp.reg_b * eta, steps_per_chain, chains);
+        }
         CU(cudaEventRecord(s->ev[4 * e + 0], s->st));
         cudaError_t le = launch_sgd_epoch(tp, grid, s->st);
         if (le != cudaSuccess) return fail(RFM_ERR_CUDA, "sgd_epoch launch failed: %s", cudaGetErrorString(le));
+        if (feat_parallel) { CU(launch_gp_apply(s->T.GP, s->d_gp_acc, (int)s->gp_floats, s->st)); s->launches += 1; }
         CU(cudaEventRecord(s->ev[4 * e + 1], s->st));
         s->launches += 1;
         CU(cudaEventRecord(s->ev[4 * e + 2], s->st));
         if (s->comm) {
             int rc = exchange_deltas(s, s->T.IT, s->d_it_snap, (size_t)s->T.I * s->T.ldi);
             if (rc) return rc;
-            if (s->T.x_uf_any || s->T.x_if_any) { rc = exchange_deltas(s, s->T.GP, s->d_gp_snap, s->gp_floats); if (rc) return rc; }
+            if (s->T.x_uf_any || s->T.x_if_any) {
+                // every rank ran its own feature-parameter chains: fold the ranks with the same rule
+                const float rank_gain = feat_parallel ? fold_gain((double)tp.reg_b * eta, (double)s->N, (double)p.world) : 1.0f;
+                rc = exchange_deltas(s, s->T.GP, s->d_gp_snap, s->gp_floats, rank_gain);
+                if (rc) return rc;
+            }
         }
         CU(cudaEventRecord(s->ev[4 * e + 3], s->st));
         CU(launch_weight_stats(s->T, (s->d_acc + e)->wstats, s->n_sm * 2, s->st));

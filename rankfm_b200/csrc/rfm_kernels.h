@@ -34,6 +34,9 @@ struct TrainParams {
     int32_t depth;           // stages of the TMA row pipeline (set by the launcher)
     int32_t spec;            // WARP sampler look-ahead: 1, 2, 4 attempts per round; 0 = choose from prev_acc
     const EpochAcc* prev_acc;   // previous epoch's record (device), or nullptr
+    float* gp_acc;           // [gp_floats] accumulator of the warps' feature-parameter deltas (production, FEAT)
+    float gp_gain;           // weight of each warp's delta when the chains are folded (see rfm_session_train)
+    int32_t gp_floats;
     uint32_t k0, k1, epoch_key;
     MtState* mt;             // non-null -> MT19937 sampler (serial only)
     EpochAcc* acc;
@@ -43,6 +46,8 @@ struct TrainParams {
 int train_group_size(const Tables& T, int* qpl_out);
 cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st);
 cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bitmap, int words, cudaStream_t st);
+cudaError_t launch_gp_apply(float* gp, float* acc, int n, cudaStream_t st);
+size_t sgd_pipe_smem_bytes(const Tables& T);
 cudaError_t launch_weight_stats(const Tables& T, double* out12, int grid, cudaStream_t st);
 
 // scoring (rfm_score.cu)

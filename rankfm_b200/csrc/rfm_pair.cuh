@@ -37,9 +37,15 @@ __device__ __forceinline__ void load_user(const Tables& T, int u, bool valid, in
     if (FEAT) c.xu = (valid && 4 * sub < T.Pp) ? __ldg(reinterpret_cast<const float4*>(row + T.Fp + 4 * sub)) : zero4();
 }
 
-// a[] and b[]: warp-uniform loops over P and Q; every lane of the warp must call
-template <int G, int QPL, bool FEAT>
-__device__ __forceinline__ void user_precompute(const Tables& T, bool valid, int sub, UserCtx<QPL>& c)
+// feature parameters live either in HBM (shared by everybody, read through L2) or in a warp-private shared-memory copy
+template <bool GPS>
+__device__ __forceinline__ float4 gp_ld4(const float* q) { return GPS ? *reinterpret_cast<const float4*>(q) : ld_cg4(q); }
+template <bool GPS>
+__device__ __forceinline__ float gp_ld1(const float* q) { return GPS ? *q : ld_cg1(q); }
+
+// a[] and b[]: warp-uniform loops over P and Q; every lane of the warp must call.  gp = base of [w_if | v_uf | v_if]
+template <int G, int QPL, bool FEAT, bool GPS = false>
+__device__ __forceinline__ void user_precompute(const Tables& T, const float* gp, bool valid, int sub, UserCtx<QPL>& c)
 {
 #pragma unroll
     for (int k = 0; k < QPL; ++k) c.a[k] = c.vu[k];
@@ -52,7 +58,7 @@ __device__ __forceinline__ void user_precompute(const Tables& T, bool valid, int
             for (int k = 0; k < QPL; ++k) {
                 const int q = sub + k * G;
                 if (valid && q < T.NQ) {
-                    const float4 w = ld_cg4(T.GP + T.gp_vuf + (size_t)p * T.Fp + 4 * q);
+                    const float4 w = gp_ld4<GPS>(gp + T.gp_vuf + (size_t)p * T.Fp + 4 * q);
                     c.a[k].x += w.x * xp; c.a[k].y += w.y * xp; c.a[k].z += w.z * xp; c.a[k].w += w.w * xp;
                 }
             }
@@ -64,11 +70,11 @@ __device__ __forceinline__ void user_precompute(const Tables& T, bool valid, int
 #pragma unroll
             for (int k = 0; k < QPL; ++k) {
                 const int qq = sub + k * G;
-                if (valid && qq < T.NQ) part = dot4(ld_cg4(T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq), c.vu[k], part);
+                if (valid && qq < T.NQ) part = dot4(gp_ld4<GPS>(gp + T.gp_vif + (size_t)q * T.Fp + 4 * qq), c.vu[k], part);
             }
             part = group_sum<G>(part);
             if ((q >> 2) == sub) {
-                const float s = part + (valid ? ld_cg1(T.GP + q) : 0.f);
+                const float s = part + (valid ? gp_ld1<GPS>(gp + q) : 0.f);
                 const int cidx = q & 3;
                 if (cidx == 0) c.b.x = s; else if (cidx == 1) c.b.y = s; else if (cidx == 2) c.b.z = s; else c.b.w = s;
             }

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) predict_kernel(const Tables T, const floa
         ItemRow<QPL> it;
         load_user<G, QPL, FEAT>(T, u, known, sub, uc);
         load_item<G, QPL, FEAT>(T, i, known, sub, it);
-        user_precompute<G, QPL, FEAT>(T, known, sub, uc);
+        user_precompute<G, QPL, FEAT>(T, T.GP, known, sub, uc);
         const float s = utility<G, QPL, FEAT>(uc, it);
         if (inb && sub == 0) scores[r] = known ? s : __int_as_float(0x7fc00000);
     }
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) score_users_kernel(const Tables T, const 
     const bool known = u >= 0;
     UserCtx<QPL> uc;
     load_user<G, QPL, FEAT>(T, known ? u : 0, known, sub, uc);
-    user_precompute<G, QPL, FEAT>(T, known, sub, uc);
+    user_precompute<G, QPL, FEAT>(T, T.GP, known, sub, uc);
     const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
     const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
     float* out = S + (size_t)b * T.I;

@@ -147,8 +147,18 @@ struct SmemSink {
 // One gradient step on (u, i, j): reads nothing but GP (feature parameters) from memory, everything else arrives in
 // registers; writes go out as vector reductions.  Update formula and operand association follow the generated C of the
 // reference:  w += eta * (((sw*mult) * (d_outer*d)) - (2reg * w)).
-template <int G, int QPL, bool FEAT, bool EXACT, typename Sink>
-__device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx<QPL>& uc, const ItemRow<QPL>& pos, const ItemRow<QPL>& neg,
+// add a delta quad to a feature parameter: HBM -> vector reduction; warp-private shared copy -> plain or atomic add
+// (atomic only when several lane groups of the warp work on different positives at once)
+template <int G, bool GPS>
+__device__ __forceinline__ void gp_add4(float* q, const float4& w, const float4& d)
+{
+    if (!GPS) { red_add4(q, d); return; }
+    if (G == 32) { *reinterpret_cast<float4*>(q) = make_float4(w.x + d.x, w.y + d.y, w.z + d.z, w.w + d.w); return; }
+    atomicAdd(q + 0, d.x); atomicAdd(q + 1, d.y); atomicAdd(q + 2, d.z); atomicAdd(q + 3, d.w);
+}
+
+template <int G, int QPL, bool FEAT, bool EXACT, bool GPS, typename Sink>
+__device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, const UserCtx<QPL>& uc, const ItemRow<QPL>& pos, const ItemRow<QPL>& neg,
                                              int min_j, float sw, int sampled, float min_pu, bool valid, long long r,
                                              int sub, StepAcc& acc, const Sink& sink)
 {
@@ -193,7 +203,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
             for (int k = 0; k < QPL; ++k) {
                 const int qq = sub + k * G;
                 if (upd && qq < T.NQ) {
-                    const float4 w = ld_cg4(T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq);
+                    const float4 w = gp_ld4<GPS>(gp + T.gp_vif + (size_t)q * T.Fp + 4 * qq);
                     dvu[k].x += w.x * dxq; dvu[k].y += w.y * dxq; dvu[k].z += w.z * dxq; dvu[k].w += w.w * dxq;
                 }
             }
@@ -233,10 +243,10 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
         const float rb_or_ra = rb;
         if (T.x_if_any) {
             if (upd && 4 * sub < T.Qp) {                                   // w_if, every q (:283-286)
-                const float4 w = ld_cg4(T.GP + 4 * sub);
+                const float4 w = gp_ld4<GPS>(gp + 4 * sub);
                 float4 d;
                 d.x = RFM_G(dx.x, w.x); d.y = RFM_G(dx.y, w.y); d.z = RFM_G(dx.z, w.z); d.w = RFM_G(dx.w, w.w);
-                red_add4(T.GP + 4 * sub, d);
+                gp_add4<G, GPS>(gp + 4 * sub, w, d);
             }
         }
         if (T.x_uf_any) {                                                  // v_uf[p] for x_uf[u,p] != 0 (:313-318)
@@ -247,12 +257,12 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
                 for (int k = 0; k < QPL; ++k) {
                     const int q = sub + k * G;
                     if (upd && nz && q < T.NQ) {
-                        float* wp = T.GP + T.gp_vuf + (size_t)pp * T.Fp + 4 * q;
-                        const float4 w = ld_cg4(wp);
+                        float* wp = gp + T.gp_vuf + (size_t)pp * T.Fp + 4 * q;
+                        const float4 w = gp_ld4<GPS>(wp);
                         float4 d;
                         d.x = RFM_G(xp * dij_new[k].x, w.x); d.y = RFM_G(xp * dij_new[k].y, w.y);
                         d.z = RFM_G(xp * dij_new[k].z, w.z); d.w = RFM_G(xp * dij_new[k].w, w.w);
-                        red_add4(wp, d);
+                        gp_add4<G, GPS>(wp, w, d);
                     }
                 }
             }
@@ -265,12 +275,12 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, const UserCtx
                 for (int k = 0; k < QPL; ++k) {
                     const int qq = sub + k * G;
                     if (upd && nz && qq < T.NQ) {
-                        float* wp = T.GP + T.gp_vif + (size_t)q * T.Fp + 4 * qq;
-                        const float4 w = ld_cg4(wp);
+                        float* wp = gp + T.gp_vif + (size_t)q * T.Fp + 4 * qq;
+                        const float4 w = gp_ld4<GPS>(wp);
                         float4 d;
                         d.x = RFM_G(dxq * vu_new[k].x, w.x); d.y = RFM_G(dxq * vu_new[k].y, w.y);
                         d.z = RFM_G(dxq * vu_new[k].z, w.z); d.w = RFM_G(dxq * vu_new[k].w, w.w);
-                        red_add4(wp, d);
+                        gp_add4<G, GPS>(wp, w, d);
                     }
                 }
             }

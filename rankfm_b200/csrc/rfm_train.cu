@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(32) sgd_serial_kernel(const TrainParams p)
         load_item<G, QPL, FEAT>(T, i, valid, sub, pos);
         long long seg = 0; int deg = 0;
         if (valid) { seg = __ldg(p.indptr + u); deg = (int)(__ldg(p.indptr + u + 1) - seg); }
-        user_precompute<G, QPL, FEAT>(T, valid, sub, uc);
+        user_precompute<G, QPL, FEAT>(T, T.GP, valid, sub, uc);
         const float ut_ui = utility<G, QPL, FEAT>(uc, pos);
         // ---- WARP / BPR sampling loop: _rankfm.pyx:244-264 ----
         int sampled = 0, min_j = -1;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(32) sgd_serial_kernel(const TrainParams p)
         else    sample_negatives_spec<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, 0, done, attempt, p.spec, sub, gw, neg, min_pu, min_j, sampled);
         // ---- gradient step: _rankfm.pyx:267-326 ----
         const RedSink sink{T.UT + (size_t)u * T.ldu, T.IT + (size_t)i * T.ldi, T.IT + (size_t)(min_j >= 0 ? min_j : 0) * T.ldi, T.Fp};
-        apply_update<G, QPL, FEAT, true>(p, uc, pos, neg, min_j, sw, sampled, min_pu, valid, r, sub, acc, sink);
+        apply_update<G, QPL, FEAT, true, false>(p, T.GP, uc, pos, neg, min_j, sw, sampled, min_pu, valid, r, sub, acc, sink);
         acc.fold();
         __threadfence(); __syncwarp();          // the next step must observe this step's reductions
     }
@@ -194,9 +194,16 @@ __global__ void __launch_bounds__(kTrainThreads, (QPL == 1 && !FEAT) ? 3 : (QPL 
     const int tuple_floats = T.ldu + 2 * T.ldi;
     const uint32_t tuple_bytes = (uint32_t)tuple_floats * 4u;
     const int stage_floats = GPW * tuple_floats;
-    unsigned char* wbase = smem_raw + (size_t)(threadIdx.x >> 5) * (kPipeBarBytes + (size_t)D * stage_floats * 4);
+    // per warp: [mbarriers | D stages | private copy of the feature parameters GP (FEAT only)]
+    const int gp_floats = FEAT ? p.gp_floats : 0;
+    unsigned char* wbase = smem_raw + (size_t)(threadIdx.x >> 5) * (kPipeBarBytes + ((size_t)D * stage_floats + gp_floats) * 4);
     const uint32_t bars = smem_u32(wbase);
     float* stages = reinterpret_cast<float*>(wbase + kPipeBarBytes);
+    float* gp = FEAT ? stages + (size_t)D * stage_floats : nullptr;
+    if (FEAT) {          // every warp starts the epoch from the same parameters and evolves its copy over its own positives
+        for (int e = lane; e < gp_floats; e += 32) gp[e] = __ldcg(T.GP + e);
+        __syncwarp();
+    }
     if (lane == 0) {
         for (int d = 0; d < D; ++d) mbar_init(bars + 8u * d, TMA ? 1u : 32u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(kTrainThreads, (QPL == 1 && !FEAT) ? 3 : (QPL 
                 for (int q = 0; q < QPL; ++q) { uc.vu[q] = zero4(); pos.v[q] = zero4(); neg.v[q] = zero4(); }
                 uc.xu = zero4(); pos.x = zero4(); neg.x = zero4(); pos.w = 0.f; neg.w = 0.f;
             }
-            user_precompute<G, QPL, FEAT>(T, valid, sub, uc);
+            user_precompute<G, QPL, FEAT, true>(T, gp, valid, sub, uc);
             float ut_ui = 0.f, pu1;
             if (!WARP) {                       // BPR: only the difference is needed -> one group reduction instead of two
                 float part = 0.f;
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(kTrainThreads, (QPL == 1 && !FEAT) ? 3 : (QPL 
                     if (4 * sub < T.Pp) slot[T.NQ + sub] = zero4();
                     if (4 * sub < T.Qp) { slot[nu4 + T.NQ + 1 + sub] = zero4(); slot[nu4 + ni4 + T.NQ + 1 + sub] = zero4(); }
                 }
-                apply_update<G, QPL, FEAT, false>(p, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
+                apply_update<G, QPL, FEAT, false, true>(p, gp, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
                 fence_async_smem();
                 __syncwarp();
                 const bool upd = valid && min_j >= 0;
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(kTrainThreads, (QPL == 1 && !FEAT) ? 3 : (QPL 
                 if (step >= 1 && step - 1 + D < STEPS) { if (sub < 3) bulk_wait_read1(); __syncwarp(); issue(cur, step - 1 + D); }
             } else {
                 const RedSink sink{T.UT + (size_t)u * T.ldu, T.IT + (size_t)i * T.ldi, T.IT + (size_t)jj * T.ldi, T.Fp};
-                apply_update<G, QPL, FEAT, false>(p, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
+                apply_update<G, QPL, FEAT, false, true>(p, gp, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
             }
         }
         if (TRED) { if (sub < 3) bulk_wait_read0(); __syncwarp(); }   // the next batch refills every stage
@@ -334,6 +341,14 @@ __global__ void __launch_bounds__(kTrainThreads, (QPL == 1 && !FEAT) ? 3 : (QPL 
         cur = nxt;
     }
     if (TRED) bulk_wait_all();
+    if (FEAT && warp_global < n_batches) {
+        // fold this warp's chain into the epoch result: GP_new = GP_start + gain * sum over active warps of (copy - GP_start)
+        __syncwarp();
+        for (int e = lane; e < gp_floats; e += 32) {
+            const float d = gp[e] - __ldcg(T.GP + e);
+            if (d != 0.f) red_add1(p.gp_acc + e, p.gp_gain * d);
+        }
+    }
     flush_acc<G>(acc, p.acc);
 }
 
@@ -358,10 +373,17 @@ static int pipe_depth(const Tables& T, int G)
     if (const char* e = getenv("RANKFM_B200_DEPTH")) d = atoi(e);      // experiments
     return d < 2 ? 2 : (d > 8 ? 8 : d);
 }
+static size_t gp_floats_of(const Tables& T) { return (T.x_uf_any || T.x_if_any) ? (size_t)T.gp_vif + (size_t)T.Q * T.Fp : 0; }
 static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
 {
     const size_t stage_bytes = (size_t)(32 / G) * (T.ldu + 2 * T.ldi) * 4;
-    return (size_t)(kTrainThreads / 32) * (kPipeBarBytes + (size_t)depth * stage_bytes);
+    return (size_t)(kTrainThreads / 32) * (kPipeBarBytes + (size_t)depth * stage_bytes + gp_floats_of(T) * 4);
+}
+size_t sgd_pipe_smem_bytes(const Tables& T)
+{
+    int qpl = 1;
+    const int G = train_group_size(T, &qpl);
+    return pipe_smem_bytes(T, G, pipe_depth(T, G));
 }
 
 template <typename K>
@@ -413,6 +435,7 @@ static cudaError_t launch_gq(const TrainParams& p0, int grid, cudaStream_t st)
         return cudaGetLastError();
     }
     p.depth = pipe_depth(p.T, G);
+    p.gp_floats = (int)gp_floats_of(p.T);
     const size_t smem = pipe_smem_bytes(p.T, G, p.depth);
     return launch_pipe<G, QPL>(p, feat, grid, smem, st);
 }
@@ -456,6 +479,17 @@ int sgd_epoch_blocks_per_sm(const TrainParams& p)
         case 16: return occ_gq<16, 1>(p);
         default: return qpl == 1 ? occ_gq<32, 1>(p) : (qpl == 2 ? occ_gq<32, 2>(p) : occ_gq<32, 4>(p));
     }
+}
+
+// GP += accumulated (already gain-weighted) warp deltas; clears the accumulator for the next epoch
+__global__ void gp_apply_kernel(float* __restrict__ gp, float* __restrict__ acc, int n)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) { gp[e] += acc[e]; acc[e] = 0.f; }
+}
+cudaError_t launch_gp_apply(float* gp, float* acc, int n, cudaStream_t st)
+{
+    gp_apply_kernel<<<(n + 255) / 256 > 64 ? 64 : (n + 255) / 256, 256, 0, st>>>(gp, acc, n);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
