@@ -353,6 +353,11 @@ class Session:
         check(_lib.lib().rfm_session_trace_read(self._h, ptr(out)))
         return out
 
+    def debug_gemm(self, users):
+        out = np.empty((users.shape[0], self._p.I), dtype=np.float32)
+        check(_lib.lib().rfm_session_debug_gemm(self._h, ptr(users), users.shape[0], ptr(out)))
+        return out
+
     def flush_l2(self):
         check(_lib.lib().rfm_session_flush_l2(self._h))
 

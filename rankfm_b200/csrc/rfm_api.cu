@@ -16,6 +16,9 @@
 
 using namespace rfm;
 
+namespace rfm { bool gemm_encode_available(); }
+static bool encode_ok() { return rfm::gemm_encode_available(); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------------------------------------
@@ -141,6 +144,9 @@ struct rfm_session {
     float *d_snap_ut = nullptr, *d_snap_it = nullptr, *d_snap_gp = nullptr; int snap_epochs = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int32_t* d_trace = nullptr;
+    // tensor-core recommend: bf16 item operand + bias, rebuilt lazily whenever the weights change
+    void* d_gemm_B = nullptr; float* d_gemm_bias = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
+    std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
     float* d_flush = nullptr; size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;
 };
@@ -204,6 +210,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
     cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
+    cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
     if (s->st) cudaStreamDestroy(s->st);
@@ -275,6 +282,7 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
         CUB(cudaMemcpyAsync(s->d_sw, p->sample_weight, (size_t)s->N * 4, cudaMemcpyHostToDevice, s->st));
         CUB(cudaMemcpyAsync(s->d_indptr, p->csr_indptr, ((size_t)p->U + 1) * 8, cudaMemcpyHostToDevice, s->st));
         CUB(cudaMemcpyAsync(s->d_indices, p->csr_indices, (size_t)s->nnz * 4, cudaMemcpyHostToDevice, s->st));
+        s->h_indptr.assign(p->csr_indptr, p->csr_indptr + p->U + 1);
         // WARP multiplier by number of draws: log((I-1)//sampled)/log(I)  (_rankfm.pyx:269, integer quotient)
         std::vector<float> mult((size_t)p->max_samples + 1, 0.f);
         for (int k = 1; k <= p->max_samples; ++k)
@@ -354,6 +362,7 @@ extern "C" int rfm_session_set_weights(rfm_session* s, const float* w_i, const f
     }
     int rc = upload_weights(s, w_i, w_if, v_u, v_i, v_uf, v_if, s->p.x_uf, s->p.x_if, false);
     if (rc) return rc;
+    s->gemm_valid = false;
     if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->T.UT, (size_t)s->T.U * s->T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
     s->epochs_done = 0;
     if (s->d_mt) {
@@ -397,6 +406,7 @@ extern "C" int rfm_session_restore(rfm_session* s)
     CU(cudaMemcpyAsync(s->T.GP, s->d_snap_gp, s->gp_floats * 4, cudaMemcpyDeviceToDevice, s->st));
     if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->d_snap_ut, nu * 4, cudaMemcpyDeviceToDevice, s->st));
     s->epochs_done = s->snap_epochs;
+    s->gemm_valid = false;
     return RFM_OK;
 }
 
@@ -586,6 +596,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
         s->launches += 1;
     }
     s->epochs_done += epochs;
+    s->gemm_valid = false;
     if (s->comm) {
         // user rows are owned by exactly one rank: the sum over ranks of (UT - UT_at_start) restores the full table
         const size_t n = (size_t)s->T.U * s->T.ldu;
@@ -677,10 +688,12 @@ static void users_to_int(const float* users, int64_t n, std::vector<int32_t>& ou
     for (int64_t k = 0; k < n; ++k) out[(size_t)k] = std::isnan(users[k]) ? -1 : (int32_t)users[k];
 }
 
-static int recommend_dev(rfm_session* s, const int32_t* d_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
-                         float* d_rec, float* gemm_ms)
+// exact fp32 path: score every item, exact radix select
+static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
+                           float* d_rec, float* gemm_ms)
 {
     const Tables& T = s->T;
+    if (n_users <= 0) return RFM_OK;
     // batch users so the score matrix stays under ~8 GB
     const int64_t max_batch = std::max<int64_t>(1, std::min<int64_t>(n_users, ((int64_t)2 << 30) / std::max(1, T.I)));
     float* S = nullptr;
@@ -707,9 +720,120 @@ static int recommend_dev(rfm_session* s, const int32_t* d_users, int64_t n_users
         if (gemm_ms) { CU(cudaStreamSynchronize(s->st)); float ms = 0.f; cudaEventElapsedTime(&ms, a, b); acc_ms += ms; }
     }
     CU(cudaStreamSynchronize(s->st));
-    if (gemm_ms) { *gemm_ms = acc_ms; cudaEventDestroy(a); cudaEventDestroy(b); }
+    if (gemm_ms) { *gemm_ms += acc_ms; cudaEventDestroy(a); cudaEventDestroy(b); }
     cudaFree(S);
     return RFM_OK;
+}
+
+constexpr int kCandCap = 1024;       // candidate slots per (user row, item split)
+
+static int ensure_gemm_items(rfm_session* s)
+{
+    if (s->gemm_valid) return RFM_OK;
+    const Tables& T = s->T;
+    const int Kp = gemm_kp(T), BN = gemm_block_n(T);
+    const int I_pad = (T.I + BN - 1) / BN * BN;
+    if (!s->d_gemm_B || s->gemm_I_pad != I_pad) {
+        cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
+        s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr;
+        CU(cudaMalloc(&s->d_gemm_B, (size_t)I_pad * Kp * 2));
+        int rc = dev_alloc(&s->d_gemm_bias, (size_t)I_pad);
+        if (rc) return rc;
+        s->gemm_I_pad = I_pad;
+    }
+    CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->d_gemm_bias, s->st));
+    s->launches += 1;
+    s->gemm_valid = true;
+    return RFM_OK;
+}
+
+// tensor-core path for users whose shortlist target fits the candidate buffer (rfm_gemm.cu)
+static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
+                        float* d_rec, float* gemm_ms)
+{
+    const Tables& T = s->T;
+    if (n_users <= 0) return RFM_OK;
+    int rc = ensure_gemm_items(s);
+    if (rc) return rc;
+    const int Kp = gemm_kp(T), BN = gemm_block_n(T), I_pad = s->gemm_I_pad, n_tiles = I_pad / BN;
+    const int64_t max_rows = 16384;
+    void* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
+    auto done = [&](int code) { cudaFree(d_A); cudaFree(d_ntgt); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_S2); cudaFree(d_map); return code; };
+    const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + 127) / 128 * 128);
+    const int max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(8, n_tiles), (2 * s->n_sm + rows_alloc / 128 - 1) / (rows_alloc / 128)));
+    CU(cudaMalloc(&d_A, (size_t)rows_alloc * Kp * 2));
+    if ((rc = dev_alloc(&d_ntgt, (size_t)rows_alloc))) return done(rc);
+    if ((rc = dev_alloc(&d_cand, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
+    if ((rc = dev_alloc(&d_cnt, (size_t)rows_alloc * max_splits))) return done(rc);
+    if ((rc = dev_alloc(&d_S2, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
+    if ((rc = dev_alloc(&d_map, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
+    std::vector<int> ntgt((size_t)rows_alloc);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
+    for (int64_t off = 0; off < n_users; off += rows_alloc) {
+        const int nb = (int)std::min<int64_t>(rows_alloc, n_users - off);
+        const int M_pad = (nb + 127) / 128 * 128;
+        const int n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(max_splits, (2 * s->n_sm + M_pad / 128 - 1) / (M_pad / 128)));
+        for (int r = 0; r < M_pad; ++r) {
+            int need = 2 * n_items + 16;
+            if (r < nb && filter_previous && h_users[off + r] >= 0) need += (int)(s->h_indptr[h_users[off + r] + 1] - s->h_indptr[h_users[off + r]]);
+            ntgt[(size_t)r] = need;
+        }
+        CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), (size_t)M_pad * 4, cudaMemcpyHostToDevice, s->st));
+        CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
+        if (gemm_ms) CU(cudaEventRecord(a, s->st));
+        cudaError_t e = launch_score_filter(T, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_ntgt, kCandCap, nullptr, s->st);
+        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e)));
+        if (gemm_ms) CU(cudaEventRecord(b, s->st));
+        e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, n_splits, kCandCap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, s->st);
+        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "rescore launch failed: %s", cudaGetErrorString(e)));
+        e = launch_topn_select(d_S2, n_splits * kCandCap, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
+        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "topn_select launch failed: %s", cudaGetErrorString(e)));
+        s->launches += 4;
+        CU(cudaStreamSynchronize(s->st));
+        if (gemm_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); *gemm_ms += ms; }
+    }
+    if (gemm_ms) { cudaEventDestroy(a); cudaEventDestroy(b); }
+    return done(RFM_OK);
+}
+
+// 0 = auto, 1 = force tensor-core path where it applies, 2 = force the exact path       (RANKFM_B200_RECOMMEND=auto|tc|exact)
+static int recommend_mode()
+{
+    const char* e = getenv("RANKFM_B200_RECOMMEND");
+    if (!e) return 0;
+    return !strcmp(e, "tc") ? 1 : (!strcmp(e, "exact") ? 2 : 0);
+}
+
+// Plan: users whose shortlist (2n+16 [+ seen items]) fits the candidate buffer go through the tensor cores, the rest (and
+// everything when the shape is not supported / too small to pay off) through the exact path.  `order` receives a
+// permutation of [0,n_users): tensor-core users first.  Returns the number of tensor-core users.
+static int64_t recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, int32_t n_items, int32_t filter_previous, std::vector<int64_t>& order)
+{
+    const int64_t n = (int64_t)hu.size();
+    order.resize((size_t)n);
+    const int mode = recommend_mode();
+    const Tables& T = s->T;
+    bool tc = mode != 2 && gemm_supported(T) && encode_ok() && (mode == 1 || ((int64_t)T.I >= 4096 && n * (int64_t)T.I >= ((int64_t)1 << 24)));
+    const int limit = kCandCap - gemm_block_n(T) - 32;
+    if (2 * n_items + 16 > limit) tc = false;
+    int64_t lo = 0, hi = n;
+    for (int64_t k = 0; k < n; ++k) {
+        bool light = tc;
+        if (light && filter_previous && hu[(size_t)k] >= 0)
+            light = 2 * n_items + 16 + (s->h_indptr[hu[(size_t)k] + 1] - s->h_indptr[hu[(size_t)k]]) <= limit;
+        if (light) order[(size_t)lo++] = k; else order[(size_t)--hi] = k;
+    }
+    return lo;
+}
+
+static int recommend_dev(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_tc, int64_t n_users, int32_t n_items,
+                         int32_t filter_previous, float* d_rec, float* gemm_ms)
+{
+    if (gemm_ms) *gemm_ms = 0.f;
+    int rc = recommend_tc(s, d_users, h_users, n_tc, n_items, filter_previous, d_rec, gemm_ms);
+    if (rc) return rc;
+    return recommend_exact(s, d_users + n_tc, n_users - n_tc, n_items, filter_previous, d_rec + (size_t)n_tc * n_items, gemm_ms);
 }
 
 static int recommend_checks(rfm_session* s, int64_t n_users, int32_t n_items, int32_t filter_previous)
@@ -731,13 +855,20 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     std::vector<int32_t> hu;
     users_to_int(users, n_users, hu);
     for (auto u : hu) if (u >= s->T.U) return fail(RFM_ERR_ARG, "user index %d out of range", u);
+    std::vector<int64_t> order;
+    const int64_t n_tc = recommend_plan(s, hu, n_items, filter_previous, order);
+    std::vector<int32_t> hp((size_t)n_users);
+    for (int64_t k = 0; k < n_users; ++k) hp[(size_t)k] = hu[(size_t)order[(size_t)k]];
     int32_t* d_users = nullptr; float* d_rec = nullptr;
     if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
     if ((rc = dev_alloc(&d_rec, (size_t)n_users * n_items))) return rc;
-    CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
-    if ((rc = recommend_dev(s, d_users, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
-    CU(cudaMemcpyAsync(rec_items, d_rec, (size_t)n_users * n_items * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
+    if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
+    std::vector<float> tmp((size_t)n_users * n_items);
+    CU(cudaMemcpyAsync(tmp.data(), d_rec, (size_t)n_users * n_items * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
+    for (int64_t k = 0; k < n_users; ++k)
+        memcpy(rec_items + (size_t)order[(size_t)k] * n_items, tmp.data() + (size_t)k * n_items, (size_t)n_items * 4);
     cudaFree(d_users); cudaFree(d_rec);
     return RFM_OK;
 }
@@ -751,18 +882,22 @@ extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, in
     CU(cudaSetDevice(s->device));
     std::vector<int32_t> hu;
     users_to_int(users, n_users, hu);
+    std::vector<int64_t> order;
+    const int64_t n_tc = recommend_plan(s, hu, n_items, filter_previous, order);
+    std::vector<int32_t> hp((size_t)n_users);
+    for (int64_t k = 0; k < n_users; ++k) hp[(size_t)k] = hu[(size_t)order[(size_t)k]];
     int32_t* d_users = nullptr; float* d_rec = nullptr;
     if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
     if ((rc = dev_alloc(&d_rec, (size_t)n_users * n_items))) return rc;
-    CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
-    if ((rc = recommend_dev(s, d_users, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;   // warm-up
+    CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
+    if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;   // warm-up
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
     float gemm_total = 0.f;
     CU(cudaEventRecord(a, s->st));
     for (int k = 0; k < iters; ++k) {
         float g = 0.f;
-        if ((rc = recommend_dev(s, d_users, n_users, n_items, filter_previous, d_rec, gemm_ms_out ? &g : nullptr))) return rc;
+        if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, gemm_ms_out ? &g : nullptr))) return rc;
         gemm_total += g;
     }
     CU(cudaEventRecord(b, s->st));
@@ -773,6 +908,32 @@ extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, in
     if (gemm_ms_out) *gemm_ms_out = gemm_total / iters;
     cudaEventDestroy(a); cudaEventDestroy(b);
     cudaFree(d_users); cudaFree(d_rec);
+    return RFM_OK;
+}
+
+// debugging / parity: the bf16 tensor-core scores S = A.B^T + bias of the requested users against ALL items, dense
+extern "C" int rfm_session_debug_gemm(rfm_session* s, const float* users, int64_t n_users, float* scores_out /* [n_users, I] */)
+{
+    if (!s || !users || !scores_out || n_users <= 0) return fail(RFM_ERR_ARG, "bad argument");
+    if (!gemm_supported(s->T) || !encode_ok()) return fail(RFM_ERR_UNSUPPORTED, "tensor-core scoring not available for this shape");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_gemm_items(s);
+    if (rc) return rc;
+    std::vector<int32_t> hu;
+    users_to_int(users, n_users, hu);
+    const Tables& T = s->T;
+    const int Kp = gemm_kp(T), I_pad = s->gemm_I_pad, M_pad = (int)((n_users + 127) / 128 * 128);
+    int32_t* d_users = nullptr; void* d_A = nullptr; float* d_S = nullptr;
+    if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
+    CU(cudaMalloc(&d_A, (size_t)M_pad * Kp * 2));
+    if ((rc = dev_alloc(&d_S, (size_t)M_pad * I_pad))) return rc;
+    CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
+    CU(launch_pack_gemm_users(T, d_users, (int)n_users, M_pad, Kp, d_A, s->st));
+    cudaError_t e = launch_score_filter(T, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, d_S, s->st);
+    if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e));
+    CU(cudaMemcpy2DAsync(scores_out, (size_t)T.I * 4, d_S, (size_t)I_pad * 4, (size_t)T.I * 4, (size_t)n_users, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    cudaFree(d_users); cudaFree(d_A); cudaFree(d_S);
     return RFM_OK;
 }
 
@@ -854,6 +1015,7 @@ static int attach_csr(rfm_session* s, const rfm_problem* p)
     if ((rc = dev_alloc(&s->d_indices, (size_t)nnz))) return rc;
     CU(cudaMemcpyAsync(s->d_indptr, p->csr_indptr, ((size_t)p->U + 1) * 8, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(s->d_indices, p->csr_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s->st));
+    s->h_indptr.assign(p->csr_indptr, p->csr_indptr + p->U + 1);
     CU(cudaStreamSynchronize(s->st));
     return RFM_OK;
 }

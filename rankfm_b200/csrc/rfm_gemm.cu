@@ -1,0 +1,451 @@
+// rfm_gemm.cu -- tensor-core candidate generation for `_recommend` (rankfm/_rankfm.pyx:393-460).
+//
+// The reference scores every item for every requested user with a scalar loop (:440-441) and fully sorts the scores
+// (:444).  Mathematically that is S = A . B^T + bias with
+//     A[u]  = [ v_u + x_uf.v_uf  |  v_u ]            (second half only with item features)
+//     B[i]  = [ v_i              |  x_if[i].v_if ]
+//     bias  = w_i + x_if[i].w_if
+// (derived from compute_ui_utility :48-89; there is no user-feature x item-feature cross term), i.e. a dense GEMM whose
+// output (U x I) can never be materialised at cfg5 scale (1M x 1M).  So:
+//
+//   score_filter_kernel   bf16 operands, fp32 accumulation on the 5th-generation tensor cores:
+//       TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma (cta_group::1, M=128, N=256|128,
+//       K=16 per instruction, issued by one elected thread) -> accumulators in TMEM (2 stages) -> tcgen05.ld in the
+//       epilogue warps.  One CTA owns 128 users (A stays resident in shared memory) and streams its slice of item
+//       tiles; warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+//       The epilogue never writes scores: thread r owns user row r, keeps a running threshold tau_r and appends
+//       (score, item) to the row's candidate buffer only when score >= tau_r; when the buffer fills, the row's
+//       n'-th largest candidate becomes the new tau_r and the buffer is compacted.  tau only ever rises, so the
+//       buffer always contains the row's n' best items (by bf16 score) seen so far.
+//   rescore_kernel        exact fp32 utility of the surviving candidates (same code as predict), seen items masked
+//   topn_select_kernel    (rfm_score.cu) exact top-n of the shortlist.
+//
+// n' = 2*n_items (+ the user's number of seen items when filtering) absorbs the bf16 rounding of the candidate scores;
+// the final ranking is exact fp32.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include "rfm_kernels.h"
+#include "rfm_pair.cuh"
+
+namespace rfm {
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand packing: bf16 A (requested users) / B (all items), fp32 bias
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pack_gemm_items_kernel(const Tables T, int Kp, int I_pad, __nv_bfloat16* __restrict__ B, float* __restrict__ bias)
+{
+    const long long n = (long long)I_pad * Kp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / Kp), c = (int)(e % Kp);
+        float v = 0.f;
+        if (i < T.I) {
+            const float* row = T.IT + (size_t)i * T.ldi;
+            if (c < T.F) v = row[c];
+            else if (T.x_if_any && c >= T.Fp && c - T.Fp < T.F) {             // second half: x_if[i] . v_if[:, f]
+                const int f = c - T.Fp;
+                for (int q = 0; q < T.Q; ++q) v += row[T.Fp + 4 + q] * T.GP[T.gp_vif + (size_t)q * T.Fp + f];
+            }
+        }
+        B[e] = __float2bfloat16(v);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I_pad; i += gridDim.x * blockDim.x) {
+        float b = -INFINITY;                                                 // padded items never pass the filter
+        if (i < T.I) {
+            const float* row = T.IT + (size_t)i * T.ldi;
+            b = row[T.Fp];
+            if (T.x_if_any) for (int q = 0; q < T.Q; ++q) b += row[T.Fp + 4 + q] * T.GP[q];
+        }
+        bias[i] = b;
+    }
+}
+
+__global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, int M_pad, int Kp, __nv_bfloat16* __restrict__ A)
+{
+    const long long n = (long long)M_pad * Kp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / Kp), c = (int)(e % Kp);
+        float v = 0.f;
+        const int u = r < n_users ? users[r] : -1;
+        if (u >= 0) {
+            const float* row = T.UT + (size_t)u * T.ldu;
+            if (c < T.F) {
+                v = row[c];
+                if (T.x_uf_any) for (int p = 0; p < T.P; ++p) v += row[T.Fp + p] * T.GP[T.gp_vuf + (size_t)p * T.Fp + c];
+            } else if (T.x_if_any && c >= T.Fp && c - T.Fp < T.F) v = row[c - T.Fp];
+        }
+        A[e] = __float2bfloat16(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v)
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// shared-memory matrix descriptor: K-major tile of 128-byte rows, 128B swizzle, 8-row groups 1024 B apart (sm_100 format)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+{
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
+
+__device__ __forceinline__ uint32_t ord_key(float s) { const uint32_t b = __float_as_uint(s); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// the GEMM + running-threshold filter
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmParams {
+    const float* bias;           // [I_pad]
+    int kblocks;                 // Kp / 64
+    int n_tiles;                 // I_pad / BLOCK_N
+    int n_splits;                // item-range splits (grid.y)
+    int n_users;                 // valid rows of A
+    int nstage;
+    // filter mode
+    float2* cand;                // [M_pad * n_splits, cap]  (score, item index as int bits)
+    int* cand_cnt;               // [M_pad * n_splits]
+    const int* n_target;         // [M_pad] candidates to keep per row
+    int cap;
+    // dump mode
+    float* S;                    // [M_pad, I_pad] or nullptr
+    long long ldS;
+};
+
+constexpr int kGemmThreads = 256;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int A_KB_BYTES = 128 * 128;              // one 64-wide k-block of the A tile (128 rows x 128 B)
+    constexpr int B_KB_BYTES = BLOCK_N * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_n = p.kblocks, nstage = p.nstage;
+    unsigned char* sA = smem;
+    unsigned char* sB = sA + (size_t)kb_n * A_KB_BYTES;
+    unsigned char* sBar = sB + (size_t)nstage * kb_n * B_KB_BYTES;
+    const uint32_t bar_full = s32(sBar), bar_empty = bar_full + 8u * nstage, bar_a = bar_empty + 8u * nstage;
+    const uint32_t bar_tfull = bar_a + 8u, bar_tempty = bar_tfull + 16u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 8 * (2 * nstage + 5));
+
+    // this CTA: user tile blockIdx.x, item tiles [t0, t1)
+    const int m0 = blockIdx.x * 128;
+    const int per = (p.n_tiles + p.n_splits - 1) / p.n_splits;
+    const int t0 = blockIdx.y * per, t1 = min(p.n_tiles, t0 + per);
+    const int my_tiles = max(0, t1 - t0);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < nstage; ++s) { bar_init(bar_full + 8u * s, 1); bar_init(bar_empty + 8u * s, 1); }
+        bar_init(bar_a, 1);
+        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8u * a, 1); bar_init(bar_tempty + 8u * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {            // TMEM: 2 accumulator stages of BLOCK_N fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(2 * BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            bar_expect_tx(bar_a, (uint32_t)kb_n * A_KB_BYTES);
+            for (int kb = 0; kb < kb_n; ++kb) tma_load_2d(s32(sA + (size_t)kb * A_KB_BYTES), &tmA, kb * 64, m0, bar_a);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % nstage;
+                const uint32_t ph = (uint32_t)(it / nstage) & 1u;
+                bar_wait(bar_empty + 8u * s, ph ^ 1u);
+                bar_expect_tx(bar_full + 8u * s, (uint32_t)kb_n * B_KB_BYTES);
+                const int n0 = (t0 + it) * BLOCK_N;
+                for (int kb = 0; kb < kb_n; ++kb)
+                    tma_load_2d(s32(sB + ((size_t)s * kb_n + kb) * B_KB_BYTES), &tmB, kb * 64, n0, bar_full + 8u * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread drives the tensor core =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16_f32(BLOCK_N);
+            bar_wait(bar_a, 0);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % nstage, as = it & 1;
+                const uint32_t ph = (uint32_t)(it / nstage) & 1u, aph = (uint32_t)(it >> 1) & 1u;
+                bar_wait(bar_tempty + 8u * as, aph ^ 1u);           // epilogue has drained this accumulator stage
+                bar_wait(bar_full + 8u * s, ph);                    // B tile has landed
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(as * BLOCK_N);
+                for (int kb = 0; kb < kb_n; ++kb) {
+                    const uint64_t ad = smem_desc_sw128(s32(sA + (size_t)kb * A_KB_BYTES));
+                    const uint64_t bd = smem_desc_sw128(s32(sB + ((size_t)s * kb_n + kb) * B_KB_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)                     // 4 x (K=16) per 64-wide k-block: +32 B per step
+                        tc_mma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(bar_empty + 8u * s);                      // smem stage reusable once these MMAs retire
+                tc_commit(bar_tfull + 8u * as);                     // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread <-> user row (TMEM lane) =====
+        const int wq = warp & 3;                                    // TMEM lane quarter this warp may access
+        const int r = wq * 32 + lane;
+        const int row = m0 + r;
+        const bool row_ok = row < p.n_users;
+        const bool filter = p.S == nullptr;
+        float tau = -INFINITY;
+        int cnt = 0;
+        const int cap = p.cap;
+        const int ntgt = filter ? p.n_target[row] : 0;
+        float2* my = filter ? p.cand + ((size_t)row * p.n_splits + blockIdx.y) * cap : nullptr;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const int as = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            if (filter && __any_sync(0xffffffffu, cnt > cap - BLOCK_N)) {
+                // raise the threshold to the ntgt-th largest candidate (bisection on the ordered key) and compact
+                if (cnt > ntgt) {
+                    uint32_t lo = 0u, hi = 0xffffffffu;             // invariant: count(key >= lo) >= ntgt
+                    for (int pass = 0; pass < 32 && lo < hi; ++pass) {
+                        const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;
+                        int c = 0;
+                        for (int k = 0; k < cnt; ++k) c += ord_key(my[k].x) >= mid;
+                        if (c >= ntgt) lo = mid; else hi = mid - 1u;
+                    }
+                    int j = 0;
+                    for (int k = 0; k < cnt; ++k) { const float2 e = my[k]; if (ord_key(e.x) >= lo) my[j++] = e; }
+                    cnt = j;
+                    const uint32_t kb = lo;                         // invert ord_key
+                    tau = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb);
+                }
+            }
+            bar_wait(bar_tfull + 8u * as, aph);
+            tc_fence_after();
+            const int n0 = (t0 + it) * BLOCK_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                float v[32];
+                tc_ld32(taddr + (uint32_t)(c * 32), v);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+                if (filter) {
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = __ldg(b4 + q);
+                        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                        mx = fmaxf(mx, fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
+                    }
+                    if (row_ok && mx >= tau) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            if (v[k] >= tau && cnt < cap) { my[cnt] = make_float2(v[k], __int_as_float(n0 + c * 32 + k)); ++cnt; }
+                    }
+                } else {
+                    float* out = p.S + (size_t)row * p.ldS + n0 + c * 32;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = __ldg(b4 + q);
+                        reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(bar_tempty + 8u * as);
+        }
+        if (filter) p.cand_cnt[(size_t)row * p.n_splits + blockIdx.y] = row_ok ? cnt : 0;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BLOCK_N) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// exact fp32 re-score of the candidates (lane group per (user, candidate)); seen items get the "removed" marker
+// ---------------------------------------------------------------------------------------------------------------
+template <int G, int QPL, bool FEAT>
+__global__ void __launch_bounds__(256) rescore_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, const float2* __restrict__ cand,
+                                                      const int* __restrict__ cand_cnt, int slots, int cap, const int64_t* __restrict__ indptr,
+                                                      const int32_t* __restrict__ indices, int filter_previous, float* __restrict__ S2,
+                                                      int32_t* __restrict__ idxmap)
+{
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31, sub = lane % G, gw = lane / G;
+    const int b = blockIdx.y;
+    const int u = __ldg(users + b);
+    const bool known = u >= 0;
+    UserCtx<QPL> uc;
+    load_user<G, QPL, FEAT>(T, known ? u : 0, known, sub, uc);
+    user_precompute<G, QPL, FEAT>(T, T.GP, known, sub, uc);
+    const int width = slots * cap;                                      // row length of S2 / idxmap
+    const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
+    long long seg = 0; int deg = 0;
+    if (known && filter_previous) { seg = __ldg(indptr + u); deg = (int)(__ldg(indptr + u + 1) - seg); }
+    const long long span = ((long long)width + stride - 1) / stride * stride;
+    for (long long e = group_global; e < span; e += stride) {
+        const int slot = (int)(e / cap), k = (int)(e % cap);
+        const bool inb = known && e < width && k < __ldg(cand_cnt + (size_t)b * slots + slot);
+        int item = 0;
+        if (inb) item = __float_as_int(cand[((size_t)b * slots + slot) * cap + k].y);
+        const bool ok = inb && item >= 0 && item < T.I;
+        ItemRow<QPL> it;
+        load_item<G, QPL, FEAT>(T, ok ? item : 0, ok, sub, it);
+        const float s = utility<G, QPL, FEAT>(uc, it);
+        const bool seen = filter_previous ? group_member<G>(item, indices + seg, deg, ok, sub, gw) : false;
+        if (e < width && sub == 0) {
+            S2[(size_t)b * width + e] = (ok && !seen) ? s : __uint_as_float(0xffffffffu);
+            idxmap[(size_t)b * width + e] = item;
+        }
+    }
+}
+
+template <int G, int QPL>
+static cudaError_t rescore_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
+                              const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, cudaStream_t st)
+{
+    const dim3 grid(max(1, min(16, (slots * cap + 255) / 256)), n_users);
+    if (T.x_uf_any || T.x_if_any) rescore_kernel<G, QPL, true><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap);
+    else rescore_kernel<G, QPL, false><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rescore(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
+                           const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, cudaStream_t st)
+{
+    int qpl = 1;
+    const int G = train_group_size(T, &qpl);
+    if (max(T.Pp, T.Qp) > 4 * G || qpl > 4) return cudaErrorInvalidValue;
+    switch (G) {
+        case 4:  return rescore_gq<4, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+        case 8:  return rescore_gq<8, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+        case 16: return rescore_gq<16, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+        default:
+            if (qpl == 1) return rescore_gq<32, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+            if (qpl == 2) return rescore_gq<32, 2>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+            return rescore_gq<32, 4>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// row-major bf16 [rows, Kp] -> boxes of 64 (K) x box_rows, 128B swizzle
+static bool make_map(CUtensorMap* map, const void* base, long long rows, int Kp, int box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Kp * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool gemm_encode_available() { return encode_tiled_fn() != nullptr; }
+int gemm_kp(const Tables& T) { const int k = T.x_if_any ? 2 * T.Fp : T.Fp; return (k + 63) / 64 * 64; }
+int gemm_block_n(const Tables& T) { return gemm_kp(T) <= 128 ? 256 : 128; }
+bool gemm_supported(const Tables& T) { return gemm_kp(T) <= 256; }
+
+cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st)
+{
+    pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, Kp, I_pad, reinterpret_cast<__nv_bfloat16*>(B), bias);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st)
+{
+    pack_gemm_users_kernel<<<148 * 4, 256, 0, st>>>(T, users, n_users, M_pad, Kp, reinterpret_cast<__nv_bfloat16*>(A));
+    return cudaGetLastError();
+}
+
+// S == nullptr: filter mode (cand/cand_cnt/n_target/cap required); else dump mode (S [M_pad, I_pad])
+cudaError_t launch_score_filter(const Tables& T, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
+                                float2* cand, int* cand_cnt, const int* n_target, int cap, float* S, cudaStream_t st)
+{
+    const int Kp = gemm_kp(T), BN = gemm_block_n(T);
+    alignas(64) CUtensorMap tmA, tmB;
+    if (!make_map(&tmA, A, M_pad, Kp, 128) || !make_map(&tmB, B, I_pad, Kp, BN)) return cudaErrorNotSupported;
+    GemmParams p{};
+    p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = I_pad / BN; p.n_splits = n_splits; p.n_users = n_users;
+    p.cand = cand; p.cand_cnt = cand_cnt; p.n_target = n_target; p.cap = cap; p.S = S; p.ldS = I_pad;
+    const size_t a_bytes = (size_t)p.kblocks * 128 * 128, stage_bytes = (size_t)p.kblocks * BN * 128;
+    int nstage = (int)((200 * 1024 - a_bytes) / stage_bytes);
+    nstage = nstage > 4 ? 4 : (nstage < 2 ? 2 : nstage);
+    p.nstage = nstage;
+    const size_t smem = a_bytes + nstage * stage_bytes + 8 * (2 * nstage + 5) + 16 + 1024;
+    const dim3 grid(M_pad / 128, n_splits);
+    cudaError_t e;
+    if (BN == 256) {
+        e = cudaFuncSetAttribute(score_filter_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        score_filter_kernel<256><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+    } else {
+        e = cudaFuncSetAttribute(score_filter_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        score_filter_kernel<128><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace rfm

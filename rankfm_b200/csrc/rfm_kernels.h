@@ -55,7 +55,19 @@ cudaError_t launch_predict(const Tables& T, const float2* pairs, long long n, fl
 
 cudaError_t launch_score_users(const Tables& T, const int32_t* users, int n_users, float* S, int chunks, cudaStream_t st);
 cudaError_t launch_topn_select(float* S, int I, const int32_t* users, int n_users, const int64_t* indptr, const int32_t* indices,
-                               int filter_previous, int n_items, float* rec, const int32_t* exclude, cudaStream_t st);
+                               int filter_previous, int n_items, float* rec, const int32_t* exclude, cudaStream_t st,
+                               const int32_t* idxmap = nullptr);
+
+// tensor-core candidate generation for recommend (rfm_gemm.cu)
+int gemm_kp(const Tables& T);
+int gemm_block_n(const Tables& T);
+bool gemm_supported(const Tables& T);
+cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st);
+cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st);
+cudaError_t launch_score_filter(const Tables& T, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
+                                float2* cand, int* cand_cnt, const int* n_target, int cap, float* S, cudaStream_t st);
+cudaError_t launch_rescore(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
+                           const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, cudaStream_t st);
 cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);
 int sgd_epoch_blocks_per_sm(const TrainParams& p);
 

@@ -123,7 +123,7 @@ constexpr int kSelThreads = 512;
 __global__ void __launch_bounds__(kSelThreads) topn_select_kernel(float* __restrict__ S, int I, const int32_t* __restrict__ users,
                                                                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                                   int filter_previous, int n_items, float* __restrict__ rec,
-                                                                  const int32_t* __restrict__ exclude)
+                                                                  const int32_t* __restrict__ exclude, const int32_t* __restrict__ idxmap)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);        // [npow2] (key<<32 | index)
@@ -237,12 +237,13 @@ __global__ void __launch_bounds__(kSelThreads) topn_select_kernel(float* __restr
     }
     for (int k = tid; k < n_items; k += kSelThreads) {
         const unsigned long long e = sel[k];
-        out[k] = (e >> 32) == 0ull ? __int_as_float(0x7fc00000) : (float)(uint32_t)(e & 0xffffffffull);
+        const uint32_t pos = (uint32_t)(e & 0xffffffffull);              // position in the row; shortlist rows map it to an item id
+        out[k] = (e >> 32) == 0ull ? __int_as_float(0x7fc00000) : (float)(idxmap ? (uint32_t)idxmap[(size_t)b * I + pos] : pos);
     }
 }
 
 cudaError_t launch_topn_select(float* S, int I, const int32_t* users, int n_users, const int64_t* indptr, const int32_t* indices,
-                               int filter_previous, int n_items, float* rec, const int32_t* exclude, cudaStream_t st)
+                               int filter_previous, int n_items, float* rec, const int32_t* exclude, cudaStream_t st, const int32_t* idxmap)
 {
     int npow2 = 1;
     while (npow2 < n_items) npow2 <<= 1;
@@ -250,7 +251,7 @@ cudaError_t launch_topn_select(float* S, int I, const int32_t* users, int n_user
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(topn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    topn_select_kernel<<<n_users, kSelThreads, smem, st>>>(S, I, users, indptr, indices, filter_previous, n_items, rec, exclude);
+    topn_select_kernel<<<n_users, kSelThreads, smem, st>>>(S, I, users, indptr, indices, filter_previous, n_items, rec, exclude, idxmap);
     return cudaGetLastError();
 }
 

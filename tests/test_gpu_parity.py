@@ -359,3 +359,61 @@ def test_rankfm_class_replay_matches_reference_class(gpu_lib):
     iid = np.unique(g['interactions'][:, 1]); uid = np.unique(g['interactions'][:, 0])
     assert len(set(model.similar_items(iid[3], 5).tolist()) & set(g['sim_items'].tolist())) >= 4
     assert len(set(model.similar_users(uid[7], 5).tolist()) & set(g['sim_users'].tolist())) >= 4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) candidate generation for recommend
+# ---------------------------------------------------------------------------------------------------------------
+def _scoring_session(U, I, F, P, Q, seed):
+    X = zipf_interactions(U, I, max(4 * U, 2000), seed=seed)
+    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    x_uf, x_if = features(U, I, P, Q, seed=seed)
+    w = init_weights(U, I, F, P, Q, seed=seed, sigma=0.3)
+    w['w_i'][:] = np.random.default_rng(seed).normal(0, 0.5, I).astype(np.float32)
+    if Q:
+        w['w_if'][:] = np.random.default_rng(seed + 1).normal(0, 0.3, Q).astype(np.float32)
+        w['v_if'] *= 10
+    if P:
+        w['v_uf'] *= 10
+    keep = []
+    prob = _rankfm.fit_problem(X, np.ones(len(X), np.float32), ui, x_uf, x_if, *[w[k] for k in WEIGHTS], 0.01, 0.1, 0.1, 'constant', 0.25, 1, keep=keep)
+    return _rankfm.Session(prob, keep), w, ui, x_uf, x_if, U, I
+
+
+@pytest.mark.parametrize("F,P,Q,I", [(16, 0, 0, 1000), (128, 0, 0, 1500), (20, 3, 0, 700), (40, 0, 5, 1100), (100, 4, 6, 900)])
+def test_tcgen05_gemm_scores_match_fp32(gpu_lib, F, P, Q, I):
+    """bf16 x bf16 -> fp32 tensor-core scores (TMA + tcgen05.mma + TMEM) against the fp32 oracle utility"""
+    sess, w, ui, x_uf, x_if, U, I = _scoring_session(300, I, F, P, Q, seed=F)
+    users = np.array([0, 1, 5, U - 1, 17, 200, 131], np.float32)
+    S = sess.debug_gemm(users)
+    sess.close()
+    assert S.shape == (len(users), I)
+    for r, u in enumerate(users.astype(int)):
+        ref = oracle.scores_user(u, x_uf, x_if, *[w[k] for k in WEIGHTS])
+        scale = float(np.abs(ref).mean())
+        # bf16 operands: ~2^-8 relative per factor product
+        assert np.abs(S[r] - ref).max() < 0.03 * max(scale, 1.0), (r, np.abs(S[r] - ref).max(), scale)
+        assert np.corrcoef(S[r], ref)[0, 1] > 0.9995
+
+
+@pytest.mark.parametrize("F,P,Q", [(32, 0, 0), (20, 2, 3)])
+@pytest.mark.parametrize("filt", [False, True])
+def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, monkeypatch):
+    sess, w, ui, x_uf, x_if, U, I = _scoring_session(600, 6000, F, P, Q, seed=7 + F)
+    rng = np.random.default_rng(0)
+    users = rng.integers(0, U, 300).astype(np.float32)
+    users[5] = np.nan
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "exact")
+    exact = sess.recommend(users, 20, filt)
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    fast = sess.recommend(users, 20, filt)
+    sess.close()
+    assert np.array_equal(np.isnan(fast), np.isnan(exact))
+    assert topk_overlap(fast, exact) >= 0.99                      # north_star: top-k set overlap >= 0.99
+    assert np.mean(fast[~np.isnan(exact)] == exact[~np.isnan(exact)]) >= 0.97
+    if filt:
+        for row, u in zip(fast, users):
+            if not np.isnan(u):
+                assert not set(row.astype(int).tolist()) & set(ui[int(u)].tolist())
