@@ -264,7 +264,13 @@ def run_ours(args):
                 (c["x_uf"].nbytes if c["P"] else 0) + (c["x_if"].nbytes if c["Q"] else 0)
             d2h = sum(v.nbytes for v in c["w0"].values())
             e2e = {"value": N * epochs / float(np.mean(dts)), "unit": "interactions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": 1e3 * float(np.mean(dts)), "call": "rankfm_b200._rankfm._fit(host ndarray buffers) -> ctypes -> rfm_fit"}
+                   "ms_per_step": 1e3 * float(np.mean(dts)), "ms_each": [round(1e3 * d, 2) for d in dts], "call": "rankfm_b200._rankfm._fit(host ndarray buffers) -> ctypes -> rfm_fit"}
+        recommend = None
+        if world == 1 and not args.no_recommend:
+            try:
+                recommend = recommend_probe(device=local_rank)
+            except Exception as exc:                    # secondary measurement must never take the headline down
+                recommend = {"error": repr(exc)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sample_epochs = 3
@@ -279,6 +285,7 @@ def run_ours(args):
                        "parallelism": "user-sharded x%d, per-epoch NCCL sum of item deltas" % world if world > 1 else "single GPU",
                        "schedule": "production: Hogwild lane-group per positive, Philox negatives, on-device Feistel order"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
+            "recommend": recommend,
             "final_log_likelihood": flat[-1]["log_likelihood"],
         }
     sess.close()
@@ -289,6 +296,42 @@ def run_ours(args):
         print(json.dumps(line))
 
 
+def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, device=0):
+    """secondary measurement (BASELINE.json configs[4] shape, scaled to seconds): recommend() top-100 through the
+    tcgen05 candidate GEMM.  TFLOP/s = 2*U*I*K / CUDA-event time of the GEMM+filter kernel; inputs resident in HBM."""
+    from rankfm_b200 import _rankfm
+    rng = np.random.default_rng(0)
+    w = dict(w_i=rng.normal(0, 0.3, n_items_cat).astype(np.float32), w_if=np.zeros(1, np.float32),
+             v_u=rng.normal(0, 0.1, (n_users, factors)).astype(np.float32), v_i=rng.normal(0, 0.1, (n_items_cat, factors)).astype(np.float32),
+             v_uf=np.zeros((1, factors), np.float32), v_if=np.zeros((1, factors), np.float32))
+    x_uf, x_if = np.zeros((n_users, 1), np.float32), np.zeros((n_items_cat, 1), np.float32)
+    keep = []
+    prob = _rankfm._problem(x_uf, x_if, *[w[k] for k in WEIGHTS], keep)
+    prob.device = device
+    sess = _rankfm.Session(prob, keep)
+    users = np.arange(n_users, dtype=np.float32)
+    os.environ["RANKFM_B200_RECOMMEND"] = "tc"
+    ms, gemm_ms = sess.time_recommend(users, topn, False, iters=3)
+    sample = users[:256]
+    fast = sess.recommend(sample, topn, False)
+    os.environ["RANKFM_B200_RECOMMEND"] = "exact"
+    exact = sess.recommend(sample, topn, False)
+    ms_exact, _ = sess.time_recommend(users[:4096], topn, False, iters=1)
+    os.environ.pop("RANKFM_B200_RECOMMEND", None)
+    sess.close()
+    overlap = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / topn for a, b in zip(fast, exact)]))
+    flops = 2.0 * n_users * n_items_cat * factors
+    peak = 1693.1
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    return {"workload": "recommend top-%d, %d users x %d items, factors=%d (tcgen05 bf16 candidate GEMM + exact fp32 re-score)" % (topn, n_users, n_items_cat, factors),
+            "ms_total": ms, "ms_gemm_filter": gemm_ms, "tflops_gemm_filter": flops / (gemm_ms * 1e-3) / 1e12, "tflops_end_to_end": flops / (ms * 1e-3) / 1e12,
+            "bf16_peak_tflops": peak, "frac_of_bf16_peak": flops / (gemm_ms * 1e-3) / 1e12 / peak, "users_per_s": n_users / (ms * 1e-3),
+            "exact_fp32_path_users_per_s": 4096 / (ms_exact * 1e-3), "topk_overlap_vs_exact": overlap}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -297,6 +340,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-recommend", action="store_true", help="skip the secondary recommend() tensor-core measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

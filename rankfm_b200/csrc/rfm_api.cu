@@ -725,7 +725,7 @@ static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_use
     return RFM_OK;
 }
 
-constexpr int kCandCap = 1024;       // candidate slots per (user row, item split)
+constexpr int kCandCap = 512;        // candidate slots per (user row, item split)
 
 static int ensure_gemm_items(rfm_session* s)
 {
@@ -747,7 +747,14 @@ static int ensure_gemm_items(rfm_session* s)
     return RFM_OK;
 }
 
-// tensor-core path for users whose shortlist target fits the candidate buffer (rfm_gemm.cu)
+static int shortlist_target(rfm_session* s, int32_t u, int32_t n_items, int32_t filter_previous)
+{
+    int need = 2 * n_items + 16;                                   // 2x absorbs the bf16 rounding of the candidate scores
+    if (filter_previous && u >= 0) need += (int)(s->h_indptr[(size_t)u + 1] - s->h_indptr[(size_t)u]);
+    return need;
+}
+
+// tensor-core path (rfm_gemm.cu): pass 1 block maxima -> per-row threshold -> pass 2 candidates -> exact re-score -> top-n
 static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
                         float* d_rec, float* gemm_ms)
 {
@@ -755,43 +762,64 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     if (n_users <= 0) return RFM_OK;
     int rc = ensure_gemm_items(s);
     if (rc) return rc;
-    const int Kp = gemm_kp(T), BN = gemm_block_n(T), I_pad = s->gemm_I_pad, n_tiles = I_pad / BN;
-    const int64_t max_rows = 16384;
+    const int Kp = gemm_kp(T), BN = gemm_block_n(T), I_pad = s->gemm_I_pad, n_tiles = I_pad / BN, n_sub = I_pad / 64;
+    int64_t max_rows = std::min<int64_t>(16384, (((int64_t)1 << 30) / ((int64_t)n_sub * 4)) / 128 * 128);
+    max_rows = std::max<int64_t>(128, max_rows);
     void* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
-    auto done = [&](int code) { cudaFree(d_A); cudaFree(d_ntgt); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_S2); cudaFree(d_map); return code; };
+    float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr;
+    auto done = [&](int code) { cudaFree(d_A); cudaFree(d_ntgt); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_S2); cudaFree(d_map);
+                                cudaFree(d_rowmax); cudaFree(d_tau); cudaFree(d_fix); cudaFree(d_fix_users); return code; };
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + 127) / 128 * 128);
     const int max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(8, n_tiles), (2 * s->n_sm + rows_alloc / 128 - 1) / (rows_alloc / 128)));
     CU(cudaMalloc(&d_A, (size_t)rows_alloc * Kp * 2));
     if ((rc = dev_alloc(&d_ntgt, (size_t)rows_alloc))) return done(rc);
+    if ((rc = dev_alloc(&d_tau, (size_t)rows_alloc))) return done(rc);
+    if ((rc = dev_alloc(&d_rowmax, (size_t)rows_alloc * n_sub))) return done(rc);
     if ((rc = dev_alloc(&d_cand, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
     if ((rc = dev_alloc(&d_cnt, (size_t)rows_alloc * max_splits))) return done(rc);
     if ((rc = dev_alloc(&d_S2, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
     if ((rc = dev_alloc(&d_map, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
-    std::vector<int> ntgt((size_t)rows_alloc);
+    std::vector<int> ntgt((size_t)rows_alloc), cnt_h;
     cudaEvent_t a = nullptr, b = nullptr;
     if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
     for (int64_t off = 0; off < n_users; off += rows_alloc) {
         const int nb = (int)std::min<int64_t>(rows_alloc, n_users - off);
         const int M_pad = (nb + 127) / 128 * 128;
         const int n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(max_splits, (2 * s->n_sm + M_pad / 128 - 1) / (M_pad / 128)));
-        for (int r = 0; r < M_pad; ++r) {
-            int need = 2 * n_items + 16;
-            if (r < nb && filter_previous && h_users[off + r] >= 0) need += (int)(s->h_indptr[h_users[off + r] + 1] - s->h_indptr[h_users[off + r]]);
-            ntgt[(size_t)r] = need;
-        }
+        for (int r = 0; r < M_pad; ++r) ntgt[(size_t)r] = shortlist_target(s, r < nb ? h_users[off + r] : -1, n_items, filter_previous);
         CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), (size_t)M_pad * 4, cudaMemcpyHostToDevice, s->st));
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
         if (gemm_ms) CU(cudaEventRecord(a, s->st));
-        cudaError_t e = launch_score_filter(T, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_ntgt, kCandCap, nullptr, s->st);
-        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e)));
+        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
+        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
+        CU(launch_row_threshold(d_rowmax, M_pad, n_sub, d_ntgt, d_tau, s->st));
+        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_tau, kCandCap, nullptr, nullptr, s->st);
+        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         if (gemm_ms) CU(cudaEventRecord(b, s->st));
         e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, n_splits, kCandCap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "rescore launch failed: %s", cudaGetErrorString(e)));
         e = launch_topn_select(d_S2, n_splits * kCandCap, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "topn_select launch failed: %s", cudaGetErrorString(e)));
-        s->launches += 4;
+        s->launches += 6;
+        // rows whose candidate buffer overflowed (pathological ties / clustered scores) are redone on the exact path
+        cnt_h.resize((size_t)nb * n_splits);
+        CU(cudaMemcpyAsync(cnt_h.data(), d_cnt, (size_t)nb * n_splits * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaStreamSynchronize(s->st));
         if (gemm_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); *gemm_ms += ms; }
+        std::vector<int32_t> redo_users; std::vector<int> redo_rows;
+        for (int r = 0; r < nb; ++r)
+            for (int sp = 0; sp < n_splits; ++sp)
+                if (cnt_h[(size_t)r * n_splits + sp] > kCandCap) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); break; }
+        if (!redo_users.empty()) {
+            cudaFree(d_fix); cudaFree(d_fix_users); d_fix = nullptr; d_fix_users = nullptr;
+            if ((rc = dev_alloc(&d_fix_users, redo_users.size()))) return done(rc);
+            if ((rc = dev_alloc(&d_fix, redo_users.size() * n_items))) return done(rc);
+            CU(cudaMemcpyAsync(d_fix_users, redo_users.data(), redo_users.size() * 4, cudaMemcpyHostToDevice, s->st));
+            if ((rc = recommend_exact(s, d_fix_users, (int64_t)redo_users.size(), n_items, filter_previous, d_fix, nullptr))) return done(rc);
+            for (size_t k = 0; k < redo_rows.size(); ++k)
+                CU(cudaMemcpyAsync(d_rec + (size_t)(off + redo_rows[k]) * n_items, d_fix + k * n_items, (size_t)n_items * 4, cudaMemcpyDeviceToDevice, s->st));
+            CU(cudaStreamSynchronize(s->st));
+        }
     }
     if (gemm_ms) { cudaEventDestroy(a); cudaEventDestroy(b); }
     return done(RFM_OK);
@@ -814,14 +842,15 @@ static int64_t recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, in
     order.resize((size_t)n);
     const int mode = recommend_mode();
     const Tables& T = s->T;
-    bool tc = mode != 2 && gemm_supported(T) && encode_ok() && (mode == 1 || ((int64_t)T.I >= 4096 && n * (int64_t)T.I >= ((int64_t)1 << 24)));
-    const int limit = kCandCap - gemm_block_n(T) - 32;
+    bool tc = mode != 2 && gemm_supported(T) && encode_ok() && (mode == 1 || ((int64_t)T.I >= 32768 && n * (int64_t)T.I >= ((int64_t)1 << 26)));
+    // the per-row threshold is the n'-th largest maximum over 64-item blocks: needs comfortably more blocks than n'
+    const int BN = gemm_block_n(T);
+    const int n_sub = ((T.I + BN - 1) / BN * BN) / 64;
+    const int limit = std::min(kCandCap / 2, n_sub / 2);
     if (2 * n_items + 16 > limit) tc = false;
     int64_t lo = 0, hi = n;
     for (int64_t k = 0; k < n; ++k) {
-        bool light = tc;
-        if (light && filter_previous && hu[(size_t)k] >= 0)
-            light = 2 * n_items + 16 + (s->h_indptr[hu[(size_t)k] + 1] - s->h_indptr[hu[(size_t)k]]) <= limit;
+        const bool light = tc && shortlist_target(s, hu[(size_t)k], n_items, filter_previous) <= limit;
         if (light) order[(size_t)lo++] = k; else order[(size_t)--hi] = k;
     }
     return lo;
@@ -929,7 +958,7 @@ extern "C" int rfm_session_debug_gemm(rfm_session* s, const float* users, int64_
     if ((rc = dev_alloc(&d_S, (size_t)M_pad * I_pad))) return rc;
     CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     CU(launch_pack_gemm_users(T, d_users, (int)n_users, M_pad, Kp, d_A, s->st));
-    cudaError_t e = launch_score_filter(T, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, d_S, s->st);
+    cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
     if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e));
     CU(cudaMemcpy2DAsync(scores_out, (size_t)T.I * 4, d_S, (size_t)I_pad * 4, (size_t)T.I * 4, (size_t)n_users, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));

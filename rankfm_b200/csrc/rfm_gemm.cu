@@ -13,10 +13,12 @@
 //       K=16 per instruction, issued by one elected thread) -> accumulators in TMEM (2 stages) -> tcgen05.ld in the
 //       epilogue warps.  One CTA owns 128 users (A stays resident in shared memory) and streams its slice of item
 //       tiles; warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
-//       The epilogue never writes scores: thread r owns user row r, keeps a running threshold tau_r and appends
-//       (score, item) to the row's candidate buffer only when score >= tau_r; when the buffer fills, the row's
-//       n'-th largest candidate becomes the new tau_r and the buffer is compacted.  tau only ever rises, so the
-//       buffer always contains the row's n' best items (by bf16 score) seen so far.
+//       The epilogue never writes scores.  Two passes over the same GEMM (thread r of the epilogue owns user row r):
+//         pass 1 (MODE_ROWMAX)  only the maximum of every 64-item block is kept (one FMNMX per score).  The n'-th
+//                               largest block maximum of a row is a valid lower bound tau_r of its n'-th best score
+//                               (row_threshold_kernel, exact radix select over the block maxima).
+//         pass 2 (MODE_FILTER)  (score, item) is appended to the row's candidate buffer only when score >= tau_r:
+//                               a superset of the row's n' best items, typically 1-2x n' entries.
 //   rescore_kernel        exact fp32 utility of the surviving candidates (same code as predict), seen items masked
 //   topn_select_kernel    (rfm_score.cu) exact top-n of the shortlist.
 //
@@ -141,19 +143,22 @@ struct GemmParams {
     int n_splits;                // item-range splits (grid.y)
     int n_users;                 // valid rows of A
     int nstage;
-    // filter mode
+    // MODE_FILTER
     float2* cand;                // [M_pad * n_splits, cap]  (score, item index as int bits)
-    int* cand_cnt;               // [M_pad * n_splits]
-    const int* n_target;         // [M_pad] candidates to keep per row
+    int* cand_cnt;               // [M_pad * n_splits]; cap+1 flags an overflowing row
+    const float* tau;            // [M_pad] per-row threshold from pass 1
     int cap;
-    // dump mode
-    float* S;                    // [M_pad, I_pad] or nullptr
+    // MODE_ROWMAX
+    float* rowmax;               // [M_pad, I_pad/64] block maxima
+    // MODE_DUMP
+    float* S;                    // [M_pad, I_pad]
     long long ldS;
 };
 
 constexpr int kGemmThreads = 256;
+constexpr int MODE_DUMP = 0, MODE_ROWMAX = 1, MODE_FILTER = 2;
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
 {
@@ -235,43 +240,33 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int r = wq * 32 + lane;
         const int row = m0 + r;
         const bool row_ok = row < p.n_users;
-        const bool filter = p.S == nullptr;
-        float tau = -INFINITY;
+        const float tau = MODE == MODE_FILTER ? p.tau[row] : 0.f;
         int cnt = 0;
         const int cap = p.cap;
-        const int ntgt = filter ? p.n_target[row] : 0;
-        float2* my = filter ? p.cand + ((size_t)row * p.n_splits + blockIdx.y) * cap : nullptr;
+        float2* my = MODE == MODE_FILTER ? p.cand + ((size_t)row * p.n_splits + blockIdx.y) * cap : nullptr;
+        float* rmax = MODE == MODE_ROWMAX ? p.rowmax + (size_t)row * (p.n_tiles * (BLOCK_N / 64)) : nullptr;
 
         for (int it = 0; it < my_tiles; ++it) {
             const int as = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            if (filter && __any_sync(0xffffffffu, cnt > cap - BLOCK_N)) {
-                // raise the threshold to the ntgt-th largest candidate (bisection on the ordered key) and compact
-                if (cnt > ntgt) {
-                    uint32_t lo = 0u, hi = 0xffffffffu;             // invariant: count(key >= lo) >= ntgt
-                    for (int pass = 0; pass < 32 && lo < hi; ++pass) {
-                        const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;
-                        int c = 0;
-                        for (int k = 0; k < cnt; ++k) c += ord_key(my[k].x) >= mid;
-                        if (c >= ntgt) lo = mid; else hi = mid - 1u;
-                    }
-                    int j = 0;
-                    for (int k = 0; k < cnt; ++k) { const float2 e = my[k]; if (ord_key(e.x) >= lo) my[j++] = e; }
-                    cnt = j;
-                    const uint32_t kb = lo;                         // invert ord_key
-                    tau = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb);
-                }
-            }
             bar_wait(bar_tfull + 8u * as, aph);
             tc_fence_after();
             const int n0 = (t0 + it) * BLOCK_N;
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BLOCK_N);
+            float blockmax = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 float v[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
                 const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
-                if (filter) {
+                if (MODE == MODE_DUMP) {
+                    float* out = p.S + (size_t)row * p.ldS + n0 + c * 32;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = __ldg(b4 + q);
+                        reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w);
+                    }
+                } else {
                     float mx = -INFINITY;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -279,17 +274,13 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
                         mx = fmaxf(mx, fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
                     }
-                    if (row_ok && mx >= tau) {
+                    if (MODE == MODE_ROWMAX) {
+                        blockmax = (c & 1) ? fmaxf(blockmax, mx) : mx;
+                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + (c >> 1)] = blockmax;
+                    } else if (row_ok && mx >= tau) {
 #pragma unroll
                         for (int k = 0; k < 32; ++k)
-                            if (v[k] >= tau && cnt < cap) { my[cnt] = make_float2(v[k], __int_as_float(n0 + c * 32 + k)); ++cnt; }
-                    }
-                } else {
-                    float* out = p.S + (size_t)row * p.ldS + n0 + c * 32;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = __ldg(b4 + q);
-                        reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w);
+                            if (v[k] >= tau) { if (cnt < cap) my[cnt] = make_float2(v[k], __int_as_float(n0 + c * 32 + k)); ++cnt; }
                     }
                 }
             }
@@ -297,7 +288,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) bar_arrive(bar_tempty + 8u * as);
         }
-        if (filter) p.cand_cnt[(size_t)row * p.n_splits + blockIdx.y] = row_ok ? cnt : 0;
+        if (MODE == MODE_FILTER) p.cand_cnt[(size_t)row * p.n_splits + blockIdx.y] = row_ok ? min(cnt, cap + 1) : 0;
     }
 
     tc_fence_before();
@@ -330,7 +321,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const Tables T, const int3
     const long long span = ((long long)width + stride - 1) / stride * stride;
     for (long long e = group_global; e < span; e += stride) {
         const int slot = (int)(e / cap), k = (int)(e % cap);
-        const bool inb = known && e < width && k < __ldg(cand_cnt + (size_t)b * slots + slot);
+        const bool inb = known && e < width && k < min(__ldg(cand_cnt + (size_t)b * slots + slot), cap);
         int item = 0;
         if (inb) item = __float_as_int(cand[((size_t)b * slots + slot) * cap + k].y);
         const bool ok = inb && item >= 0 && item < T.I;
@@ -419,33 +410,79 @@ cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_
     return cudaGetLastError();
 }
 
-// S == nullptr: filter mode (cand/cand_cnt/n_target/cap required); else dump mode (S [M_pad, I_pad])
-cudaError_t launch_score_filter(const Tables& T, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
-                                float2* cand, int* cand_cnt, const int* n_target, int cap, float* S, cudaStream_t st)
+// n_target[row]-th largest of the row's block maxima -> tau[row]  (one block per row, radix select over ordered keys)
+__global__ void __launch_bounds__(256) row_threshold_kernel(const float* __restrict__ rowmax, int n_blocks, const int* __restrict__ n_target,
+                                                            float* __restrict__ tau)
+{
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float* v = rowmax + (size_t)row * n_blocks;
+    const int want = n_target[row];
+    if (want > n_blocks) { if (tid == 0) tau[row] = -INFINITY; return; }
+    if (tid == 0) { s_prefix = 0u; s_remaining = (uint32_t)want; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int k = tid; k < n_blocks; k += 256) {
+            const uint32_t key = ord_key(v[k]);
+            if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t remaining = s_remaining, bin = 0u;
+            for (int d = 255; d >= 0; --d) { if (hist[d] >= remaining) { bin = (uint32_t)d; break; } remaining -= hist[d]; }
+            s_prefix = prefix | (bin << shift);
+            s_remaining = remaining;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { const uint32_t kb = s_prefix; tau[row] = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb); }
+}
+
+cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st)
+{
+    row_threshold_kernel<<<n_rows, 256, 0, st>>>(rowmax, n_blocks, n_target, tau);
+    return cudaGetLastError();
+}
+
+template <int BN, int MODE>
+static cudaError_t launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(score_filter_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    score_filter_kernel<BN, MODE><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+// mode 0: dump dense scores into S [M_pad, I_pad]; 1: block maxima into rowmax [M_pad, I_pad/64];
+// 2: candidates with score >= tau[row] into cand/cand_cnt
+cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
+                                float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st)
 {
     const int Kp = gemm_kp(T), BN = gemm_block_n(T);
     alignas(64) CUtensorMap tmA, tmB;
     if (!make_map(&tmA, A, M_pad, Kp, 128) || !make_map(&tmB, B, I_pad, Kp, BN)) return cudaErrorNotSupported;
     GemmParams p{};
     p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = I_pad / BN; p.n_splits = n_splits; p.n_users = n_users;
-    p.cand = cand; p.cand_cnt = cand_cnt; p.n_target = n_target; p.cap = cap; p.S = S; p.ldS = I_pad;
+    p.cand = cand; p.cand_cnt = cand_cnt; p.tau = tau; p.cap = cap; p.rowmax = rowmax; p.S = S; p.ldS = I_pad;
     const size_t a_bytes = (size_t)p.kblocks * 128 * 128, stage_bytes = (size_t)p.kblocks * BN * 128;
     int nstage = (int)((200 * 1024 - a_bytes) / stage_bytes);
     nstage = nstage > 4 ? 4 : (nstage < 2 ? 2 : nstage);
     p.nstage = nstage;
     const size_t smem = a_bytes + nstage * stage_bytes + 8 * (2 * nstage + 5) + 16 + 1024;
     const dim3 grid(M_pad / 128, n_splits);
-    cudaError_t e;
     if (BN == 256) {
-        e = cudaFuncSetAttribute(score_filter_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        score_filter_kernel<256><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
-    } else {
-        e = cudaFuncSetAttribute(score_filter_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        score_filter_kernel<128><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+        if (mode == MODE_DUMP) return launch_mode<256, MODE_DUMP>(tmA, tmB, p, grid, smem, st);
+        if (mode == MODE_ROWMAX) return launch_mode<256, MODE_ROWMAX>(tmA, tmB, p, grid, smem, st);
+        return launch_mode<256, MODE_FILTER>(tmA, tmB, p, grid, smem, st);
     }
-    return cudaGetLastError();
+    if (mode == MODE_DUMP) return launch_mode<128, MODE_DUMP>(tmA, tmB, p, grid, smem, st);
+    if (mode == MODE_ROWMAX) return launch_mode<128, MODE_ROWMAX>(tmA, tmB, p, grid, smem, st);
+    return launch_mode<128, MODE_FILTER>(tmA, tmB, p, grid, smem, st);
 }
 
 }  // namespace rfm

@@ -365,8 +365,10 @@ def test_rankfm_class_replay_matches_reference_class(gpu_lib):
 # tensor-core (tcgen05) candidate generation for recommend
 # ---------------------------------------------------------------------------------------------------------------
 def _scoring_session(U, I, F, P, Q, seed):
-    X = zipf_interactions(U, I, max(4 * U, 2000), seed=seed)
-    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    rng0 = np.random.default_rng(seed + 99)
+    X = np.concatenate([np.stack([rng0.integers(0, U, 4 * U), rng0.integers(0, I, 4 * U)], 1),
+                        np.stack([np.arange(U), rng0.integers(0, I, U)], 1), np.stack([rng0.integers(0, U, I), np.arange(I)], 1)])
+    X = np.unique(X, axis=0).astype(np.int32)              # every user and every item occurs: U and I are exactly as asked
     indptr, indices = csr_of(X, U)
     ui = CSRItems(indptr, indices)
     x_uf, x_if = features(U, I, P, Q, seed=seed)
@@ -401,7 +403,7 @@ def test_tcgen05_gemm_scores_match_fp32(gpu_lib, F, P, Q, I):
 @pytest.mark.parametrize("F,P,Q", [(32, 0, 0), (20, 2, 3)])
 @pytest.mark.parametrize("filt", [False, True])
 def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, monkeypatch):
-    sess, w, ui, x_uf, x_if, U, I = _scoring_session(600, 6000, F, P, Q, seed=7 + F)
+    sess, w, ui, x_uf, x_if, U, I = _scoring_session(600, 40000, F, P, Q, seed=7 + F)
     rng = np.random.default_rng(0)
     users = rng.integers(0, U, 300).astype(np.float32)
     users[5] = np.nan
