@@ -145,7 +145,7 @@ struct rfm_session {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int32_t* d_trace = nullptr;
     // tensor-core recommend: bf16 item operand + bias, rebuilt lazily whenever the weights change
-    void* d_gemm_B = nullptr; float* d_gemm_bias = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
+    void* d_gemm_B = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
     std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
     float* d_flush = nullptr; size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;
@@ -210,7 +210,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
     cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
-    cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
+    cudaFree(s->d_gemm_B);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
     if (s->st) cudaStreamDestroy(s->st);
@@ -725,7 +725,7 @@ static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_use
     return RFM_OK;
 }
 
-constexpr int kCandCap = 512;        // candidate slots per (user row, item split)
+constexpr int kCandCap = 256;        // candidate slots per (user row, item split, column half)
 
 static int ensure_gemm_items(rfm_session* s)
 {
@@ -734,14 +734,12 @@ static int ensure_gemm_items(rfm_session* s)
     const int Kp = gemm_kp(T), BN = gemm_block_n(T);
     const int I_pad = (T.I + BN - 1) / BN * BN;
     if (!s->d_gemm_B || s->gemm_I_pad != I_pad) {
-        cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
-        s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr;
+        cudaFree(s->d_gemm_B);
+        s->d_gemm_B = nullptr;
         CU(cudaMalloc(&s->d_gemm_B, (size_t)I_pad * Kp * 2));
-        int rc = dev_alloc(&s->d_gemm_bias, (size_t)I_pad);
-        if (rc) return rc;
         s->gemm_I_pad = I_pad;
     }
-    CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->d_gemm_bias, s->st));
+    CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->st));
     s->launches += 1;
     s->gemm_valid = true;
     return RFM_OK;
@@ -775,10 +773,10 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     if ((rc = dev_alloc(&d_ntgt, (size_t)rows_alloc))) return done(rc);
     if ((rc = dev_alloc(&d_tau, (size_t)rows_alloc))) return done(rc);
     if ((rc = dev_alloc(&d_rowmax, (size_t)rows_alloc * n_sub))) return done(rc);
-    if ((rc = dev_alloc(&d_cand, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
-    if ((rc = dev_alloc(&d_cnt, (size_t)rows_alloc * max_splits))) return done(rc);
-    if ((rc = dev_alloc(&d_S2, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
-    if ((rc = dev_alloc(&d_map, (size_t)rows_alloc * max_splits * kCandCap))) return done(rc);
+    if ((rc = dev_alloc(&d_cand, (size_t)rows_alloc * 2 * max_splits * kCandCap))) return done(rc);
+    if ((rc = dev_alloc(&d_cnt, (size_t)rows_alloc * 2 * max_splits))) return done(rc);
+    if ((rc = dev_alloc(&d_S2, (size_t)rows_alloc * 2 * max_splits * kCandCap))) return done(rc);
+    if ((rc = dev_alloc(&d_map, (size_t)rows_alloc * 2 * max_splits * kCandCap))) return done(rc);
     std::vector<int> ntgt((size_t)rows_alloc), cnt_h;
     cudaEvent_t a = nullptr, b = nullptr;
     if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
@@ -790,26 +788,26 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), (size_t)M_pad * 4, cudaMemcpyHostToDevice, s->st));
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
         if (gemm_ms) CU(cudaEventRecord(a, s->st));
-        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
+        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, nb, M_pad, I_pad, n_splits, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         CU(launch_row_threshold(d_rowmax, M_pad, n_sub, d_ntgt, d_tau, s->st));
-        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_tau, kCandCap, nullptr, nullptr, s->st);
+        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_tau, kCandCap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         if (gemm_ms) CU(cudaEventRecord(b, s->st));
-        e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, n_splits, kCandCap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, s->st);
+        e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, 2 * n_splits, kCandCap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "rescore launch failed: %s", cudaGetErrorString(e)));
-        e = launch_topn_select(d_S2, n_splits * kCandCap, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
+        e = launch_topn_select(d_S2, 2 * n_splits * kCandCap, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "topn_select launch failed: %s", cudaGetErrorString(e)));
         s->launches += 6;
         // rows whose candidate buffer overflowed (pathological ties / clustered scores) are redone on the exact path
-        cnt_h.resize((size_t)nb * n_splits);
-        CU(cudaMemcpyAsync(cnt_h.data(), d_cnt, (size_t)nb * n_splits * 4, cudaMemcpyDeviceToHost, s->st));
+        cnt_h.resize((size_t)nb * 2 * n_splits);
+        CU(cudaMemcpyAsync(cnt_h.data(), d_cnt, (size_t)nb * 2 * n_splits * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaStreamSynchronize(s->st));
         if (gemm_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); *gemm_ms += ms; }
         std::vector<int32_t> redo_users; std::vector<int> redo_rows;
         for (int r = 0; r < nb; ++r)
-            for (int sp = 0; sp < n_splits; ++sp)
-                if (cnt_h[(size_t)r * n_splits + sp] > kCandCap) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); break; }
+            for (int sp = 0; sp < 2 * n_splits; ++sp)
+                if (cnt_h[(size_t)r * 2 * n_splits + sp] > kCandCap) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); break; }
         if (!redo_users.empty()) {
             cudaFree(d_fix); cudaFree(d_fix_users); d_fix = nullptr; d_fix_users = nullptr;
             if ((rc = dev_alloc(&d_fix_users, redo_users.size()))) return done(rc);
@@ -846,7 +844,7 @@ static int64_t recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, in
     // the per-row threshold is the n'-th largest maximum over 64-item blocks: needs comfortably more blocks than n'
     const int BN = gemm_block_n(T);
     const int n_sub = ((T.I + BN - 1) / BN * BN) / 64;
-    const int limit = std::min(kCandCap / 2, n_sub / 2);
+    const int limit = std::min(kCandCap, n_sub / 2);
     if (2 * n_items + 16 > limit) tc = false;
     int64_t lo = 0, hi = n;
     for (int64_t k = 0; k < n; ++k) {
@@ -958,7 +956,7 @@ extern "C" int rfm_session_debug_gemm(rfm_session* s, const float* users, int64_
     if ((rc = dev_alloc(&d_S, (size_t)M_pad * I_pad))) return rc;
     CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     CU(launch_pack_gemm_users(T, d_users, (int)n_users, M_pad, Kp, d_A, s->st));
-    cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
+    cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
     if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e));
     CU(cudaMemcpy2DAsync(scores_out, (size_t)T.I * 4, d_S, (size_t)I_pad * 4, (size_t)T.I * 4, (size_t)n_users, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));

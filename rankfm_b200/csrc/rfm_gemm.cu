@@ -35,13 +35,25 @@ namespace rfm {
 // ---------------------------------------------------------------------------------------------------------------
 // operand packing: bf16 A (requested users) / B (all items), fp32 bias
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void pack_gemm_items_kernel(const Tables T, int Kp, int I_pad, __nv_bfloat16* __restrict__ B, float* __restrict__ bias)
+// K layout of both operands: [ factor block(s) : Kraw-2 columns | bias_hi | bias_lo | zero pad to a multiple of 64 ].
+// The item bias rides inside the GEMM as two bf16 columns (hi + lo, relative error 2^-17) against two columns of ones
+// in A, so the epilogue never touches a bias vector.
+__global__ void pack_gemm_items_kernel(const Tables T, int Kraw, int Kp, int I_pad, __nv_bfloat16* __restrict__ B)
 {
     const long long n = (long long)I_pad * Kp;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e / Kp), c = (int)(e % Kp);
         float v = 0.f;
-        if (i < T.I) {
+        if (c >= Kraw - 2 && c < Kraw) {
+            float b = -1e30f;                                                // padded items never pass any threshold
+            if (i < T.I) {
+                const float* row = T.IT + (size_t)i * T.ldi;
+                b = row[T.Fp];
+                if (T.x_if_any) for (int q = 0; q < T.Q; ++q) b += row[T.Fp + 4 + q] * T.GP[q];
+            }
+            const float hi = __bfloat162float(__float2bfloat16(b));
+            v = c == Kraw - 2 ? hi : (i < T.I ? b - hi : 0.f);
+        } else if (i < T.I) {
             const float* row = T.IT + (size_t)i * T.ldi;
             if (c < T.F) v = row[c];
             else if (T.x_if_any && c >= T.Fp && c - T.Fp < T.F) {             // second half: x_if[i] . v_if[:, f]
@@ -51,18 +63,9 @@ __global__ void pack_gemm_items_kernel(const Tables T, int Kp, int I_pad, __nv_b
         }
         B[e] = __float2bfloat16(v);
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I_pad; i += gridDim.x * blockDim.x) {
-        float b = -INFINITY;                                                 // padded items never pass the filter
-        if (i < T.I) {
-            const float* row = T.IT + (size_t)i * T.ldi;
-            b = row[T.Fp];
-            if (T.x_if_any) for (int q = 0; q < T.Q; ++q) b += row[T.Fp + 4 + q] * T.GP[q];
-        }
-        bias[i] = b;
-    }
 }
 
-__global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, int M_pad, int Kp, __nv_bfloat16* __restrict__ A)
+__global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, int M_pad, int Kraw, int Kp, __nv_bfloat16* __restrict__ A)
 {
     const long long n = (long long)M_pad * Kp;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -71,7 +74,8 @@ __global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict
         const int u = r < n_users ? users[r] : -1;
         if (u >= 0) {
             const float* row = T.UT + (size_t)u * T.ldu;
-            if (c < T.F) {
+            if (c >= Kraw - 2 && c < Kraw) v = 1.0f;
+            else if (c < T.F) {
                 v = row[c];
                 if (T.x_uf_any) for (int p = 0; p < T.P; ++p) v += row[T.Fp + p] * T.GP[T.gp_vuf + (size_t)p * T.Fp + c];
             } else if (T.x_if_any && c >= T.Fp && c - T.Fp < T.F) v = row[c - T.Fp];
@@ -137,15 +141,14 @@ __device__ __forceinline__ uint32_t ord_key(float s) { const uint32_t b = __floa
 // the GEMM + running-threshold filter
 // ---------------------------------------------------------------------------------------------------------------
 struct GemmParams {
-    const float* bias;           // [I_pad]
     int kblocks;                 // Kp / 64
     int n_tiles;                 // I_pad / BLOCK_N
     int n_splits;                // item-range splits (grid.y)
     int n_users;                 // valid rows of A
     int nstage;
     // MODE_FILTER
-    float2* cand;                // [M_pad * n_splits, cap]  (score, item index as int bits)
-    int* cand_cnt;               // [M_pad * n_splits]; cap+1 flags an overflowing row
+    float2* cand;                // [M_pad * 2*n_splits, cap]  (score, item index as int bits); 2 column halves per split
+    int* cand_cnt;               // [M_pad * 2*n_splits]; cap+1 flags an overflowing slot
     const float* tau;            // [M_pad] per-row threshold from pass 1
     int cap;
     // MODE_ROWMAX
@@ -155,7 +158,7 @@ struct GemmParams {
     long long ldS;
 };
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;          // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue
 constexpr int MODE_DUMP = 0, MODE_ROWMAX = 1, MODE_FILTER = 2;
 
 template <int BLOCK_N, int MODE>
@@ -183,7 +186,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < nstage; ++s) { bar_init(bar_full + 8u * s, 1); bar_init(bar_empty + 8u * s, 1); }
         bar_init(bar_a, 1);
-        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8u * a, 1); bar_init(bar_tempty + 8u * a, 4); }
+        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8u * a, 1); bar_init(bar_tempty + 8u * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -235,15 +238,18 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread <-> user row (TMEM lane) =====
+        // ===== epilogue: thread <-> user row (TMEM lane); two warps per lane quarter split the tile's columns =====
         const int wq = warp & 3;                                    // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;                           // which half of the tile's columns
+        constexpr int HALF_N = BLOCK_N / 2;
         const int r = wq * 32 + lane;
         const int row = m0 + r;
         const bool row_ok = row < p.n_users;
         const float tau = MODE == MODE_FILTER ? p.tau[row] : 0.f;
         int cnt = 0;
         const int cap = p.cap;
-        float2* my = MODE == MODE_FILTER ? p.cand + ((size_t)row * p.n_splits + blockIdx.y) * cap : nullptr;
+        const int slot = blockIdx.y * 2 + half;
+        float2* my = MODE == MODE_FILTER ? p.cand + ((size_t)row * (2 * p.n_splits) + slot) * cap : nullptr;
         float* rmax = MODE == MODE_ROWMAX ? p.rowmax + (size_t)row * (p.n_tiles * (BLOCK_N / 64)) : nullptr;
 
         for (int it = 0; it < my_tiles; ++it) {
@@ -251,32 +257,24 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             bar_wait(bar_tfull + 8u * as, aph);
             tc_fence_after();
-            const int n0 = (t0 + it) * BLOCK_N;
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BLOCK_N);
+            const int n0 = (t0 + it) * BLOCK_N + half * HALF_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BLOCK_N + half * HALF_N);
             float blockmax = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = 0; c < HALF_N / 32; ++c) {
                 float v[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
                 if (MODE == MODE_DUMP) {
                     float* out = p.S + (size_t)row * p.ldS + n0 + c * 32;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = __ldg(b4 + q);
-                        reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w);
-                    }
+                    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 } else {
-                    float mx = -INFINITY;
+                    float mx = v[0];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = __ldg(b4 + q);
-                        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-                        mx = fmaxf(mx, fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
-                    }
+                    for (int k = 1; k < 32; ++k) mx = fmaxf(mx, v[k]);
                     if (MODE == MODE_ROWMAX) {
                         blockmax = (c & 1) ? fmaxf(blockmax, mx) : mx;
-                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + (c >> 1)] = blockmax;
+                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + half * (HALF_N / 64) + (c >> 1)] = blockmax;
                     } else if (row_ok && mx >= tau) {
 #pragma unroll
                         for (int k = 0; k < 32; ++k)
@@ -288,7 +286,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) bar_arrive(bar_tempty + 8u * as);
         }
-        if (MODE == MODE_FILTER) p.cand_cnt[(size_t)row * p.n_splits + blockIdx.y] = row_ok ? min(cnt, cap + 1) : 0;
+        if (MODE == MODE_FILTER) p.cand_cnt[(size_t)row * (2 * p.n_splits) + slot] = row_ok ? min(cnt, cap + 1) : 0;
     }
 
     tc_fence_before();
@@ -395,18 +393,19 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int Kp,
 }
 
 bool gemm_encode_available() { return encode_tiled_fn() != nullptr; }
-int gemm_kp(const Tables& T) { const int k = T.x_if_any ? 2 * T.Fp : T.Fp; return (k + 63) / 64 * 64; }
+int gemm_kraw(const Tables& T) { return (T.x_if_any ? 2 * T.Fp : T.Fp) + 2; }     // factor columns + bias hi/lo
+int gemm_kp(const Tables& T) { return (gemm_kraw(T) + 63) / 64 * 64; }
 int gemm_block_n(const Tables& T) { return gemm_kp(T) <= 128 ? 256 : 128; }
 bool gemm_supported(const Tables& T) { return gemm_kp(T) <= 256; }
 
-cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st)
+cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, cudaStream_t st)
 {
-    pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, Kp, I_pad, reinterpret_cast<__nv_bfloat16*>(B), bias);
+    pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, gemm_kraw(T), Kp, I_pad, reinterpret_cast<__nv_bfloat16*>(B));
     return cudaGetLastError();
 }
 cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st)
 {
-    pack_gemm_users_kernel<<<148 * 4, 256, 0, st>>>(T, users, n_users, M_pad, Kp, reinterpret_cast<__nv_bfloat16*>(A));
+    pack_gemm_users_kernel<<<148 * 4, 256, 0, st>>>(T, users, n_users, M_pad, gemm_kraw(T), Kp, reinterpret_cast<__nv_bfloat16*>(A));
     return cudaGetLastError();
 }
 
@@ -460,14 +459,14 @@ static cudaError_t launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, c
 
 // mode 0: dump dense scores into S [M_pad, I_pad]; 1: block maxima into rowmax [M_pad, I_pad/64];
 // 2: candidates with score >= tau[row] into cand/cand_cnt
-cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
+cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, int n_users, int M_pad, int I_pad, int n_splits,
                                 float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st)
 {
     const int Kp = gemm_kp(T), BN = gemm_block_n(T);
     alignas(64) CUtensorMap tmA, tmB;
     if (!make_map(&tmA, A, M_pad, Kp, 128) || !make_map(&tmB, B, I_pad, Kp, BN)) return cudaErrorNotSupported;
     GemmParams p{};
-    p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = I_pad / BN; p.n_splits = n_splits; p.n_users = n_users;
+    p.kblocks = Kp / 64; p.n_tiles = I_pad / BN; p.n_splits = n_splits; p.n_users = n_users;
     p.cand = cand; p.cand_cnt = cand_cnt; p.tau = tau; p.cap = cap; p.rowmax = rowmax; p.S = S; p.ldS = I_pad;
     const size_t a_bytes = (size_t)p.kblocks * 128 * 128, stage_bytes = (size_t)p.kblocks * BN * 128;
     int nstage = (int)((200 * 1024 - a_bytes) / stage_bytes);
