@@ -13,6 +13,7 @@
 
 #include "../../include/rankfm_b200.h"
 #include "rfm_kernels.h"
+#include <cuda_bf16.h>
 
 using namespace rfm;
 
@@ -146,6 +147,7 @@ struct rfm_session {
     int32_t* d_trace = nullptr;
     // tensor-core recommend: bf16 item operand + bias, rebuilt lazily whenever the weights change
     void* d_gemm_B = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
+    void* scratch[12] = {nullptr}; size_t scratch_bytes[12] = {0};   // grow-only device scratch of the recommend paths
     std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
     float* d_flush = nullptr; size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;
@@ -211,6 +213,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
     cudaFree(s->d_gemm_B);
+    for (void* q : s->scratch) cudaFree(q);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
     if (s->st) cudaStreamDestroy(s->st);
@@ -688,6 +691,21 @@ static void users_to_int(const float* users, int64_t n, std::vector<int32_t>& ou
     for (int64_t k = 0; k < n; ++k) out[(size_t)k] = std::isnan(users[k]) ? -1 : (int32_t)users[k];
 }
 
+// grow-only scratch buffers (cudaMalloc/cudaFree of hundreds of MB per call would dominate a recommend() call)
+template <typename T>
+static int scratch_get(rfm_session* s, int slot, size_t count, T** out)
+{
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if (s->scratch_bytes[slot] < bytes) {
+        cudaFree(s->scratch[slot]);
+        s->scratch[slot] = nullptr; s->scratch_bytes[slot] = 0;
+        CU(cudaMalloc(&s->scratch[slot], bytes));
+        s->scratch_bytes[slot] = bytes;
+    }
+    *out = reinterpret_cast<T*>(s->scratch[slot]);
+    return RFM_OK;
+}
+
 // exact fp32 path: score every item, exact radix select
 static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
                            float* d_rec, float* gemm_ms)
@@ -698,7 +716,7 @@ static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_use
     const int64_t max_batch = std::max<int64_t>(1, std::min<int64_t>(n_users, ((int64_t)2 << 30) / std::max(1, T.I)));
     float* S = nullptr;
     int rc;
-    if ((rc = dev_alloc(&S, (size_t)max_batch * T.I))) return rc;
+    if ((rc = scratch_get(s, 0, (size_t)max_batch * T.I, &S))) return rc;
     const int chunks = std::max(1, std::min(64, (T.I + 2047) / 2048));
     cudaEvent_t a = nullptr, b = nullptr;
     float acc_ms = 0.f;
@@ -721,7 +739,6 @@ static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_use
     }
     CU(cudaStreamSynchronize(s->st));
     if (gemm_ms) { *gemm_ms += acc_ms; cudaEventDestroy(a); cudaEventDestroy(b); }
-    cudaFree(S);
     return RFM_OK;
 }
 
@@ -763,20 +780,19 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     const int Kp = gemm_kp(T), BN = gemm_block_n(T), I_pad = s->gemm_I_pad, n_tiles = I_pad / BN, n_sub = I_pad / 64;
     int64_t max_rows = std::min<int64_t>(16384, (((int64_t)1 << 30) / ((int64_t)n_sub * 4)) / 128 * 128);
     max_rows = std::max<int64_t>(128, max_rows);
-    void* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
+    __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
     float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr;
-    auto done = [&](int code) { cudaFree(d_A); cudaFree(d_ntgt); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_S2); cudaFree(d_map);
-                                cudaFree(d_rowmax); cudaFree(d_tau); cudaFree(d_fix); cudaFree(d_fix_users); return code; };
+    auto done = [&](int code) { cudaFree(d_fix); cudaFree(d_fix_users); return code; };
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + 127) / 128 * 128);
     const int max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(8, n_tiles), (2 * s->n_sm + rows_alloc / 128 - 1) / (rows_alloc / 128)));
-    CU(cudaMalloc(&d_A, (size_t)rows_alloc * Kp * 2));
-    if ((rc = dev_alloc(&d_ntgt, (size_t)rows_alloc))) return done(rc);
-    if ((rc = dev_alloc(&d_tau, (size_t)rows_alloc))) return done(rc);
-    if ((rc = dev_alloc(&d_rowmax, (size_t)rows_alloc * n_sub))) return done(rc);
-    if ((rc = dev_alloc(&d_cand, (size_t)rows_alloc * 2 * max_splits * kCandCap))) return done(rc);
-    if ((rc = dev_alloc(&d_cnt, (size_t)rows_alloc * 2 * max_splits))) return done(rc);
-    if ((rc = dev_alloc(&d_S2, (size_t)rows_alloc * 2 * max_splits * kCandCap))) return done(rc);
-    if ((rc = dev_alloc(&d_map, (size_t)rows_alloc * 2 * max_splits * kCandCap))) return done(rc);
+    if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
+    if ((rc = scratch_get(s, 2, (size_t)rows_alloc, &d_ntgt))) return rc;
+    if ((rc = scratch_get(s, 3, (size_t)rows_alloc, &d_tau))) return rc;
+    if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub, &d_rowmax))) return rc;
+    if ((rc = scratch_get(s, 5, (size_t)rows_alloc * 2 * max_splits * kCandCap, &d_cand))) return rc;
+    if ((rc = scratch_get(s, 6, (size_t)rows_alloc * 2 * max_splits, &d_cnt))) return rc;
+    if ((rc = scratch_get(s, 7, (size_t)rows_alloc * 2 * max_splits * kCandCap, &d_S2))) return rc;
+    if ((rc = scratch_get(s, 8, (size_t)rows_alloc * 2 * max_splits * kCandCap, &d_map))) return rc;
     std::vector<int> ntgt((size_t)rows_alloc), cnt_h;
     cudaEvent_t a = nullptr, b = nullptr;
     if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }

@@ -316,18 +316,26 @@ __global__ void __launch_bounds__(256) rescore_kernel(const Tables T, const int3
     const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
     long long seg = 0; int deg = 0;
     if (known && filter_previous) { seg = __ldg(indptr + u); deg = (int)(__ldg(indptr + u + 1) - seg); }
-    const long long span = ((long long)width + stride - 1) / stride * stride;
+    // dense enumeration of the row's candidates: entry e of the concatenation of the slots' filled prefixes; output is
+    // written densely too (positions >= total are pre-filled with the "removed" marker by the memset in the launcher)
+    int total = 0;
+    for (int sl = 0; sl < slots; ++sl) total += min(__ldg(cand_cnt + (size_t)b * slots + sl), cap);
+    if (!known) total = 0;
+    const long long span = ((long long)total + stride - 1) / stride * stride;
     for (long long e = group_global; e < span; e += stride) {
-        const int slot = (int)(e / cap), k = (int)(e % cap);
-        const bool inb = known && e < width && k < min(__ldg(cand_cnt + (size_t)b * slots + slot), cap);
+        const bool inb = e < total;
         int item = 0;
-        if (inb) item = __float_as_int(cand[((size_t)b * slots + slot) * cap + k].y);
+        if (inb) {
+            int rem = (int)e, sl = 0;
+            for (; sl < slots; ++sl) { const int c = min(__ldg(cand_cnt + (size_t)b * slots + sl), cap); if (rem < c) break; rem -= c; }
+            item = __float_as_int(cand[((size_t)b * slots + sl) * cap + rem].y);
+        }
         const bool ok = inb && item >= 0 && item < T.I;
         ItemRow<QPL> it;
         load_item<G, QPL, FEAT>(T, ok ? item : 0, ok, sub, it);
         const float s = utility<G, QPL, FEAT>(uc, it);
         const bool seen = filter_previous ? group_member<G>(item, indices + seg, deg, ok, sub, gw) : false;
-        if (e < width && sub == 0) {
+        if (inb && sub == 0) {
             S2[(size_t)b * width + e] = (ok && !seen) ? s : __uint_as_float(0xffffffffu);
             idxmap[(size_t)b * width + e] = item;
         }
@@ -338,7 +346,8 @@ template <int G, int QPL>
 static cudaError_t rescore_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
                               const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, cudaStream_t st)
 {
-    const dim3 grid(max(1, min(16, (slots * cap + 255) / 256)), n_users);
+    const dim3 grid(2, n_users);
+    cudaMemsetAsync(S2, 0xff, (size_t)n_users * slots * cap * 4, st);           // 0xffffffff = "removed" marker of topn_select_kernel
     if (T.x_uf_any || T.x_if_any) rescore_kernel<G, QPL, true><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap);
     else rescore_kernel<G, QPL, false><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap);
     return cudaGetLastError();
