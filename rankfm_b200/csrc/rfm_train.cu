@@ -181,8 +181,13 @@ __device__ __forceinline__ void smem_item(const Tables& T, const float* s, int s
 
 constexpr int kPipeBarBytes = 128;      // up to 16 mbarriers per warp, keeps the stages 128-byte aligned
 
+// resident blocks per SM the register allocator is told to aim for: BPR fits 3 without spilling; the WARP look-ahead
+// sampler and the feature variants need the 128-register budget of 2
+template <int QPL, bool FEAT, bool WARP>
+constexpr int pipe_min_blocks() { return QPL > 2 ? 1 : ((FEAT || WARP || QPL == 2) ? 2 : 3); }
+
 template <int G, int QPL, bool FEAT, bool WARP, bool TRED>
-__global__ void __launch_bounds__(kTrainThreads, (QPL == 1 && !FEAT) ? 3 : (QPL <= 2 ? 2 : 1)) sgd_pipe_kernel(const TrainParams p)
+__global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP>()) sgd_pipe_kernel(const TrainParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Tables& T = p.T;
