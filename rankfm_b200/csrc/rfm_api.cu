@@ -539,13 +539,15 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     std::vector<float> etas((size_t)epochs);
     const char* spec_s = getenv("RANKFM_B200_SPEC");          // 0 (default) = adaptive, else force 1 / 2 / 4
     const int spec_env = spec_s ? atoi(spec_s) : 0;
-    // Hogwild staleness cap: never keep more than 1/16 of an epoch in flight, so that on small inputs the schedule
+    // Hogwild staleness cap: never keep more than 1/8 of an epoch in flight, so that on small inputs the schedule
     // degrades towards sequential SGD instead of one giant stale batch (large inputs always get the full machine).
     // A warp of the pipelined kernel holds one batch of 32 positives.
     int grid = s->grid;
     {
         const long long in_flight_per_block = (long long)(kTrainThreads / 32) * 32;
-        const long long cap_blocks = std::max<long long>(1, (s->N / 16) / in_flight_per_block);
+        long long div = 8;
+        if (const char* e = getenv("RANKFM_B200_INFLIGHT_DIV")) div = std::max(1, atoi(e));      // experiments
+        const long long cap_blocks = std::max<long long>(1, (s->N / div) / in_flight_per_block);
         grid = (int)std::min<long long>(grid, cap_blocks);
     }
 
