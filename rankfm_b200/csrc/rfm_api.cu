@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <dlfcn.h>
 #include <string>
 #include <vector>
@@ -245,9 +246,16 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
 #define TRY(x) do { rc = (x); if (rc) return bail(rc); } while (0)
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(RFM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
     CUB(cudaSetDevice(s->device));
-    cudaDeviceProp prop;
-    CUB(cudaGetDeviceProperties(&prop, s->device));
-    s->n_sm = prop.multiProcessorCount;
+    {
+        static int sm_count_cache[64] = {0};                       // cudaGetDeviceProperties costs ~1 ms per call
+        if (s->device < 64 && sm_count_cache[s->device] > 0) s->n_sm = sm_count_cache[s->device];
+        else {
+            int n = 0;
+            CUB(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, s->device));
+            s->n_sm = n;
+            if (s->device < 64) sm_count_cache[s->device] = n;
+        }
+    }
     CUB(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
 
     Tables& T = s->T;
@@ -1023,19 +1031,32 @@ extern "C" int rfm_session_launch_count(rfm_session* s, int64_t* launches)
 // ---------------------------------------------------------------------------------------------------------------
 // one-shot entry points on host buffers
 // ---------------------------------------------------------------------------------------------------------------
+static double now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 extern "C" int rfm_fit(const rfm_problem* p, int32_t epochs, const int32_t* perms, rfm_epoch_stats* stats)
 {
+    const bool timing = getenv("RANKFM_B200_TIMING") != nullptr;
+    const double t0 = now_ms();
     rfm_session* s = nullptr;
     int rc = rfm_session_create(p, &s);
     if (rc) return rc;
+    const double t1 = now_ms();
     rc = rfm_session_train(s, epochs, perms, stats);
+    const double t2 = now_ms();
     // like the reference, weights are written back even when they went non-finite (_rankfm.pyx:329 raises after mutation)
     if (rc == RFM_OK || rc == RFM_ERR_NONFINITE) {
         const std::string keep = g_err;
         int rc2 = rfm_session_download(s, p->w_i, p->w_if, p->v_u, p->v_i, p->v_uf, p->v_if);
         if (rc2) rc = rc2; else g_err = keep;
     }
+    const double t3 = now_ms();
     rfm_session_destroy(s);
+    if (timing) fprintf(stderr, "[rfm_fit] create+H2D %.2f ms, train %.2f ms, D2H %.2f ms, destroy %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
     return rc;
 }
 
