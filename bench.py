@@ -92,12 +92,9 @@ class ClockSampler:
 def make_workload(name, rank=0, world=1):
     c = dict(CONFIGS[name])
     X = zipf_interactions(c["U"], c["I"], c["N"], seed=42 + rank, a_u=float(os.environ.get("BENCH_ZIPF_U", 0.6)), a_i=float(os.environ.get("BENCH_ZIPF_I", 1.0)))
-    U_local = int(X[:, 0].max()) + 1
-    c["U_local"] = U_local
     U_alloc = c["U"]                                       # fixed block per rank so every rank agrees on the global U
     X[:, 0] += rank * U_alloc
     c["U_global"] = U_alloc * world
-    c["I_obs"] = c["I"]
     c["X"] = X
     c["sw"] = np.ones(len(X), np.float32)
     c["x_uf"], c["x_if"] = side_features(c["U_global"], c["I"], c["P"], c["Q"])

@@ -172,7 +172,7 @@ static int dev_alloc(T** out, size_t n)
 }
 
 static int upload_weights(rfm_session* s, const float* w_i, const float* w_if, const float* v_u, const float* v_i,
-                          const float* v_uf, const float* v_if, const float* x_uf, const float* x_if, bool features_too)
+                          const float* v_uf, const float* v_if, const float* x_uf, const float* x_if)
 {
     const Tables& T = s->T;
     float *st_vu = nullptr, *st_vi = nullptr, *st_wi = nullptr, *st_xu = nullptr, *st_xi = nullptr, *st_g = nullptr;
@@ -185,7 +185,6 @@ static int upload_weights(rfm_session* s, const float* w_i, const float* w_if, c
     CU(cudaMemcpyAsync(st_wi, w_i, (size_t)T.I * 4, cudaMemcpyHostToDevice, s->st));
     if (T.Pp) { if ((rc = dev_alloc(&st_xu, (size_t)T.U * T.P))) return rc; CU(cudaMemcpyAsync(st_xu, x_uf, (size_t)T.U * T.P * 4, cudaMemcpyHostToDevice, s->st)); }
     if (T.Qp) { if ((rc = dev_alloc(&st_xi, (size_t)T.I * T.Q))) return rc; CU(cudaMemcpyAsync(st_xi, x_if, (size_t)T.I * T.Q * 4, cudaMemcpyHostToDevice, s->st)); }
-    (void)features_too;
     CU(launch_pack_users(T, st_vu, st_xu, s->st));
     CU(launch_pack_items(T, st_vi, st_wi, st_xi, s->st));
     s->launches += 2;
@@ -280,7 +279,7 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
     TRY(dev_alloc(&T.UT, (size_t)T.U * T.ldu));
     TRY(dev_alloc(&T.IT, (size_t)T.I * T.ldi));
     TRY(dev_alloc(&T.GP, s->gp_floats));
-    TRY(upload_weights(s, p->w_i, p->w_if, p->v_u, p->v_i, p->v_uf, p->v_if, p->x_uf, p->x_if, true));
+    TRY(upload_weights(s, p->w_i, p->w_if, p->v_u, p->v_i, p->v_uf, p->v_if, p->x_uf, p->x_if));
 
     s->N = p->n_interactions;
     if (s->N > 0) {
@@ -371,7 +370,7 @@ extern "C" int rfm_session_set_weights(rfm_session* s, const float* w_i, const f
     if (s->T.Pp || s->T.Qp) {
         if (!s->p.x_uf || !s->p.x_if) return fail(RFM_ERR_ARG, "set_weights with features needs the original x_uf/x_if pointers to be alive");
     }
-    int rc = upload_weights(s, w_i, w_if, v_u, v_i, v_uf, v_if, s->p.x_uf, s->p.x_if, false);
+    int rc = upload_weights(s, w_i, w_if, v_u, v_i, v_uf, v_if, s->p.x_uf, s->p.x_if);
     if (rc) return rc;
     s->gemm_valid = false;
     if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->T.UT, (size_t)s->T.U * s->T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
@@ -560,9 +559,9 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     }
 
     for (int e = 0; e < epochs; ++e) {
-        const int epoch = s->epochs_done + e;               // LR schedule restarts per call, like the reference's per-_fit epoch counter
-        (void)epoch;
-        float eta = p.learning_rate;                        // _rankfm.pyx:220-223
+        // the LR schedule restarts with every call, like the reference's per-`_fit` epoch counter (_rankfm.pyx:218-223);
+        // the Philox/Feistel keys keep counting (epochs_done) so a warm start does not replay the same randomness
+        float eta = p.learning_rate;
         if (p.schedule == RFM_SCHEDULE_INVSCALING) eta = (float)(((double)p.learning_rate) / std::pow((double)(e + 1), (double)p.learning_exponent));
         etas[e] = eta;
         tp.eta = eta;

@@ -191,7 +191,6 @@ __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Tables& T = p.T;
-    constexpr bool TMA = true;                        // rows are staged by TMA bulk copies (the cp.async path lost: profiles/)
     constexpr int GPW = 32 / G;                       // tuples processed per step (one per lane group)
     constexpr int STEPS = 32 / GPW;                   // steps per batch of 32 tuples
     const int lane = threadIdx.x & 31, sub = lane % G, gw = lane / G;
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP
         __syncwarp();
     }
     if (lane == 0) {
-        for (int d = 0; d < D; ++d) mbar_init(bars + 8u * d, TMA ? 1u : 32u);
+        for (int d = 0; d < D; ++d) mbar_init(bars + 8u * d, 1u);      // one arrival: the lane that posts expect_tx
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
