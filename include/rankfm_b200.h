@@ -97,6 +97,11 @@ const char *rfm_last_error(void);
 int rfm_device_count(void);                                      /* number of CUDA devices, 0 if none */
 int rfm_nccl_unique_id(uint8_t *out128);                         /* rank 0 calls, caller broadcasts */
 
+/* page-lock / unlock a caller-owned host buffer (cudaHostRegister) so that the one-shot calls below copy it at full PCIe
+ * speed; optional -- every entry point also accepts pageable memory */
+int rfm_host_register(void *ptr, uint64_t bytes);
+int rfm_host_unregister(void *ptr);
+
 /* host-side evaluation of the kernels' RNG definitions (csrc/rfm_rng.cuh), so CPU tests can hold them to the
  * contract shared with the oracle: Philox4x32-10 block and the per-epoch Feistel permutation of [0,n) */
 int rfm_debug_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4);

@@ -18,7 +18,7 @@ SAMPLER_PHILOX, SAMPLER_MT = 0, 1
 SCHED_PARALLEL, SCHED_SERIAL = 0, 1
 
 EXPORTS = [
-    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_debug_philox", "rfm_debug_feistel",
+    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_host_register", "rfm_host_unregister", "rfm_debug_philox", "rfm_debug_feistel",
     "rfm_fit", "rfm_predict", "rfm_recommend", "rfm_similar",
     "rfm_session_create", "rfm_session_train", "rfm_session_set_weights", "rfm_session_download",
     "rfm_session_snapshot", "rfm_session_restore", "rfm_session_timer_start", "rfm_session_timer_stop",
@@ -66,6 +66,8 @@ def lib():
     L.rfm_device_count.restype = C.c_int
     pp, vp, i32, i64 = C.POINTER(Problem), C.c_void_p, C.c_int32, C.c_int64
     L.rfm_nccl_unique_id.argtypes = [vp]
+    L.rfm_host_register.argtypes = [vp, C.c_uint64]
+    L.rfm_host_unregister.argtypes = [vp]
     L.rfm_debug_philox.argtypes = [C.c_uint32] * 6 + [vp]
     L.rfm_debug_feistel.argtypes = [i64, C.c_uint64, i32, i64, i64, vp]
     L.rfm_fit.argtypes = [pp, i32, vp, vp]

@@ -62,6 +62,19 @@ def nccl_unique_id():
     return out.tobytes()
 
 
+def pin(*arrays):
+    """page-lock NumPy buffers in place (cudaHostRegister) so `_fit/_predict/_recommend` upload them at PCIe speed"""
+    for a in arrays:
+        if a is not None and a.nbytes:
+            check(_lib.lib().rfm_host_register(ptr(a), a.nbytes))
+
+
+def unpin(*arrays):
+    for a in arrays:
+        if a is not None and a.nbytes:
+            _lib.lib().rfm_host_unregister(ptr(a))
+
+
 def device_count():
     return _lib.lib().rfm_device_count()
 

@@ -102,6 +102,24 @@ extern "C" int rfm_nccl_unique_id(uint8_t* out128)
     return RFM_OK;
 }
 
+extern "C" int rfm_host_register(void* ptr, uint64_t bytes)
+{
+    if (!ptr || bytes == 0) return fail(RFM_ERR_ARG, "NULL buffer");
+    if (rfm_device_count() == 0) return fail(RFM_ERR_NO_DEVICE, "no CUDA device");
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RFM_OK; }
+    if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
+    return RFM_OK;
+}
+
+extern "C" int rfm_host_unregister(void* ptr)
+{
+    if (!ptr) return fail(RFM_ERR_ARG, "NULL buffer");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(RFM_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+    return RFM_OK;
+}
+
 extern "C" int rfm_debug_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4)
 {
     if (!out4) return fail(RFM_ERR_ARG, "out4 is NULL");
@@ -147,7 +165,7 @@ struct rfm_session {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int32_t* d_trace = nullptr;
     // tensor-core recommend: bf16 item operand + bias, rebuilt lazily whenever the weights change
-    void* d_gemm_B = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
+    void* d_gemm_B = nullptr; float* d_gemm_bias = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
     void* scratch[12] = {nullptr}; size_t scratch_bytes[12] = {0};   // grow-only device scratch of the recommend paths
     std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
     float* d_flush = nullptr; size_t flush_bytes = 0;
@@ -212,7 +230,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
     cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
-    cudaFree(s->d_gemm_B);
+    cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
     for (void* q : s->scratch) cudaFree(q);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
@@ -760,12 +778,14 @@ static int ensure_gemm_items(rfm_session* s)
     const int Kp = gemm_kp(T), BN = gemm_block_n(T);
     const int I_pad = (T.I + BN - 1) / BN * BN;
     if (!s->d_gemm_B || s->gemm_I_pad != I_pad) {
-        cudaFree(s->d_gemm_B);
-        s->d_gemm_B = nullptr;
+        cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
+        s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr;
         CU(cudaMalloc(&s->d_gemm_B, (size_t)I_pad * Kp * 2));
+        int rc = dev_alloc(&s->d_gemm_bias, (size_t)I_pad);
+        if (rc) return rc;
         s->gemm_I_pad = I_pad;
     }
-    CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->st));
+    CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->d_gemm_bias, s->st));
     s->launches += 1;
     s->gemm_valid = true;
     return RFM_OK;
@@ -813,10 +833,10 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), (size_t)M_pad * 4, cudaMemcpyHostToDevice, s->st));
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
         if (gemm_ms) CU(cudaEventRecord(a, s->st));
-        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, nb, M_pad, I_pad, n_splits, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
+        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         CU(launch_row_threshold(d_rowmax, M_pad, n_sub, d_ntgt, d_tau, s->st));
-        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_tau, kCandCap, nullptr, nullptr, s->st);
+        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_tau, kCandCap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         if (gemm_ms) CU(cudaEventRecord(b, s->st));
         e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, 2 * n_splits, kCandCap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, s->st);
@@ -981,7 +1001,7 @@ extern "C" int rfm_session_debug_gemm(rfm_session* s, const float* users, int64_
     if ((rc = dev_alloc(&d_S, (size_t)M_pad * I_pad))) return rc;
     CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     CU(launch_pack_gemm_users(T, d_users, (int)n_users, M_pad, Kp, d_A, s->st));
-    cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
+    cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
     if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e));
     CU(cudaMemcpy2DAsync(scores_out, (size_t)T.I * 4, d_S, (size_t)I_pad * 4, (size_t)T.I * 4, (size_t)n_users, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));

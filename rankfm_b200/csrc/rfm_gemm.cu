@@ -4,7 +4,7 @@
 // (:444).  Mathematically that is S = A . B^T + bias with
 //     A[u]  = [ v_u + x_uf.v_uf  |  v_u ]            (second half only with item features)
 //     B[i]  = [ v_i              |  x_if[i].v_if ]
-//     bias  = w_i + x_if[i].w_if
+//     bias  = w_i + x_if[i].w_if                     (fp32, added in the epilogue from a shared-memory tile)
 // (derived from compute_ui_utility :48-89; there is no user-feature x item-feature cross term), i.e. a dense GEMM whose
 // output (U x I) can never be materialised at cfg5 scale (1M x 1M).  So:
 //
@@ -35,25 +35,14 @@ namespace rfm {
 // ---------------------------------------------------------------------------------------------------------------
 // operand packing: bf16 A (requested users) / B (all items), fp32 bias
 // ---------------------------------------------------------------------------------------------------------------
-// K layout of both operands: [ factor block(s) : Kraw-2 columns | bias_hi | bias_lo | zero pad to a multiple of 64 ].
-// The item bias rides inside the GEMM as two bf16 columns (hi + lo, relative error 2^-17) against two columns of ones
-// in A, so the epilogue never touches a bias vector.
-__global__ void pack_gemm_items_kernel(const Tables T, int Kraw, int Kp, int I_pad, __nv_bfloat16* __restrict__ B)
+// bf16 operands [rows, Kp] (Kp = factor columns padded to a multiple of 64) and the fp32 item bias
+__global__ void pack_gemm_items_kernel(const Tables T, int Kp, int I_pad, __nv_bfloat16* __restrict__ B, float* __restrict__ bias)
 {
     const long long n = (long long)I_pad * Kp;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e / Kp), c = (int)(e % Kp);
         float v = 0.f;
-        if (c >= Kraw - 2 && c < Kraw) {
-            float b = -1e30f;                                                // padded items never pass any threshold
-            if (i < T.I) {
-                const float* row = T.IT + (size_t)i * T.ldi;
-                b = row[T.Fp];
-                if (T.x_if_any) for (int q = 0; q < T.Q; ++q) b += row[T.Fp + 4 + q] * T.GP[q];
-            }
-            const float hi = __bfloat162float(__float2bfloat16(b));
-            v = c == Kraw - 2 ? hi : (i < T.I ? b - hi : 0.f);
-        } else if (i < T.I) {
+        if (i < T.I) {
             const float* row = T.IT + (size_t)i * T.ldi;
             if (c < T.F) v = row[c];
             else if (T.x_if_any && c >= T.Fp && c - T.Fp < T.F) {             // second half: x_if[i] . v_if[:, f]
@@ -63,9 +52,18 @@ __global__ void pack_gemm_items_kernel(const Tables T, int Kraw, int Kp, int I_p
         }
         B[e] = __float2bfloat16(v);
     }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I_pad; i += gridDim.x * blockDim.x) {
+        float b = -1e30f;                                                    // padded items never pass any threshold
+        if (i < T.I) {
+            const float* row = T.IT + (size_t)i * T.ldi;
+            b = row[T.Fp];
+            if (T.x_if_any) for (int q = 0; q < T.Q; ++q) b += row[T.Fp + 4 + q] * T.GP[q];
+        }
+        bias[i] = b;
+    }
 }
 
-__global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, int M_pad, int Kraw, int Kp, __nv_bfloat16* __restrict__ A)
+__global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, int M_pad, int Kp, __nv_bfloat16* __restrict__ A)
 {
     const long long n = (long long)M_pad * Kp;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -74,8 +72,7 @@ __global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict
         const int u = r < n_users ? users[r] : -1;
         if (u >= 0) {
             const float* row = T.UT + (size_t)u * T.ldu;
-            if (c >= Kraw - 2 && c < Kraw) v = 1.0f;
-            else if (c < T.F) {
+            if (c < T.F) {
                 v = row[c];
                 if (T.x_uf_any) for (int p = 0; p < T.P; ++p) v += row[T.Fp + p] * T.GP[T.gp_vuf + (size_t)p * T.Fp + c];
             } else if (T.x_if_any && c >= T.Fp && c - T.Fp < T.F) v = row[c - T.Fp];
@@ -101,6 +98,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -141,6 +142,7 @@ __device__ __forceinline__ uint32_t ord_key(float s) { const uint32_t b = __floa
 // the GEMM + running-threshold filter
 // ---------------------------------------------------------------------------------------------------------------
 struct GemmParams {
+    const float* bias;           // [I_pad] fp32 item bias (w_i + x_if.w_if); -1e30 for padded items
     int kblocks;                 // Kp / 64
     int n_tiles;                 // I_pad / BLOCK_N
     int n_splits;                // item-range splits (grid.y)
@@ -158,7 +160,7 @@ struct GemmParams {
     long long ldS;
 };
 
-constexpr int kGemmThreads = 384;          // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue
+constexpr int kGemmThreads = 384;          // warps: 0 TMA producer (A, B), 1 MMA issuer, 2 TMEM allocator, 3 bias producer, 4..11 epilogue
 constexpr int MODE_DUMP = 0, MODE_ROWMAX = 1, MODE_FILTER = 2;
 
 template <int BLOCK_N, int MODE>
@@ -172,10 +174,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int kb_n = p.kblocks, nstage = p.nstage;
     unsigned char* sA = smem;
     unsigned char* sB = sA + (size_t)kb_n * A_KB_BYTES;
-    unsigned char* sBar = sB + (size_t)nstage * kb_n * B_KB_BYTES;
+    float* sBias = reinterpret_cast<float*>(sB + (size_t)nstage * kb_n * B_KB_BYTES);      // [2][BLOCK_N], one slot per accumulator stage
+    unsigned char* sBar = reinterpret_cast<unsigned char*>(sBias + 2 * BLOCK_N);
     const uint32_t bar_full = s32(sBar), bar_empty = bar_full + 8u * nstage, bar_a = bar_empty + 8u * nstage;
-    const uint32_t bar_tfull = bar_a + 8u, bar_tempty = bar_tfull + 16u;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 8 * (2 * nstage + 5));
+    const uint32_t bar_tfull = bar_a + 8u, bar_tempty = bar_tfull + 16u, bar_bias = bar_tempty + 16u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 8 * (2 * nstage + 7));
 
     // this CTA: user tile blockIdx.x, item tiles [t0, t1)
     const int m0 = blockIdx.x * 128;
@@ -186,7 +189,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < nstage; ++s) { bar_init(bar_full + 8u * s, 1); bar_init(bar_empty + 8u * s, 1); }
         bar_init(bar_a, 1);
-        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8u * a, 1); bar_init(bar_tempty + 8u * a, 8); }
+        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8u * a, 1); bar_init(bar_tempty + 8u * a, 8); bar_init(bar_bias + 8u * a, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -237,6 +240,17 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_commit(bar_tfull + 8u * as);                     // accumulator ready for the epilogue
             }
         }
+    } else if (warp == 3) {
+        // ===== bias producer: the tile's fp32 biases ride next to the accumulator stage they belong to =====
+        if (lane == 0) {
+            for (int it = 0; it < my_tiles; ++it) {
+                const int as = it & 1;
+                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                bar_wait(bar_tempty + 8u * as, aph ^ 1u);           // the epilogue is done with this slot
+                bar_expect_tx(bar_bias + 8u * as, BLOCK_N * 4u);
+                bulk_load_1d(s32(sBias + as * BLOCK_N), p.bias + (size_t)(t0 + it) * BLOCK_N, BLOCK_N * 4u, bar_bias + 8u * as);
+            }
+        }
     } else if (warp >= 4) {
         // ===== epilogue: thread <-> user row (TMEM lane); two warps per lane quarter split the tile's columns =====
         const int wq = warp & 3;                                    // TMEM lane quarter this warp may access
@@ -255,15 +269,22 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int it = 0; it < my_tiles; ++it) {
             const int as = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            bar_wait(bar_bias + 8u * as, aph);
             bar_wait(bar_tfull + 8u * as, aph);
             tc_fence_after();
             const int n0 = (t0 + it) * BLOCK_N + half * HALF_N;
+            const float4* bias4 = reinterpret_cast<const float4*>(sBias + as * BLOCK_N + half * HALF_N);
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BLOCK_N + half * HALF_N);
             float blockmax = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < HALF_N / 32; ++c) {
                 float v[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 b = bias4[c * 8 + q];                 // broadcast LDS.128: every row adds the same item biases
+                    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                }
                 if (MODE == MODE_DUMP) {
                     float* out = p.S + (size_t)row * p.ldS + n0 + c * 32;
 #pragma unroll
@@ -402,19 +423,19 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int Kp,
 }
 
 bool gemm_encode_available() { return encode_tiled_fn() != nullptr; }
-int gemm_kraw(const Tables& T) { return (T.x_if_any ? 2 * T.Fp : T.Fp) + 2; }     // factor columns + bias hi/lo
+int gemm_kraw(const Tables& T) { return T.x_if_any ? 2 * T.Fp : T.Fp; }
 int gemm_kp(const Tables& T) { return (gemm_kraw(T) + 63) / 64 * 64; }
 int gemm_block_n(const Tables& T) { return gemm_kp(T) <= 128 ? 256 : 128; }
 bool gemm_supported(const Tables& T) { return gemm_kp(T) <= 256; }
 
-cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, cudaStream_t st)
+cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st)
 {
-    pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, gemm_kraw(T), Kp, I_pad, reinterpret_cast<__nv_bfloat16*>(B));
+    pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, Kp, I_pad, reinterpret_cast<__nv_bfloat16*>(B), bias);
     return cudaGetLastError();
 }
 cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st)
 {
-    pack_gemm_users_kernel<<<148 * 4, 256, 0, st>>>(T, users, n_users, M_pad, gemm_kraw(T), Kp, reinterpret_cast<__nv_bfloat16*>(A));
+    pack_gemm_users_kernel<<<148 * 4, 256, 0, st>>>(T, users, n_users, M_pad, Kp, reinterpret_cast<__nv_bfloat16*>(A));
     return cudaGetLastError();
 }
 
@@ -468,20 +489,20 @@ static cudaError_t launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, c
 
 // mode 0: dump dense scores into S [M_pad, I_pad]; 1: block maxima into rowmax [M_pad, I_pad/64];
 // 2: candidates with score >= tau[row] into cand/cand_cnt
-cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, int n_users, int M_pad, int I_pad, int n_splits,
+cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
                                 float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st)
 {
     const int Kp = gemm_kp(T), BN = gemm_block_n(T);
     alignas(64) CUtensorMap tmA, tmB;
     if (!make_map(&tmA, A, M_pad, Kp, 128) || !make_map(&tmB, B, I_pad, Kp, BN)) return cudaErrorNotSupported;
     GemmParams p{};
-    p.kblocks = Kp / 64; p.n_tiles = I_pad / BN; p.n_splits = n_splits; p.n_users = n_users;
+    p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = I_pad / BN; p.n_splits = n_splits; p.n_users = n_users;
     p.cand = cand; p.cand_cnt = cand_cnt; p.tau = tau; p.cap = cap; p.rowmax = rowmax; p.S = S; p.ldS = I_pad;
     const size_t a_bytes = (size_t)p.kblocks * 128 * 128, stage_bytes = (size_t)p.kblocks * BN * 128;
-    int nstage = (int)((200 * 1024 - a_bytes) / stage_bytes);
+    int nstage = (int)((196 * 1024 - a_bytes) / stage_bytes);
     nstage = nstage > 4 ? 4 : (nstage < 2 ? 2 : nstage);
     p.nstage = nstage;
-    const size_t smem = a_bytes + nstage * stage_bytes + 8 * (2 * nstage + 5) + 16 + 1024;
+    const size_t smem = a_bytes + nstage * stage_bytes + 2 * BN * 4 + 8 * (2 * nstage + 7) + 16 + 1024;
     const dim3 grid(M_pad / 128, n_splits);
     if (BN == 256) {
         if (mode == MODE_DUMP) return launch_mode<256, MODE_DUMP>(tmA, tmB, p, grid, smem, st);

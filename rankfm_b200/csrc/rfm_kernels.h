@@ -62,9 +62,9 @@ cudaError_t launch_topn_select(float* S, int I, const int32_t* users, int n_user
 int gemm_kp(const Tables& T);
 int gemm_block_n(const Tables& T);
 bool gemm_supported(const Tables& T);
-cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, cudaStream_t st);
+cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st);
 cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st);
-cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, int n_users, int M_pad, int I_pad, int n_splits,
+cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
                                 float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st);
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st);
 cudaError_t launch_rescore(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
