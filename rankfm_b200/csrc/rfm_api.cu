@@ -597,9 +597,9 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
         const bool feat_parallel = !tp.serial && (s->T.x_uf_any || s->T.x_if_any);
         double chains = 1.0, steps_per_chain = (double)s->N;
         if (feat_parallel) {
-            // warp-private feature-parameter chains: one per warp that owns >= 1 batch
+            // private feature-parameter chains: one per lane group (or warp) that owns >= 1 batch
             const double n_batches = std::ceil((double)s->N / 32.0);
-            chains = std::min((double)grid * (kTrainThreads / 32), n_batches);
+            chains = std::min((double)grid * (kTrainThreads / 32), n_batches) * sgd_pipe_chains_per_warp(s->T);
             steps_per_chain = (double)s->N / chains;
             tp.gp_acc = s->d_gp_acc;
             tp.gp_gain = fold_gain((double)tp.reg_b * eta, steps_per_chain, chains);

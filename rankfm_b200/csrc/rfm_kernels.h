@@ -37,6 +37,7 @@ struct TrainParams {
     float* gp_acc;           // [gp_floats] accumulator of the warps' feature-parameter deltas (production, FEAT)
     float gp_gain;           // weight of each warp's delta when the chains are folded (see rfm_session_train)
     int32_t gp_floats;
+    int32_t gp_private;      // 1: one feature-parameter chain per lane group (plain RMW), 0: one per warp (atomics)
     uint32_t k0, k1, epoch_key;
     MtState* mt;             // non-null -> MT19937 sampler (serial only)
     EpochAcc* acc;
@@ -48,6 +49,7 @@ cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st);
 cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bitmap, int words, cudaStream_t st);
 cudaError_t launch_gp_apply(float* gp, float* acc, int n, cudaStream_t st);
 size_t sgd_pipe_smem_bytes(const Tables& T);
+int sgd_pipe_chains_per_warp(const Tables& T);
 cudaError_t launch_weight_stats(const Tables& T, double* out12, int grid, cudaStream_t st);
 
 // scoring (rfm_score.cu)

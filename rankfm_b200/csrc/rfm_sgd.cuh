@@ -147,13 +147,13 @@ struct SmemSink {
 // One gradient step on (u, i, j): reads nothing but GP (feature parameters) from memory, everything else arrives in
 // registers; writes go out as vector reductions.  Update formula and operand association follow the generated C of the
 // reference:  w += eta * (((sw*mult) * (d_outer*d)) - (2reg * w)).
-// add a delta quad to a feature parameter: HBM -> vector reduction; warp-private shared copy -> plain or atomic add
-// (atomic only when several lane groups of the warp work on different positives at once)
+// add a delta quad to a feature parameter: HBM -> vector reduction; shared-memory chain -> plain store when the chain
+// belongs to this lane group alone, shared-memory atomics only when several groups of a warp share one copy
 template <int G, bool GPS>
-__device__ __forceinline__ void gp_add4(float* q, const float4& w, const float4& d)
+__device__ __forceinline__ void gp_add4(float* q, const float4& w, const float4& d, bool exclusive)
 {
     if (!GPS) { red_add4(q, d); return; }
-    if (G == 32) { *reinterpret_cast<float4*>(q) = make_float4(w.x + d.x, w.y + d.y, w.z + d.z, w.w + d.w); return; }
+    if (G == 32 || exclusive) { *reinterpret_cast<float4*>(q) = make_float4(w.x + d.x, w.y + d.y, w.z + d.z, w.w + d.w); return; }
     atomicAdd(q + 0, d.x); atomicAdd(q + 1, d.y); atomicAdd(q + 2, d.z); atomicAdd(q + 3, d.w);
 }
 
@@ -246,7 +246,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
                 const float4 w = gp_ld4<GPS>(gp + 4 * sub);
                 float4 d;
                 d.x = RFM_G(dx.x, w.x); d.y = RFM_G(dx.y, w.y); d.z = RFM_G(dx.z, w.z); d.w = RFM_G(dx.w, w.w);
-                gp_add4<G, GPS>(gp + 4 * sub, w, d);
+                gp_add4<G, GPS>(gp + 4 * sub, w, d, p.gp_private != 0);
             }
         }
         if (T.x_uf_any) {                                                  // v_uf[p] for x_uf[u,p] != 0 (:313-318)
@@ -262,7 +262,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
                         float4 d;
                         d.x = RFM_G(xp * dij_new[k].x, w.x); d.y = RFM_G(xp * dij_new[k].y, w.y);
                         d.z = RFM_G(xp * dij_new[k].z, w.z); d.w = RFM_G(xp * dij_new[k].w, w.w);
-                        gp_add4<G, GPS>(wp, w, d);
+                        gp_add4<G, GPS>(wp, w, d, p.gp_private != 0);
                     }
                 }
             }
@@ -280,7 +280,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
                         float4 d;
                         d.x = RFM_G(dxq * vu_new[k].x, w.x); d.y = RFM_G(dxq * vu_new[k].y, w.y);
                         d.z = RFM_G(dxq * vu_new[k].z, w.z); d.w = RFM_G(dxq * vu_new[k].w, w.w);
-                        gp_add4<G, GPS>(wp, w, d);
+                        gp_add4<G, GPS>(wp, w, d, p.gp_private != 0);
                     }
                 }
             }

@@ -198,14 +198,17 @@ __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP
     const int tuple_floats = T.ldu + 2 * T.ldi;
     const uint32_t tuple_bytes = (uint32_t)tuple_floats * 4u;
     const int stage_floats = GPW * tuple_floats;
-    // per warp: [mbarriers | D stages | private copy of the feature parameters GP (FEAT only)]
+    // per warp: [mbarriers | D stages | chain copies of the feature parameters GP (FEAT only)]: one copy per lane group
+    // (plain read-modify-write, p.gp_private) when that fits shared memory, else one per warp (shared-memory atomics)
     const int gp_floats = FEAT ? p.gp_floats : 0;
-    unsigned char* wbase = smem_raw + (size_t)(threadIdx.x >> 5) * (kPipeBarBytes + ((size_t)D * stage_floats + gp_floats) * 4);
+    const int gp_copies = FEAT ? (p.gp_private ? GPW : 1) : 0;
+    unsigned char* wbase = smem_raw + (size_t)(threadIdx.x >> 5) * (kPipeBarBytes + ((size_t)D * stage_floats + (size_t)gp_copies * gp_floats) * 4);
     const uint32_t bars = smem_u32(wbase);
     float* stages = reinterpret_cast<float*>(wbase + kPipeBarBytes);
-    float* gp = FEAT ? stages + (size_t)D * stage_floats : nullptr;
-    if (FEAT) {          // every warp starts the epoch from the same parameters and evolves its copy over its own positives
-        for (int e = lane; e < gp_floats; e += 32) gp[e] = __ldcg(T.GP + e);
+    float* gp_all = FEAT ? stages + (size_t)D * stage_floats : nullptr;
+    float* gp = FEAT ? gp_all + (size_t)(p.gp_private ? gw : 0) * gp_floats : nullptr;
+    if (FEAT) {          // every chain starts the epoch from the same parameters and evolves over its own positives
+        for (int e = lane; e < gp_copies * gp_floats; e += 32) gp_all[e] = __ldcg(T.GP + (e % gp_floats));
         __syncwarp();
     }
     if (lane == 0) {
@@ -348,9 +351,9 @@ __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP
     if (FEAT && warp_global < n_batches) {
         // fold this warp's chain into the epoch result: GP_new = GP_start + gain * sum over active warps of (copy - GP_start)
         __syncwarp();
-        for (int e = lane; e < gp_floats; e += 32) {
-            const float d = gp[e] - __ldcg(T.GP + e);
-            if (d != 0.f) red_add1(p.gp_acc + e, p.gp_gain * d);
+        for (int e = lane; e < gp_copies * gp_floats; e += 32) {
+            const float d = gp_all[e] - __ldcg(T.GP + (e % gp_floats));
+            if (d != 0.f) red_add1(p.gp_acc + (e % gp_floats), p.gp_gain * d);
         }
     }
     flush_acc<G>(acc, p.acc);
@@ -378,10 +381,25 @@ static int pipe_depth(const Tables& T, int G)
     return d < 2 ? 2 : (d > 8 ? 8 : d);
 }
 static size_t gp_floats_of(const Tables& T) { return (T.x_uf_any || T.x_if_any) ? (size_t)T.gp_vif + (size_t)T.Q * T.Fp : 0; }
-static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
+static size_t pipe_smem_bytes_copies(const Tables& T, int G, int depth, int copies)
 {
     const size_t stage_bytes = (size_t)(32 / G) * (T.ldu + 2 * T.ldi) * 4;
-    return (size_t)(kTrainThreads / 32) * (kPipeBarBytes + (size_t)depth * stage_bytes + gp_floats_of(T) * 4);
+    return (size_t)(kTrainThreads / 32) * (kPipeBarBytes + (size_t)depth * stage_bytes + (size_t)copies * gp_floats_of(T) * 4);
+}
+// group-private feature-parameter chains when two blocks of them still fit an SM, else one (atomic) chain per warp
+static int gp_private_of(const Tables& T, int G, int depth)
+{
+    return (32 / G) > 1 && pipe_smem_bytes_copies(T, G, depth, 32 / G) <= 100 * 1024 ? 1 : 0;
+}
+static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
+{
+    return pipe_smem_bytes_copies(T, G, depth, gp_private_of(T, G, depth) ? 32 / G : 1);
+}
+int sgd_pipe_chains_per_warp(const Tables& T)
+{
+    int qpl = 1;
+    const int G = train_group_size(T, &qpl);
+    return gp_private_of(T, G, pipe_depth(T, G)) ? 32 / G : 1;
 }
 size_t sgd_pipe_smem_bytes(const Tables& T)
 {
@@ -440,6 +458,7 @@ static cudaError_t launch_gq(const TrainParams& p0, int grid, cudaStream_t st)
     }
     p.depth = pipe_depth(p.T, G);
     p.gp_floats = (int)gp_floats_of(p.T);
+    p.gp_private = gp_private_of(p.T, G, p.depth);
     const size_t smem = pipe_smem_bytes(p.T, G, p.depth);
     return launch_pipe<G, QPL>(p, feat, grid, smem, st);
 }
