@@ -15,6 +15,8 @@ CONFIGS = {
                  label="1M users x 200k items, 50M Zipf interactions, factors=64, warp, 8+8 side features"),
     "cfg3m": dict(U=250_000, I=50_000, N=8_000_000, F=64, loss="warp", max_samples=10, epochs=3, P=8, Q=8,
                   label="1/6 slice of cfg3: 250k users x 50k items, 8M interactions, factors=64, warp max_samples=10, 8+8 dense side features"),
+    "cfg3n": dict(U=1_000_000, I=200_000, N=16_000_000, F=64, loss="warp", max_samples=10, epochs=3, P=0, Q=0,
+                  label="cfg3 shape without side features: 1M users x 200k items, 16M interactions, factors=64, warp max_samples=10 (tables 308 MB > L2)"),
     "cfg4m": dict(U=1_250_000, I=1_000_000, N=16_000_000, F=128, loss="bpr", max_samples=1, epochs=3, P=0, Q=0,
                   label="DRAM-resident slice of cfg4: 1.25M users x 1M items, 16M interactions, factors=128, bpr (tables 1.2 GB >> L2)"),
     "cfg4s": dict(U=1_250_000, I=1_000_000, N=62_500_000, F=128, loss="bpr", max_samples=1, epochs=2, P=0, Q=0,

@@ -429,3 +429,47 @@ def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, m
         for row, u in zip(fast, users):
             if not np.isnan(u):
                 assert not set(row.astype(int).tolist()) & set(ui[int(u)].tolist())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# model quality at the benchmark workload: the Hogwild-trained model ranks held-out interactions like the reference's
+# ---------------------------------------------------------------------------------------------------------------
+def _topk_metrics(w, train_csr, test_pairs, U, k=10):
+    """hit-rate@k and precision@k over users with held-out items, training items filtered (evaluation.py semantics)"""
+    indptr, indices = train_csr
+    scores = w['v_u'] @ w['v_i'].T + w['w_i'][None, :]
+    for u in range(U):
+        scores[u, indices[indptr[u]:indptr[u + 1]]] = -np.inf
+    top = np.argpartition(-scores, k, axis=1)[:, :k]
+    test_sets = {}
+    for u, i in test_pairs:
+        test_sets.setdefault(int(u), set()).add(int(i))
+    hits = np.array([len(test_sets[u] & set(top[u].tolist())) for u in sorted(test_sets)])
+    return float((hits > 0).mean()), float((hits / k).mean())
+
+
+def test_cfg2_model_quality_matches_sequential_reference(gpu_lib):
+    """BASELINE.json configs[1] (MovieLens-1M shape, factors=20, warp, max_samples=20, 20 epochs, invscaling): train on
+    90 %, rank the held-out 10 %.  Production (Hogwild/Philox) vs the sequential oracle (MT19937): same quality."""
+    X = zipf_interactions(6040, 3706, 1_600_000, seed=42)[:1_000_000]
+    U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
+    rng = np.random.default_rng(5)
+    test_mask = rng.random(len(X)) < 0.1
+    Xtr, Xte = np.ascontiguousarray(X[~test_mask]), X[test_mask]
+    indptr, indices = csr_of(Xtr, U)
+    ui = CSRItems(indptr, indices)
+    sw = np.ones(len(Xtr), np.float32)
+    x_uf, x_if = features(U, I, 0, 0)
+    hyper = (0.01, 0.1, 0.1, 'invscaling', 0.25, 20)
+    epochs = 20
+    wg = init_weights(U, I, 20, seed=0)
+    _rankfm.fit_ex(Xtr, sw, ui, x_uf, x_if, *[wg[k] for k in WEIGHTS], *hyper, epochs, mode="production", seed=11)
+    wo = init_weights(U, I, 20, seed=0)
+    perms = np.stack([np.random.RandomState(e).permutation(len(Xtr)) for e in range(epochs)]).astype(np.int32)
+    oracle.fit_ex(Xtr, sw, ui, x_uf, x_if, *[wo[k] for k in WEIGHTS], *hyper, epochs, perms=perms, sampler="mt")
+    hr_g, pr_g = _topk_metrics(wg, (indptr, indices), Xte, U)
+    hr_o, pr_o = _topk_metrics(wo, (indptr, indices), Xte, U)
+    # the two models are equally good rankers (absolute 0.02 on hit rate, relative 5 % on precision)
+    assert abs(hr_g - hr_o) < 0.02, (hr_g, hr_o)
+    assert abs(pr_g - pr_o) < 0.05 * pr_o + 0.002, (pr_g, pr_o)
+    assert hr_g > 0.3
