@@ -139,6 +139,8 @@ extern "C" int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_
 // ---------------------------------------------------------------------------------------------------------------
 // session
 // ---------------------------------------------------------------------------------------------------------------
+__global__ void item_histogram_kernel(const int2* __restrict__ inter, long long n, int32_t* __restrict__ count);
+
 struct rfm_session {
     rfm_problem p{};            // host pointers are NOT retained past create (copied fields only)
     Tables T{};
@@ -160,6 +162,7 @@ struct rfm_session {
     void* comm = nullptr;
     float *d_it_snap = nullptr, *d_gp_snap = nullptr, *d_ut_init = nullptr;
     float* d_gp_acc = nullptr;
+    int32_t* d_item_touch = nullptr;    // multi-GPU: how often each item occurs as a positive in this rank's shard
     // scratch
     float *d_snap_ut = nullptr, *d_snap_it = nullptr, *d_snap_gp = nullptr; int snap_epochs = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -228,7 +231,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->T.UT); cudaFree(s->T.IT); cudaFree(s->T.GP);
     cudaFree(s->d_inter); cudaFree(s->d_sw); cudaFree(s->d_indptr); cudaFree(s->d_indices);
     cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
-    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc);
+    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc); cudaFree(s->d_item_touch);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
     cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
     for (void* q : s->scratch) cudaFree(q);
@@ -370,6 +373,9 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
         TRY(dev_alloc(&s->d_it_snap, (size_t)T.I * T.ldi));
         TRY(dev_alloc(&s->d_gp_snap, s->gp_floats));
         TRY(dev_alloc(&s->d_ut_init, (size_t)T.U * T.ldu));
+        TRY(dev_alloc(&s->d_item_touch, (size_t)T.I));
+        CUB(cudaMemsetAsync(s->d_item_touch, 0, (size_t)T.I * 4, s->st));
+        if (s->N > 0) { item_histogram_kernel<<<s->n_sm * 4, 256, 0, s->st>>>(s->d_inter, s->N, s->d_item_touch); s->launches += 1; }
         CUB(cudaMemcpyAsync(s->d_ut_init, T.UT, (size_t)T.U * T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
         CUB(cudaStreamSynchronize(s->st));
     }
@@ -511,6 +517,46 @@ static int exchange_deltas(rfm_session* s, float* cur, float* snap, size_t n, fl
     return RFM_OK;
 }
 
+// Item table: every rank moved its replica of row i as if it were alone.  How the C replica deltas combine depends on how
+// far the row travelled towards its own equilibrium within the epoch: rows touched rarely barely moved (deltas add up,
+// gain 1), rows touched thousands of times have each forgotten their start (the replicas are C samples of the same
+// quasi-stationary value: average, gain 1/C).  Same fold rule as the feature-parameter chains (fold_gain), evaluated per
+// row from its touch count n_i = positives in this rank's shard + expected uniform negatives, with the per-touch
+// contraction rate eta*(2*alpha + curvature); the logistic curvature is ~0.15 for the bias and ~0.01 for a factor.
+__global__ void item_histogram_kernel(const int2* __restrict__ inter, long long n, int32_t* __restrict__ count)
+{
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) atomicAdd(count + inter[e].y, 1);
+}
+
+__global__ void item_delta_kernel(float* __restrict__ cur, const float* __restrict__ snap, int I, int ldi, int Fp, const int32_t* __restrict__ touch,
+                                  const EpochAcc* __restrict__ acc, float lam_factor, float lam_bias, float C)
+{
+    const float neg_per_item = (float)((double)acc->draws / (double)I);
+    const size_t n = (size_t)I * ldi;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / ldi), col = (int)(e % ldi);
+        const float touches = (float)touch[row] + neg_per_item;
+        const float x = (col == Fp ? lam_bias : lam_factor) * touches;       // -log of the row's own contraction over the epoch
+        float g = 1.0f;
+        if (x > 1e-4f) { const float d = __expf(-x); g = (1.0f - __expf(-x * C)) / (C * (1.0f - d)); }
+        cur[e] = g * (cur[e] - snap[e]);
+    }
+}
+
+static int exchange_item_deltas(rfm_session* s, const EpochAcc* acc, float eta)
+{
+    const Tables& T = s->T;
+    const int grid = s->n_sm * 4;
+    const size_t n = (size_t)T.I * T.ldi;
+    const float lam_factor = eta * (2.0f * s->p.alpha + 0.01f), lam_bias = eta * (2.0f * s->p.alpha + 0.15f);
+    item_delta_kernel<<<grid, 256, 0, s->st>>>(T.IT, s->d_it_snap, T.I, T.ldi, T.Fp, s->d_item_touch, acc, lam_factor, lam_bias, (float)s->p.world);
+    NC(g_nccl.AllReduce(T.IT, T.IT, n, kNcclFloat, kNcclSum, s->comm, s->st));
+    apply_kernel<<<grid, 256, 0, s->st>>>(T.IT, s->d_it_snap, n);
+    s->launches += 2;
+    CU(cudaGetLastError());
+    return RFM_OK;
+}
+
 // Folding C independent chains of a parameter with per-step decay (1-lambda), each run for n steps from the same start:
 // theta = start + gain * sum_c (theta_c - start).  gain = (1 - d^C) / (C (1 - d)), d = (1-lambda)^n, is exact for the
 // decay part: 1 (sum of deltas) when the chains barely move, 1/C (average) when each chain has forgotten its start.
@@ -612,7 +658,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
         s->launches += 1;
         CU(cudaEventRecord(s->ev[4 * e + 2], s->st));
         if (s->comm) {
-            int rc = exchange_deltas(s, s->T.IT, s->d_it_snap, (size_t)s->T.I * s->T.ldi);
+            int rc = exchange_item_deltas(s, s->d_acc + e, eta);
             if (rc) return rc;
             if (s->T.x_uf_any || s->T.x_if_any) {
                 // every rank ran its own feature-parameter chains: fold the ranks with the same rule

@@ -27,6 +27,21 @@ def problem():
     return X, U, I, CSRItems(indptr, indices), np.ones(len(X), np.float32)
 
 
+def fold_gain(x, C):
+    """gain of each replica's delta when C replicas of a parameter are folded; x = -log(contraction over the epoch).
+    Mirrors fold_gain / item_delta_kernel in rankfm_b200/csrc/rfm_api.cu."""
+    x = np.asarray(x, np.float64)
+    g = np.ones_like(x)
+    m = x > 1e-4
+    g[m] = (1.0 - np.exp(-x[m] * C)) / (C * (1.0 - np.exp(-x[m])))
+    return g.astype(np.float32)
+
+
+def item_gains(X_shard, I, draws, eta, alpha, C):
+    touch = np.bincount(X_shard[:, 1], minlength=I).astype(np.float64) + draws / I
+    return fold_gain(eta * (2 * alpha + 0.01) * touch, C), fold_gain(eta * (2 * alpha + 0.15) * touch, C)
+
+
 def allreduce_sum(a):
     t = torch.from_numpy(np.ascontiguousarray(a))
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -45,9 +60,11 @@ def gloo_oracle(rank, world):
     hyper = (0.01, 0.1, 0.1, 'constant', 0.25, 1)
     for e in range(epochs):
         snap = {k: w[k].copy() for k in ('w_i', 'v_i')}
-        oracle.fit_ex(Xr, swr, ui, x_uf, x_if, *[w[k] for k in WEIGHTS], *hyper, 1, perms=None, sampler="philox", seed=5, epoch_offset=e, max_rejects=64)
-        for k in ('w_i', 'v_i'):                       # replicated item side: sum of deltas
-            w[k][...] = snap[k] + allreduce_sum(w[k] - snap[k])
+        out = oracle.fit_ex(Xr, swr, ui, x_uf, x_if, *[w[k] for k in WEIGHTS], *hyper, 1, perms=None, sampler="philox", seed=5, epoch_offset=e, max_rejects=64)
+        g_f, g_b = item_gains(Xr, I, float(out['draws'][0]), 0.1, 0.01, world)
+        # replicated item side: gain-weighted sum of the replicas' deltas (rarely touched rows add up, hot rows average)
+        w['v_i'][...] = snap['v_i'] + allreduce_sum(g_f[:, None] * (w['v_i'] - snap['v_i']))
+        w['w_i'][...] = snap['w_i'] + allreduce_sum(g_b * (w['w_i'] - snap['w_i']))
     w['v_u'][...] = w0_vu + allreduce_sum(w['v_u'] - w0_vu)      # user rows: owned by exactly one rank
     # every rank must now hold the same model
     for k in ('w_i', 'v_i', 'v_u'):
@@ -64,9 +81,11 @@ def gloo_oracle(rank, world):
             acc = {k: np.zeros_like(ws[k]) for k in ('w_i', 'v_i', 'v_u')}
             for Xs, sws, _ in shards:
                 wr = {k: base[k].copy() for k in WEIGHTS}
-                oracle.fit_ex(Xs, sws, ui, x_uf, x_if, *[wr[k] for k in WEIGHTS], *hyper, 1, perms=None, sampler="philox", seed=5, epoch_offset=e, max_rejects=64)
-                for k in acc:
-                    acc[k] += wr[k] - base[k]
+                out = oracle.fit_ex(Xs, sws, ui, x_uf, x_if, *[wr[k] for k in WEIGHTS], *hyper, 1, perms=None, sampler="philox", seed=5, epoch_offset=e, max_rejects=64)
+                g_f, g_b = item_gains(Xs, I, float(out['draws'][0]), 0.1, 0.01, world)
+                acc['v_i'] += g_f[:, None] * (wr['v_i'] - base['v_i'])
+                acc['w_i'] += g_b * (wr['w_i'] - base['w_i'])
+                acc['v_u'] += wr['v_u'] - base['v_u']
             for k in acc:
                 ws[k][...] = base[k] + acc[k]
         for k in ('w_i', 'v_i', 'v_u'):
