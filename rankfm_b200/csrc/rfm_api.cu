@@ -333,9 +333,12 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
         if (p->order == RFM_ORDER_HOST) TRY(dev_alloc(&s->d_perm, (size_t)s->N));
         if (s->nnz >= ((int64_t)1 << 31) / 32) return bail(fail(RFM_ERR_UNSUPPORTED, "user_items larger than 2^26 entries per user are not supported"));
         {
-            // membership bitmap when U x I bits fit the budget (default 1 GiB; RANKFM_B200_BITMAP_MB=0 disables)
+            // membership bitmap when U x I bits fit the budget: default min(8 GiB, a quarter of the free HBM);
+            // RANKFM_B200_BITMAP_MB overrides, 0 disables (the kernels then search the CSR)
             const char* env = getenv("RANKFM_B200_BITMAP_MB");
-            const double budget_mb = env ? atof(env) : 1024.0;
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const double budget_mb = env ? atof(env) : std::min(8192.0, (double)free_b / (4.0 * 1024.0 * 1024.0));
             const int words = (p->I + 31) / 32;
             const double need_mb = (double)p->U * words * 4.0 / (1024.0 * 1024.0);
             if (need_mb <= budget_mb) {
