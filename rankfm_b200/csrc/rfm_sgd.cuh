@@ -83,6 +83,13 @@ __device__ __forceinline__ void sample_negatives_spec(const TrainParams& p, cons
     constexpr int KMAX = (QPL == 1) ? 4 : 2;
     const Tables& T = p.T;
     int rejects = 0;
+    // CSR membership without a memory access per candidate: a user with at most 4*G observed items is held entirely
+    // in the registers of its lane group (lane `sub` keeps items sub, sub+G, sub+2G, sub+3G); longer lists are searched
+    constexpr int OWN = 4;
+    int own[OWN];
+    const bool listed = !p.bitmap && deg <= OWN * G;
+#pragma unroll
+    for (int k = 0; k < OWN; ++k) own[k] = (!done && listed && sub + k * G < deg) ? __ldg(p.indices + seg + sub + k * G) : -1;
     while (__any_sync(0xffffffffu, !done)) {
         const Philox4 blk = philox4x32_10((uint32_t)row, p.epoch_key, attempt >> 2, 0u, p.k0, p.k1);
         const int off = (int)(attempt & 3u);
@@ -106,7 +113,12 @@ __device__ __forceinline__ void sample_negatives_spec(const TrainParams& p, cons
             const bool live = !done && w < navail;
             bool member;
             if (p.bitmap) member = ((mword[w] >> (cj[w] & 31)) & 1u) != 0u;
-            else member = group_member<G>(cj[w], p.indices + seg, deg, live, sub, gw);
+            else {
+                const int c = cj[w];
+                const bool hit = group_ballot<G>(own[0] == c || own[1] == c || own[2] == c || own[3] == c, gw) != 0u;
+                const bool searched = group_member<G>(c, p.indices + seg, deg, live && !listed, sub, gw);
+                member = listed ? hit : searched;
+            }
             const float pu = ut_ui - utility<G, QPL, FEAT>(uc, cand[w]);
             if (live) {
                 ++attempt;

@@ -57,6 +57,27 @@ def test_serial_philox_fit_matches_oracle(gpu_lib, case):
     assert [s['draws'] for s in stats] == out['draws'].tolist()
 
 
+@pytest.mark.parametrize("case", ["warp_f20", "warp_feat", "warp_if_only", "bpr_f16"])
+def test_serial_philox_without_bitmap_matches_oracle(gpu_lib, case, monkeypatch):
+    """membership through the CSR (register-resident short lists, (G+1)-ary search for long ones) instead of the bitmap"""
+    monkeypatch.setenv("RANKFM_B200_BITMAP_MB", "0")
+    g = load_golden(case)
+    deg = np.diff(g['indptr'])
+    assert deg.max() > 32 and deg.min() <= 16            # both the listed and the searched path are exercised
+    args, w, _ = golden_fit_args(g)
+    stats = _rankfm.fit_ex(*args, g['epochs'], seed=99, order=_lib.ORDER_FEISTEL, sampler=_lib.SAMPLER_PHILOX, sched=_lib.SCHED_SERIAL, max_rejects=64)
+    args_o, wo, _ = golden_fit_args(g)
+    out = oracle.fit_ex(*args_o, g['epochs'], perms=None, sampler="philox", seed=99, max_rejects=64)
+    for k in WEIGHTS:
+        assert rel_err(w[k], wo[k]) < 1e-4, k
+    assert [s['draws'] for s in stats] == out['draws'].tolist()
+    # and the Hogwild schedule runs through the same code
+    args_p, wp, _ = golden_fit_args(g)
+    sp = _rankfm.fit_ex(*args_p, g['epochs'], mode="production", seed=99)
+    np.testing.assert_allclose([s['draws'] for s in sp], out['draws'], rtol=0.1)
+    assert all(all(s['finite']) for s in sp)
+
+
 @pytest.mark.parametrize("case,sampler", [("warp_f20", "mt"), ("warp_feat", "mt"), ("warp_f20", "philox"), ("bpr_f16", "philox")])
 def test_sampler_is_draw_for_draw_identical_to_the_oracle(gpu_lib, case, sampler):
     """per position of the epoch: same negative item, same number of draws as the oracle (first epoch, where both
