@@ -162,6 +162,7 @@ struct rfm_session {
     void* comm = nullptr;
     float *d_it_snap = nullptr, *d_gp_snap = nullptr, *d_ut_init = nullptr;
     float* d_gp_acc = nullptr;
+    float *d_xuf = nullptr, *d_xif = nullptr;   // device copies of x_uf [U,P] / x_if [I,Q] (only when that block is active)
     int32_t* d_item_touch = nullptr;    // multi-GPU: how often each item occurs as a positive in this rank's shard
     // scratch
     float *d_snap_ut = nullptr, *d_snap_it = nullptr, *d_snap_gp = nullptr; int snap_epochs = 0;
@@ -192,33 +193,45 @@ static int dev_alloc(T** out, size_t n)
     return RFM_OK;
 }
 
+// scope-owned device buffer: freed on every exit path
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return dev_alloc(&p, n); }
+    operator T*() const { return p; }
+};
+
 static int upload_weights(rfm_session* s, const float* w_i, const float* w_if, const float* v_u, const float* v_i,
                           const float* v_uf, const float* v_if, const float* x_uf, const float* x_if)
 {
     const Tables& T = s->T;
-    float *st_vu = nullptr, *st_vi = nullptr, *st_wi = nullptr, *st_xu = nullptr, *st_xi = nullptr, *st_g = nullptr;
+    DevBuf<float> st_vu, st_vi, st_wi, st_g;
     int rc;
-    if ((rc = dev_alloc(&st_vu, (size_t)T.U * T.F))) return rc;
-    if ((rc = dev_alloc(&st_vi, (size_t)T.I * T.F))) return rc;
-    if ((rc = dev_alloc(&st_wi, (size_t)T.I))) return rc;
+    if ((rc = st_vu.alloc((size_t)T.U * T.F))) return rc;
+    if ((rc = st_vi.alloc((size_t)T.I * T.F))) return rc;
+    if ((rc = st_wi.alloc((size_t)T.I))) return rc;
     CU(cudaMemcpyAsync(st_vu, v_u, (size_t)T.U * T.F * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(st_vi, v_i, (size_t)T.I * T.F * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(st_wi, w_i, (size_t)T.I * 4, cudaMemcpyHostToDevice, s->st));
-    if (T.Pp) { if ((rc = dev_alloc(&st_xu, (size_t)T.U * T.P))) return rc; CU(cudaMemcpyAsync(st_xu, x_uf, (size_t)T.U * T.P * 4, cudaMemcpyHostToDevice, s->st)); }
-    if (T.Qp) { if ((rc = dev_alloc(&st_xi, (size_t)T.I * T.Q))) return rc; CU(cudaMemcpyAsync(st_xi, x_if, (size_t)T.I * T.Q * 4, cudaMemcpyHostToDevice, s->st)); }
-    CU(launch_pack_users(T, st_vu, st_xu, s->st));
-    CU(launch_pack_items(T, st_vi, st_wi, st_xi, s->st));
+    // the (read-only) feature matrices are uploaded once per session and kept, so later weight uploads need no host copy
+    if (T.Pp && !s->d_xuf) { if ((rc = dev_alloc(&s->d_xuf, (size_t)T.U * T.P))) return rc; CU(cudaMemcpyAsync(s->d_xuf, x_uf, (size_t)T.U * T.P * 4, cudaMemcpyHostToDevice, s->st)); }
+    if (T.Qp && !s->d_xif) { if ((rc = dev_alloc(&s->d_xif, (size_t)T.I * T.Q))) return rc; CU(cudaMemcpyAsync(s->d_xif, x_if, (size_t)T.I * T.Q * 4, cudaMemcpyHostToDevice, s->st)); }
+    CU(launch_pack_users(T, st_vu, s->d_xuf, s->st));
+    CU(launch_pack_items(T, st_vi, st_wi, s->d_xif, s->st));
     s->launches += 2;
     // globals
     const size_t n_wif = (size_t)T.Q, n_vuf = (size_t)T.P * T.F, n_vif = (size_t)T.Q * T.F;
-    if ((rc = dev_alloc(&st_g, n_wif + n_vuf + n_vif))) return rc;
+    if ((rc = st_g.alloc(n_wif + n_vuf + n_vif))) return rc;
     CU(cudaMemcpyAsync(st_g, w_if, n_wif * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(st_g + n_wif, v_uf, n_vuf * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(st_g + n_wif + n_vuf, v_if, n_vif * 4, cudaMemcpyHostToDevice, s->st));
     CU(launch_pack_globals(T, st_g, st_g + n_wif, st_g + n_wif + n_vuf, (int)s->gp_floats, s->st));
     s->launches += 1;
     CU(cudaStreamSynchronize(s->st));
-    cudaFree(st_vu); cudaFree(st_vi); cudaFree(st_wi); cudaFree(st_xu); cudaFree(st_xi); cudaFree(st_g);
     return RFM_OK;
 }
 
@@ -231,7 +244,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->T.UT); cudaFree(s->T.IT); cudaFree(s->T.GP);
     cudaFree(s->d_inter); cudaFree(s->d_sw); cudaFree(s->d_indptr); cudaFree(s->d_indices);
     cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
-    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc); cudaFree(s->d_item_touch);
+    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc); cudaFree(s->d_item_touch); cudaFree(s->d_xuf); cudaFree(s->d_xif);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
     cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
     for (void* q : s->scratch) cudaFree(q);
@@ -393,11 +406,7 @@ extern "C" int rfm_session_set_weights(rfm_session* s, const float* w_i, const f
 {
     if (!s) return fail(RFM_ERR_ARG, "NULL session");
     CU(cudaSetDevice(s->device));
-    // feature blocks of the fat rows are rewritten from the staging copy of x_uf / x_if kept by the caller
-    if (s->T.Pp || s->T.Qp) {
-        if (!s->p.x_uf || !s->p.x_if) return fail(RFM_ERR_ARG, "set_weights with features needs the original x_uf/x_if pointers to be alive");
-    }
-    int rc = upload_weights(s, w_i, w_if, v_u, v_i, v_uf, v_if, s->p.x_uf, s->p.x_if);
+    int rc = upload_weights(s, w_i, w_if, v_u, v_i, v_uf, v_if, nullptr, nullptr);   // features stay as uploaded at creation
     if (rc) return rc;
     s->gemm_valid = false;
     if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->T.UT, (size_t)s->T.U * s->T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
@@ -472,13 +481,13 @@ extern "C" int rfm_session_download(rfm_session* s, float* w_i, float* w_if, flo
     if (!s) return fail(RFM_ERR_ARG, "NULL session");
     CU(cudaSetDevice(s->device));
     const Tables& T = s->T;
-    float *st_vu = nullptr, *st_vi = nullptr, *st_wi = nullptr, *st_g = nullptr;
+    DevBuf<float> st_vu, st_vi, st_wi, st_g;
     int rc;
-    if ((rc = dev_alloc(&st_vu, (size_t)T.U * T.F))) return rc;
-    if ((rc = dev_alloc(&st_vi, (size_t)T.I * T.F))) return rc;
-    if ((rc = dev_alloc(&st_wi, (size_t)T.I))) return rc;
+    if ((rc = st_vu.alloc((size_t)T.U * T.F))) return rc;
+    if ((rc = st_vi.alloc((size_t)T.I * T.F))) return rc;
+    if ((rc = st_wi.alloc((size_t)T.I))) return rc;
     const size_t n_wif = (size_t)T.Q, n_vuf = (size_t)T.P * T.F, n_vif = (size_t)T.Q * T.F;
-    if ((rc = dev_alloc(&st_g, n_wif + n_vuf + n_vif))) return rc;
+    if ((rc = st_g.alloc(n_wif + n_vuf + n_vif))) return rc;
     CU(launch_unpack_users(T, st_vu, s->st));
     CU(launch_unpack_items(T, st_vi, st_wi, s->st));
     CU(launch_unpack_globals(T, st_g, st_g + n_wif, st_g + n_wif + n_vuf, s->st));
@@ -490,7 +499,6 @@ extern "C" int rfm_session_download(rfm_session* s, float* w_i, float* w_if, flo
     CU(cudaMemcpyAsync(v_uf, st_g + n_wif, n_vuf * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(v_if, st_g + n_wif + n_vuf, n_vif * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
-    cudaFree(st_vu); cudaFree(st_vi); cudaFree(st_wi); cudaFree(st_g);
     return RFM_OK;
 }
 
@@ -724,15 +732,14 @@ extern "C" int rfm_session_predict(rfm_session* s, const float* pairs, int64_t n
     if (!s || (n > 0 && (!pairs || !scores))) return fail(RFM_ERR_ARG, "NULL argument");
     if (n == 0) return RFM_OK;
     CU(cudaSetDevice(s->device));
-    float2* d_pairs = nullptr; float* d_scores = nullptr;
+    DevBuf<float2> d_pairs; DevBuf<float> d_scores;
     int rc;
-    if ((rc = dev_alloc(&d_pairs, (size_t)n))) return rc;
-    if ((rc = dev_alloc(&d_scores, (size_t)n))) return rc;
+    if ((rc = d_pairs.alloc((size_t)n))) return rc;
+    if ((rc = d_scores.alloc((size_t)n))) return rc;
     CU(cudaMemcpyAsync(d_pairs, pairs, (size_t)n * 8, cudaMemcpyHostToDevice, s->st));
     if ((rc = predict_dev(s, d_pairs, n, d_scores))) return rc;
     CU(cudaMemcpyAsync(scores, d_scores, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
-    cudaFree(d_pairs); cudaFree(d_scores);
     return RFM_OK;
 }
 
@@ -740,10 +747,10 @@ extern "C" int rfm_session_time_predict(rfm_session* s, const float* pairs, int6
 {
     if (!s || !pairs || !ms_out || n <= 0 || iters < 1) return fail(RFM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(s->device));
-    float2* d_pairs = nullptr; float* d_scores = nullptr;
+    DevBuf<float2> d_pairs; DevBuf<float> d_scores;
     int rc;
-    if ((rc = dev_alloc(&d_pairs, (size_t)n))) return rc;
-    if ((rc = dev_alloc(&d_scores, (size_t)n))) return rc;
+    if ((rc = d_pairs.alloc((size_t)n))) return rc;
+    if ((rc = d_scores.alloc((size_t)n))) return rc;
     CU(cudaMemcpyAsync(d_pairs, pairs, (size_t)n * 8, cudaMemcpyHostToDevice, s->st));
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
@@ -756,7 +763,6 @@ extern "C" int rfm_session_time_predict(rfm_session* s, const float* pairs, int6
     cudaEventElapsedTime(&ms, a, b);
     *ms_out = ms / iters;
     cudaEventDestroy(a); cudaEventDestroy(b);
-    cudaFree(d_pairs); cudaFree(d_scores);
     return RFM_OK;
 }
 
@@ -980,9 +986,9 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     const int64_t n_tc = recommend_plan(s, hu, n_items, filter_previous, order);
     std::vector<int32_t> hp((size_t)n_users);
     for (int64_t k = 0; k < n_users; ++k) hp[(size_t)k] = hu[(size_t)order[(size_t)k]];
-    int32_t* d_users = nullptr; float* d_rec = nullptr;
-    if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
-    if ((rc = dev_alloc(&d_rec, (size_t)n_users * n_items))) return rc;
+    DevBuf<int32_t> d_users; DevBuf<float> d_rec;
+    if ((rc = d_users.alloc((size_t)n_users))) return rc;
+    if ((rc = d_rec.alloc((size_t)n_users * n_items))) return rc;
     CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
     std::vector<float> tmp((size_t)n_users * n_items);
@@ -990,7 +996,6 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     CU(cudaStreamSynchronize(s->st));
     for (int64_t k = 0; k < n_users; ++k)
         memcpy(rec_items + (size_t)order[(size_t)k] * n_items, tmp.data() + (size_t)k * n_items, (size_t)n_items * 4);
-    cudaFree(d_users); cudaFree(d_rec);
     return RFM_OK;
 }
 
@@ -1007,9 +1012,9 @@ extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, in
     const int64_t n_tc = recommend_plan(s, hu, n_items, filter_previous, order);
     std::vector<int32_t> hp((size_t)n_users);
     for (int64_t k = 0; k < n_users; ++k) hp[(size_t)k] = hu[(size_t)order[(size_t)k]];
-    int32_t* d_users = nullptr; float* d_rec = nullptr;
-    if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
-    if ((rc = dev_alloc(&d_rec, (size_t)n_users * n_items))) return rc;
+    DevBuf<int32_t> d_users; DevBuf<float> d_rec;
+    if ((rc = d_users.alloc((size_t)n_users))) return rc;
+    if ((rc = d_rec.alloc((size_t)n_users * n_items))) return rc;
     CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;   // warm-up
     cudaEvent_t a, b;
@@ -1028,7 +1033,6 @@ extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, in
     *ms_out = ms / iters;
     if (gemm_ms_out) *gemm_ms_out = gemm_total / iters;
     cudaEventDestroy(a); cudaEventDestroy(b);
-    cudaFree(d_users); cudaFree(d_rec);
     return RFM_OK;
 }
 
@@ -1044,17 +1048,16 @@ extern "C" int rfm_session_debug_gemm(rfm_session* s, const float* users, int64_
     users_to_int(users, n_users, hu);
     const Tables& T = s->T;
     const int Kp = gemm_kp(T), I_pad = s->gemm_I_pad, M_pad = (int)((n_users + 127) / 128 * 128);
-    int32_t* d_users = nullptr; void* d_A = nullptr; float* d_S = nullptr;
-    if ((rc = dev_alloc(&d_users, (size_t)n_users))) return rc;
-    CU(cudaMalloc(&d_A, (size_t)M_pad * Kp * 2));
-    if ((rc = dev_alloc(&d_S, (size_t)M_pad * I_pad))) return rc;
+    DevBuf<int32_t> d_users; DevBuf<__nv_bfloat16_raw> d_A; DevBuf<float> d_S;
+    if ((rc = d_users.alloc((size_t)n_users))) return rc;
+    if ((rc = d_A.alloc((size_t)M_pad * Kp))) return rc;
+    if ((rc = d_S.alloc((size_t)M_pad * I_pad))) return rc;
     CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     CU(launch_pack_gemm_users(T, d_users, (int)n_users, M_pad, Kp, d_A, s->st));
     cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
     if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e));
     CU(cudaMemcpy2DAsync(scores_out, (size_t)T.I * 4, d_S, (size_t)I_pad * 4, (size_t)T.I * 4, (size_t)n_users, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
-    cudaFree(d_users); cudaFree(d_A); cudaFree(d_S);
     return RFM_OK;
 }
 
