@@ -67,6 +67,21 @@ def recall(model, test_interactions, k=10, filter_previous=False):
     return np.mean(hits.sum(axis=1) / n_test)
 
 
+def all_metrics(model, test_interactions, k=10, filter_previous=False):
+    """the five ranking metrics from ONE recommendation pass (the reference needs five passes, one per metric:
+    `examples/movielens.ipynb:1387`); returns a dict keyed by the metric function names"""
+    hits, n_test = _hits(model, test_interactions, k, filter_previous)
+    any_hit = hits.any(axis=1)
+    gains = 1.0 / np.log2(np.arange(hits.shape[1]) + 2)
+    return {
+        "hit_rate": float(np.mean(any_hit.astype(int))),
+        "reciprocal_rank": float(np.mean(np.where(any_hit, 1.0 / (np.argmax(hits, axis=1) + 1), 0.0))),
+        "discounted_cumulative_gain": float(np.mean((hits * gains).sum(axis=1))),
+        "precision": float(np.mean(hits.sum(axis=1) / hits.shape[1])),
+        "recall": float(np.mean(hits.sum(axis=1) / n_test)),
+    }
+
+
 def diversity(model, test_interactions, k=10, filter_previous=False):
     """count / share of users each item is recommended to (``evaluation.py:146-175``)"""
     assert model.is_fit, "you must fit the model prior to evaluating hold-out metrics"

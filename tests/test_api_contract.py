@@ -12,7 +12,7 @@ import pytest
 
 import rankfm_b200.rankfm as rankfm_mod
 from rankfm_b200 import _rankfm
-from rankfm_b200.evaluation import discounted_cumulative_gain, diversity, hit_rate, precision, recall, reciprocal_rank
+from rankfm_b200.evaluation import all_metrics, discounted_cumulative_gain, diversity, hit_rate, precision, recall, reciprocal_rank
 from rankfm_b200.rankfm import RankFM
 
 PAIRS = [(1, 1), (1, 3), (1, 5), (2, 1), (2, 2), (2, 6), (3, 3), (3, 6), (3, 4)]
@@ -182,5 +182,10 @@ def test_evaluation_metrics(backend):
     assert reciprocal_rank(model, test, k, True) == pytest.approx(np.mean([1 / (h.index(1) + 1) if 1 in h else 0 for h in hits.values()]))
     assert discounted_cumulative_gain(model, test, k, True) == pytest.approx(
         np.mean([sum(x / np.log2(r + 2) for r, x in enumerate(h)) for h in hits.values()]))
+    both = all_metrics(model, test, k, True)
+    assert both["hit_rate"] == pytest.approx(hit_rate(model, test, k, True)) and both["recall"] == pytest.approx(recall(model, test, k, True))
+    assert both["reciprocal_rank"] == pytest.approx(reciprocal_rank(model, test, k, True))
+    assert both["discounted_cumulative_gain"] == pytest.approx(discounted_cumulative_gain(model, test, k, True))
+    assert both["precision"] == pytest.approx(precision(model, test, k, True))
     div = diversity(model, test, k, True)
     assert list(div.columns) == ['item_id', 'cnt_users', 'pct_users'] and div['cnt_users'].sum() == 3 * k and len(div) == 6
