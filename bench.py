@@ -353,13 +353,15 @@ def dram_resident_probe(device=0, steps=2):
             "interactions_per_s": N * len(flat) / (kern_ms / 1e3)}
 
 
-def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, device=0):
-    """secondary measurement (BASELINE.json configs[4] shape, scaled to seconds): recommend() top-100 through the
-    tcgen05 candidate GEMM.  TFLOP/s = 2*U*I*K / CUDA-event time of the GEMM+filter kernel; inputs resident in HBM."""
+def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, device=0, iters=3, exact_users=4096):
+    """secondary measurement (BASELINE.json configs[4] shape; the default is scaled to milliseconds, `--workload cfg5` runs
+    the full 1M x 1M): recommend() top-100 through the tcgen05 candidate GEMM.  TFLOP/s = 2*U*I*K / CUDA-event time of the
+    GEMM + filter kernels (both passes, thresholds included); inputs resident in HBM."""
     from rankfm_b200 import _rankfm
     rng = np.random.default_rng(0)
     w = dict(w_i=rng.normal(0, 0.3, n_items_cat).astype(np.float32), w_if=np.zeros(1, np.float32),
-             v_u=rng.normal(0, 0.1, (n_users, factors)).astype(np.float32), v_i=rng.normal(0, 0.1, (n_items_cat, factors)).astype(np.float32),
+             v_u=rng.standard_normal((n_users, factors), dtype=np.float32) * np.float32(0.1),
+             v_i=rng.standard_normal((n_items_cat, factors), dtype=np.float32) * np.float32(0.1),
              v_uf=np.zeros((1, factors), np.float32), v_if=np.zeros((1, factors), np.float32))
     x_uf, x_if = np.zeros((n_users, 1), np.float32), np.zeros((n_items_cat, 1), np.float32)
     keep = []
@@ -368,12 +370,15 @@ def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, de
     sess = _rankfm.Session(prob, keep)
     users = np.arange(n_users, dtype=np.float32)
     os.environ["RANKFM_B200_RECOMMEND"] = "tc"
-    ms, gemm_ms = sess.time_recommend(users, topn, False, iters=3)
+    ms, gemm_ms = sess.time_recommend(users, topn, False, iters=iters)
+    tc_rows, tc_redone = sess.recommend_stats()
     sample = users[:256]
     fast = sess.recommend(sample, topn, False)
     os.environ["RANKFM_B200_RECOMMEND"] = "exact"
     exact = sess.recommend(sample, topn, False)
-    ms_exact, _ = sess.time_recommend(users[:4096], topn, False, iters=1)
+    ms_exact = None
+    if exact_users:
+        ms_exact, _ = sess.time_recommend(users[:exact_users], topn, False, iters=1)
     os.environ.pop("RANKFM_B200_RECOMMEND", None)
     sess.close()
     overlap = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / topn for a, b in zip(fast, exact)]))
@@ -386,7 +391,30 @@ def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, de
     return {"workload": "recommend top-%d, %d users x %d items, factors=%d (tcgen05 bf16 candidate GEMM + exact fp32 re-score)" % (topn, n_users, n_items_cat, factors),
             "ms_total": ms, "ms_gemm_filter": gemm_ms, "tflops_gemm_filter": flops / (gemm_ms * 1e-3) / 1e12, "tflops_end_to_end": flops / (ms * 1e-3) / 1e12,
             "bf16_peak_tflops": peak, "frac_of_bf16_peak": flops / (gemm_ms * 1e-3) / 1e12 / peak, "users_per_s": n_users / (ms * 1e-3),
-            "exact_fp32_path_users_per_s": 4096 / (ms_exact * 1e-3), "topk_overlap_vs_exact": overlap}
+            "exact_fp32_path_users_per_s": (exact_users / (ms_exact * 1e-3)) if ms_exact else None, "topk_overlap_vs_exact": overlap,
+            "rows_redone_on_exact_path": "%d of %d" % (tc_redone, tc_rows),
+            "variant": {k: os.environ.get(k, "default") for k in ("RANKFM_B200_GEMM_MSUB", "RANKFM_B200_TAU_STRIDE")}}
+
+
+def run_recommend(args):
+    """--workload cfg5: BASELINE.json configs[4] at full size (recommend top-100 for 1M users over 1M items, factors=128);
+    one JSON line, metric users/s, roofline = bf16 tensor peak"""
+    from rankfm_b200 import _lib, _rankfm
+    assert _lib.lib().rfm_device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
+    _rankfm.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    U = int(os.environ.get("BENCH_CFG5_USERS", 1_000_000))
+    I = int(os.environ.get("BENCH_CFG5_ITEMS", 1_000_000))
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    r = recommend_probe(n_users=U, n_items_cat=I, factors=128, topn=100, iters=max(1, args.steps), exact_users=1024)
+    clock_info = clocks.stop()
+    line = {"metric": "recommend users/sec", "value": r["users_per_s"], "unit": "users/s", "n_gpus": 1, "steps": max(1, args.steps), "warmup": 1,
+            "ms_per_step": r["ms_total"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 operands, f32 accumulate, f32 exact re-score",
+            "data": "synthetic", "config": {"workload": r["workload"]},
+            "roofline": {"bound": "tensor", "kernel": "score_filter_kernel (pass 1 + pass 2)", "achieved": r["tflops_gemm_filter"], "peak": r["bf16_peak_tflops"],
+                         "unit": "TFLOP/s", "frac": r["frac_of_bf16_peak"], "traffic": None,
+                         "note": "useful FLOPs 2*U*I*K over the CUDA-event time of both GEMM passes + threshold kernels"},
+            "recommend": r, "clocks": clock_info}
+    print(json.dumps(line))
 
 
 def main():
@@ -395,12 +423,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(CONFIGS) + ["cfg5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recommend", action="store_true", help="skip the secondary recommend() tensor-core measurement")
     ap.add_argument("--no-large", action="store_true", help="skip the DRAM-resident roofline probe (cfg4m)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "cfg5" and args.impl == "ours":
+        run_recommend(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

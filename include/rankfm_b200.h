@@ -153,6 +153,9 @@ int rfm_session_trace_enable(rfm_session *s);
 int rfm_session_trace_read(rfm_session *s, int32_t *neg_and_sampled /* [N,2] */);
 /* debugging / parity: dense bf16 tensor-core scores (A.B^T + bias) of the requested users against all items */
 int rfm_session_debug_gemm(rfm_session *s, const float *users, int64_t n_users, float *scores_out /* [n_users, I] */);
+/* tensor-core recommend bookkeeping since session creation: rows served by the tcgen05 path, and how many of those had to
+ * be redone on the exact fp32 path because a candidate slot overflowed */
+int rfm_session_recommend_stats(rfm_session *s, int64_t *tc_rows, int64_t *tc_redone);
 int rfm_session_flush_l2(rfm_session *s);                                    /* overwrite a >L2-sized scratch buffer */
 int rfm_session_launch_count(rfm_session *s, int64_t *launches);             /* kernels launched by this session */
 int rfm_session_destroy(rfm_session *s);

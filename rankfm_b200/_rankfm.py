@@ -373,6 +373,12 @@ class Session:
         check(_lib.lib().rfm_session_debug_gemm(self._h, ptr(users), users.shape[0], ptr(out)))
         return out
 
+    def recommend_stats(self):
+        """(rows served by the tensor-core recommend path, rows of those redone on the exact path)"""
+        rows, redo = C.c_int64(), C.c_int64()
+        check(_lib.lib().rfm_session_recommend_stats(self._h, C.byref(rows), C.byref(redo)))
+        return rows.value, redo.value
+
     def flush_l2(self):
         check(_lib.lib().rfm_session_flush_l2(self._h))
 

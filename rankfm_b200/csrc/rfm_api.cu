@@ -171,6 +171,7 @@ struct rfm_session {
     // tensor-core recommend: bf16 item operand + bias, rebuilt lazily whenever the weights change
     void* d_gemm_B = nullptr; float* d_gemm_bias = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
     void* scratch[12] = {nullptr}; size_t scratch_bytes[12] = {0};   // grow-only device scratch of the recommend paths
+    int64_t tc_rows = 0, tc_redo = 0;   // tensor-core recommend: rows served / rows redone on the exact path (candidate overflow)
     std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
     float* d_flush = nullptr; size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;
@@ -824,14 +825,14 @@ static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_use
     return RFM_OK;
 }
 
-constexpr int kCandCap = 256;        // candidate slots per (user row, item split, column half)
+constexpr int kCandCap = 256;        // smallest candidate-slot capacity; also the largest shortlist the tensor-core path accepts
 
 static int ensure_gemm_items(rfm_session* s)
 {
-    if (s->gemm_valid) return RFM_OK;
     const Tables& T = s->T;
     const int Kp = gemm_kp(T), BN = gemm_block_n(T);
     const int I_pad = (T.I + BN - 1) / BN * BN;
+    if (s->gemm_valid && s->gemm_I_pad == I_pad) return RFM_OK;
     if (!s->d_gemm_B || s->gemm_I_pad != I_pad) {
         cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
         s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr;
@@ -853,7 +854,31 @@ static int shortlist_target(rfm_session* s, int32_t u, int32_t n_items, int32_t 
     return need;
 }
 
-// tensor-core path (rfm_gemm.cu): pass 1 block maxima -> per-row threshold -> pass 2 candidates -> exact re-score -> top-n
+// Pass 1 (block maxima -> per-row threshold) may visit only every k-th item tile: the n'-th largest block maximum of a
+// SUBSET of the items is still a lower bound of the row's n'-th best score, just a looser one -- pass 2 then collects
+// about k x n' candidates instead of ~n', which costs a few KB of writes per row, against (1 - 1/k) of a GEMM pass saved.
+// k is the largest of {4, 2, 1} that leaves >= 4 n' blocks (fewer blocks make the bound collapse).  RANKFM_B200_TAU_STRIDE
+// = 1 | 2 | 4 | 8 caps k.
+static int tau_stride(const Tables& T, int32_t n_items)
+{
+    const char* e = getenv("RANKFM_B200_TAU_STRIDE");
+    const int cap = e ? std::max(1, atoi(e)) : 4;
+    const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN, want = 2 * n_items + 16;
+    int best = 1;
+    for (int k = 2; k <= std::min(cap, 8); k *= 2)
+        if ((int64_t)((n_tiles + k - 1) / k) * (BN / 64) >= (int64_t)4 * want) best = k;
+    return best;
+}
+
+// 64-item blocks pass 1 produces per row
+static int tau_blocks(const Tables& T, int stride)
+{
+    const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN;
+    return (n_tiles + stride - 1) / stride * (BN / 64);
+}
+
+// tensor-core path (rfm_gemm.cu): pass 1 block maxima -> per-row threshold -> pass 2 candidates -> n' best candidates by
+// bf16 score -> exact re-score -> top-n
 static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
                         float* d_rec, float* gemm_ms)
 {
@@ -861,53 +886,61 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     if (n_users <= 0) return RFM_OK;
     int rc = ensure_gemm_items(s);
     if (rc) return rc;
-    const int Kp = gemm_kp(T), BN = gemm_block_n(T), I_pad = s->gemm_I_pad, n_tiles = I_pad / BN, n_sub = I_pad / 64;
-    int64_t max_rows = std::min<int64_t>(16384, (((int64_t)1 << 30) / ((int64_t)n_sub * 4)) / 128 * 128);
-    max_rows = std::max<int64_t>(128, max_rows);
+    const int Kp = gemm_kp(T), MT = gemm_m_tile(T), SPS = gemm_slots_per_split(T), I_pad = s->gemm_I_pad;
+    const int stride = tau_stride(T, n_items), n_sub1 = tau_blocks(T, stride), n_tiles1 = n_sub1 / (gemm_block_n(T) / 64);
+    // candidate entries per row: ~1-2 n' with a full pass 1, ~stride x n' with a strided one (n' <= kCandCap)
+    const int width = stride == 1 ? 6 * kCandCap : 4 * kCandCap * stride;
+    // one wave: at most n_sm CTAs (one resident per SM), user tiles x item splits; >= 2 splits keep a partial last batch balanced
+    int64_t max_rows = (int64_t)std::max(1, s->n_sm / 2) * MT;
+    max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)2 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
+    const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
+    const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
-    float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr;
+    float *d_rowmax = nullptr, *d_tau = nullptr, *d_tau2 = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr;
     auto done = [&](int code) { cudaFree(d_fix); cudaFree(d_fix_users); return code; };
-    const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + 127) / 128 * 128);
-    const int max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(8, n_tiles), (2 * s->n_sm + rows_alloc / 128 - 1) / (rows_alloc / 128)));
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
     if ((rc = scratch_get(s, 2, (size_t)rows_alloc, &d_ntgt))) return rc;
     if ((rc = scratch_get(s, 3, (size_t)rows_alloc, &d_tau))) return rc;
-    if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub, &d_rowmax))) return rc;
-    if ((rc = scratch_get(s, 5, (size_t)rows_alloc * 2 * max_splits * kCandCap, &d_cand))) return rc;
-    if ((rc = scratch_get(s, 6, (size_t)rows_alloc * 2 * max_splits, &d_cnt))) return rc;
-    if ((rc = scratch_get(s, 7, (size_t)rows_alloc * 2 * max_splits * kCandCap, &d_S2))) return rc;
-    if ((rc = scratch_get(s, 8, (size_t)rows_alloc * 2 * max_splits * kCandCap, &d_map))) return rc;
+    if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub1, &d_rowmax))) return rc;
+    if ((rc = scratch_get(s, 5, (size_t)rows_alloc * width, &d_cand))) return rc;
+    if ((rc = scratch_get(s, 6, (size_t)rows_alloc * split_cap * SPS, &d_cnt))) return rc;
+    if ((rc = scratch_get(s, 7, (size_t)rows_alloc * width, &d_S2))) return rc;
+    if ((rc = scratch_get(s, 8, (size_t)rows_alloc * width, &d_map))) return rc;
+    if ((rc = scratch_get(s, 9, (size_t)rows_alloc, &d_tau2))) return rc;
     std::vector<int> ntgt((size_t)rows_alloc), cnt_h;
     cudaEvent_t a = nullptr, b = nullptr;
     if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
     for (int64_t off = 0; off < n_users; off += rows_alloc) {
         const int nb = (int)std::min<int64_t>(rows_alloc, n_users - off);
-        const int M_pad = (nb + 127) / 128 * 128;
-        const int n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(max_splits, (2 * s->n_sm + M_pad / 128 - 1) / (M_pad / 128)));
+        const int M_pad = (nb + MT - 1) / MT * MT;
+        const int n_splits = std::max(1, std::min(split_cap, s->n_sm / (M_pad / MT)));
+        const int slots = n_splits * SPS, cap = width / slots;
         for (int r = 0; r < M_pad; ++r) ntgt[(size_t)r] = shortlist_target(s, r < nb ? h_users[off + r] : -1, n_items, filter_previous);
         CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), (size_t)M_pad * 4, cudaMemcpyHostToDevice, s->st));
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
         if (gemm_ms) CU(cudaEventRecord(a, s->st));
-        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
+        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, stride, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
-        CU(launch_row_threshold(d_rowmax, M_pad, n_sub, d_ntgt, d_tau, s->st));
-        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, d_cand, d_cnt, d_tau, kCandCap, nullptr, nullptr, s->st);
+        CU(launch_row_threshold(d_rowmax, M_pad, n_sub1, d_ntgt, d_tau, s->st));
+        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, d_cand, d_cnt, d_tau, cap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
+        if (stride > 1) { CU(launch_cand_threshold(d_cand, d_cnt, nb, slots, cap, d_ntgt, d_tau2, s->st)); s->launches += 1; }
         if (gemm_ms) CU(cudaEventRecord(b, s->st));
-        e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, 2 * n_splits, kCandCap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, s->st);
+        e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, slots, cap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, stride > 1 ? d_tau2 : nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "rescore launch failed: %s", cudaGetErrorString(e)));
-        e = launch_topn_select(d_S2, 2 * n_splits * kCandCap, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
+        e = launch_topn_select(d_S2, slots * cap, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "topn_select launch failed: %s", cudaGetErrorString(e)));
         s->launches += 6;
         // rows whose candidate buffer overflowed (pathological ties / clustered scores) are redone on the exact path
-        cnt_h.resize((size_t)nb * 2 * n_splits);
-        CU(cudaMemcpyAsync(cnt_h.data(), d_cnt, (size_t)nb * 2 * n_splits * 4, cudaMemcpyDeviceToHost, s->st));
+        cnt_h.resize((size_t)nb * slots);
+        CU(cudaMemcpyAsync(cnt_h.data(), d_cnt, (size_t)nb * slots * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaStreamSynchronize(s->st));
         if (gemm_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); *gemm_ms += ms; }
         std::vector<int32_t> redo_users; std::vector<int> redo_rows;
         for (int r = 0; r < nb; ++r)
-            for (int sp = 0; sp < 2 * n_splits; ++sp)
-                if (cnt_h[(size_t)r * 2 * n_splits + sp] > kCandCap) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); break; }
+            for (int sp = 0; sp < slots; ++sp)
+                if (cnt_h[(size_t)r * slots + sp] > cap) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); break; }
+        s->tc_rows += nb; s->tc_redo += (int64_t)redo_users.size();
         if (!redo_users.empty()) {
             cudaFree(d_fix); cudaFree(d_fix_users); d_fix = nullptr; d_fix_users = nullptr;
             if ((rc = dev_alloc(&d_fix_users, redo_users.size()))) return done(rc);
@@ -942,9 +975,7 @@ static int64_t recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, in
     const Tables& T = s->T;
     bool tc = mode != 2 && gemm_supported(T) && encode_ok() && (mode == 1 || ((int64_t)T.I >= 32768 && n * (int64_t)T.I >= ((int64_t)1 << 26)));
     // the per-row threshold is the n'-th largest maximum over 64-item blocks: needs comfortably more blocks than n'
-    const int BN = gemm_block_n(T);
-    const int n_sub = ((T.I + BN - 1) / BN * BN) / 64;
-    const int limit = std::min(kCandCap, n_sub / 2);
+    const int limit = std::min(kCandCap, tau_blocks(T, tau_stride(T, n_items)) / 2);
     if (2 * n_items + 16 > limit) tc = false;
     int64_t lo = 0, hi = n;
     for (int64_t k = 0; k < n; ++k) {
@@ -1047,14 +1078,14 @@ extern "C" int rfm_session_debug_gemm(rfm_session* s, const float* users, int64_
     std::vector<int32_t> hu;
     users_to_int(users, n_users, hu);
     const Tables& T = s->T;
-    const int Kp = gemm_kp(T), I_pad = s->gemm_I_pad, M_pad = (int)((n_users + 127) / 128 * 128);
+    const int Kp = gemm_kp(T), I_pad = s->gemm_I_pad, MT = gemm_m_tile(T), M_pad = (int)((n_users + MT - 1) / MT * MT);
     DevBuf<int32_t> d_users; DevBuf<__nv_bfloat16_raw> d_A; DevBuf<float> d_S;
     if ((rc = d_users.alloc((size_t)n_users))) return rc;
     if ((rc = d_A.alloc((size_t)M_pad * Kp))) return rc;
     if ((rc = d_S.alloc((size_t)M_pad * I_pad))) return rc;
     CU(cudaMemcpyAsync(d_users, hu.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     CU(launch_pack_gemm_users(T, d_users, (int)n_users, M_pad, Kp, d_A, s->st));
-    cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
+    cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
     if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e));
     CU(cudaMemcpy2DAsync(scores_out, (size_t)T.I * 4, d_S, (size_t)I_pad * 4, (size_t)T.I * 4, (size_t)n_users, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
@@ -1076,6 +1107,13 @@ extern "C" int rfm_session_trace_read(rfm_session* s, int32_t* out)
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(out, s->d_trace, (size_t)s->N * 8, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_recommend_stats(rfm_session* s, int64_t* tc_rows, int64_t* tc_redone)
+{
+    if (!s || !tc_rows || !tc_redone) return fail(RFM_ERR_ARG, "NULL argument");
+    *tc_rows = s->tc_rows; *tc_redone = s->tc_redo;
     return RFM_OK;
 }
 

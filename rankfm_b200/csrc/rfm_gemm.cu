@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstdlib>
 #include "rfm_kernels.h"
 #include "rfm_pair.cuh"
 
@@ -144,17 +145,18 @@ __device__ __forceinline__ uint32_t ord_key(float s) { const uint32_t b = __floa
 struct GemmParams {
     const float* bias;           // [I_pad] fp32 item bias (w_i + x_if.w_if); -1e30 for padded items
     int kblocks;                 // Kp / 64
-    int n_tiles;                 // I_pad / BLOCK_N
+    int n_tiles;                 // item tiles this launch visits (pass 1 may visit only every tile_stride-th tile)
+    int tile_stride;             // visited tile k is item tile k * tile_stride
     int n_splits;                // item-range splits (grid.y)
     int n_users;                 // valid rows of A
     int nstage;
     // MODE_FILTER
-    float2* cand;                // [M_pad * 2*n_splits, cap]  (score, item index as int bits); 2 column halves per split
-    int* cand_cnt;               // [M_pad * 2*n_splits]; cap+1 flags an overflowing slot
+    float2* cand;                // [M_pad * n_slots, cap]  (score, item index as int bits); n_slots = n_splits * (MSUB == 1 ? 2 : 1)
+    int* cand_cnt;               // [M_pad * n_slots]; cap+1 flags an overflowing slot
     const float* tau;            // [M_pad] per-row threshold from pass 1
     int cap;
     // MODE_ROWMAX
-    float* rowmax;               // [M_pad, I_pad/64] block maxima
+    float* rowmax;               // [M_pad, n_tiles * BLOCK_N/64] maxima of the visited 64-item blocks
     // MODE_DUMP
     float* S;                    // [M_pad, I_pad]
     long long ldS;
@@ -163,17 +165,21 @@ struct GemmParams {
 constexpr int kGemmThreads = 384;          // warps: 0 TMA producer (A, B), 1 MMA issuer, 2 TMEM allocator, 3 bias producer, 4..11 epilogue
 constexpr int MODE_DUMP = 0, MODE_ROWMAX = 1, MODE_FILTER = 2;
 
-template <int BLOCK_N, int MODE>
+// MSUB = 128-row user sub-tiles per CTA.  MSUB == 2 halves the L2 -> shared-memory traffic per MMA: every B tile that
+// lands in shared memory feeds two M=128 MMAs (K is only 64..128 here, so with one sub-tile the kernel asks L2 for
+// 64 B/clk/SM -- 148 SMs x 64 B = 9.5 KB/clk against the ~6.3 KB/clk the L2 delivers chip-wide).
+template <int BLOCK_N, int MSUB, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
 {
+    static_assert(2 * MSUB * BLOCK_N <= 512, "two accumulator stages must fit the 512 TMEM columns");
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int A_KB_BYTES = 128 * 128;              // one 64-wide k-block of the A tile (128 rows x 128 B)
     constexpr int B_KB_BYTES = BLOCK_N * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_n = p.kblocks, nstage = p.nstage;
-    unsigned char* sA = smem;
-    unsigned char* sB = sA + (size_t)kb_n * A_KB_BYTES;
+    unsigned char* sA = smem;                          // [MSUB][kb_n] k-blocks
+    unsigned char* sB = sA + (size_t)MSUB * kb_n * A_KB_BYTES;
     float* sBias = reinterpret_cast<float*>(sB + (size_t)nstage * kb_n * B_KB_BYTES);      // [2][BLOCK_N], one slot per accumulator stage
     unsigned char* sBar = reinterpret_cast<unsigned char*>(sBias + 2 * BLOCK_N);
     const uint32_t bar_full = s32(sBar), bar_empty = bar_full + 8u * nstage, bar_a = bar_empty + 8u * nstage;
@@ -181,7 +187,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 8 * (2 * nstage + 7));
 
     // this CTA: user tile blockIdx.x, item tiles [t0, t1)
-    const int m0 = blockIdx.x * 128;
+    const int m0 = blockIdx.x * (128 * MSUB);
+    constexpr int ACC_COLS = MSUB * BLOCK_N;           // TMEM columns of one accumulator stage
     const int per = (p.n_tiles + p.n_splits - 1) / p.n_splits;
     const int t0 = blockIdx.y * per, t1 = min(p.n_tiles, t0 + per);
     const int my_tiles = max(0, t1 - t0);
@@ -194,7 +201,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {            // TMEM: 2 accumulator stages of BLOCK_N fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(2 * BLOCK_N) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(2 * ACC_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -205,14 +212,15 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            bar_expect_tx(bar_a, (uint32_t)kb_n * A_KB_BYTES);
-            for (int kb = 0; kb < kb_n; ++kb) tma_load_2d(s32(sA + (size_t)kb * A_KB_BYTES), &tmA, kb * 64, m0, bar_a);
+            bar_expect_tx(bar_a, (uint32_t)(MSUB * kb_n) * A_KB_BYTES);
+            for (int h = 0; h < MSUB; ++h)
+                for (int kb = 0; kb < kb_n; ++kb) tma_load_2d(s32(sA + (size_t)(h * kb_n + kb) * A_KB_BYTES), &tmA, kb * 64, m0 + h * 128, bar_a);
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % nstage;
                 const uint32_t ph = (uint32_t)(it / nstage) & 1u;
                 bar_wait(bar_empty + 8u * s, ph ^ 1u);
                 bar_expect_tx(bar_full + 8u * s, (uint32_t)kb_n * B_KB_BYTES);
-                const int n0 = (t0 + it) * BLOCK_N;
+                const int n0 = (t0 + it) * p.tile_stride * BLOCK_N;
                 for (int kb = 0; kb < kb_n; ++kb)
                     tma_load_2d(s32(sB + ((size_t)s * kb_n + kb) * B_KB_BYTES), &tmB, kb * 64, n0, bar_full + 8u * s);
             }
@@ -228,13 +236,16 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 bar_wait(bar_tempty + 8u * as, aph ^ 1u);           // epilogue has drained this accumulator stage
                 bar_wait(bar_full + 8u * s, ph);                    // B tile has landed
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(as * BLOCK_N);
-                for (int kb = 0; kb < kb_n; ++kb) {
-                    const uint64_t ad = smem_desc_sw128(s32(sA + (size_t)kb * A_KB_BYTES));
-                    const uint64_t bd = smem_desc_sw128(s32(sB + ((size_t)s * kb_n + kb) * B_KB_BYTES));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)                     // 4 x (K=16) per 64-wide k-block: +32 B per step
-                        tc_mma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int h = 0; h < MSUB; ++h) {                    // the same B tile against each 128-row user sub-tile
+                    const uint32_t d = tmem_base + (uint32_t)(as * ACC_COLS + h * BLOCK_N);
+                    for (int kb = 0; kb < kb_n; ++kb) {
+                        const uint64_t ad = smem_desc_sw128(s32(sA + (size_t)(h * kb_n + kb) * A_KB_BYTES));
+                        const uint64_t bd = smem_desc_sw128(s32(sB + ((size_t)s * kb_n + kb) * B_KB_BYTES));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)                 // 4 x (K=16) per 64-wide k-block: +32 B per step
+                            tc_mma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                 }
                 tc_commit(bar_empty + 8u * s);                      // smem stage reusable once these MMAs retire
                 tc_commit(bar_tfull + 8u * as);                     // accumulator ready for the epilogue
@@ -248,22 +259,25 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t aph = (uint32_t)(it >> 1) & 1u;
                 bar_wait(bar_tempty + 8u * as, aph ^ 1u);           // the epilogue is done with this slot
                 bar_expect_tx(bar_bias + 8u * as, BLOCK_N * 4u);
-                bulk_load_1d(s32(sBias + as * BLOCK_N), p.bias + (size_t)(t0 + it) * BLOCK_N, BLOCK_N * 4u, bar_bias + 8u * as);
+                bulk_load_1d(s32(sBias + as * BLOCK_N), p.bias + (size_t)(t0 + it) * p.tile_stride * BLOCK_N, BLOCK_N * 4u, bar_bias + 8u * as);
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread <-> user row (TMEM lane); two warps per lane quarter split the tile's columns =====
+        // ===== epilogue: thread <-> user row (TMEM lane).  Two warps share each TMEM lane quarter: with one user sub-tile
+        // they split the tile's columns, with two sub-tiles each takes all columns of one sub-tile =====
         const int wq = warp & 3;                                    // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;                           // which half of the tile's columns
-        constexpr int HALF_N = BLOCK_N / 2;
-        const int r = wq * 32 + lane;
-        const int row = m0 + r;
+        const int part = (warp - 4) >> 2;
+        constexpr int COLS = MSUB == 1 ? BLOCK_N / 2 : BLOCK_N;     // tile columns this warp reads
+        const int col0 = MSUB == 1 ? part * COLS : 0;               // ... starting at this tile column
+        const int tcol0 = MSUB == 1 ? col0 : part * BLOCK_N;        // ... found at this column of the accumulator stage
+        const int row = m0 + (MSUB == 1 ? 0 : part * 128) + wq * 32 + lane;
         const bool row_ok = row < p.n_users;
         const float tau = MODE == MODE_FILTER ? p.tau[row] : 0.f;
         int cnt = 0;
         const int cap = p.cap;
-        const int slot = blockIdx.y * 2 + half;
-        float2* my = MODE == MODE_FILTER ? p.cand + ((size_t)row * (2 * p.n_splits) + slot) * cap : nullptr;
+        const int n_slots = MSUB == 1 ? 2 * p.n_splits : p.n_splits;
+        const int slot = MSUB == 1 ? blockIdx.y * 2 + part : blockIdx.y;
+        float2* my = MODE == MODE_FILTER ? p.cand + ((size_t)row * n_slots + slot) * cap : nullptr;
         float* rmax = MODE == MODE_ROWMAX ? p.rowmax + (size_t)row * (p.n_tiles * (BLOCK_N / 64)) : nullptr;
 
         for (int it = 0; it < my_tiles; ++it) {
@@ -272,12 +286,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             bar_wait(bar_bias + 8u * as, aph);
             bar_wait(bar_tfull + 8u * as, aph);
             tc_fence_after();
-            const int n0 = (t0 + it) * BLOCK_N + half * HALF_N;
-            const float4* bias4 = reinterpret_cast<const float4*>(sBias + as * BLOCK_N + half * HALF_N);
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BLOCK_N + half * HALF_N);
+            const int n0 = (t0 + it) * p.tile_stride * BLOCK_N + col0;
+            const float4* bias4 = reinterpret_cast<const float4*>(sBias + as * BLOCK_N + col0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * ACC_COLS + tcol0);
             float blockmax = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < HALF_N / 32; ++c) {
+            for (int c = 0; c < COLS / 32; ++c) {
                 float v[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -295,7 +309,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int k = 1; k < 32; ++k) mx = fmaxf(mx, v[k]);
                     if (MODE == MODE_ROWMAX) {
                         blockmax = (c & 1) ? fmaxf(blockmax, mx) : mx;
-                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + half * (HALF_N / 64) + (c >> 1)] = blockmax;
+                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + col0 / 64 + (c >> 1)] = blockmax;
                     } else if (row_ok && mx >= tau) {
 #pragma unroll
                         for (int k = 0; k < 32; ++k)
@@ -307,12 +321,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) bar_arrive(bar_tempty + 8u * as);
         }
-        if (MODE == MODE_FILTER) p.cand_cnt[(size_t)row * (2 * p.n_splits) + slot] = row_ok ? min(cnt, cap + 1) : 0;
+        if (MODE == MODE_FILTER) p.cand_cnt[(size_t)row * n_slots + slot] = row_ok ? min(cnt, cap + 1) : 0;
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BLOCK_N) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -322,13 +336,14 @@ template <int G, int QPL, bool FEAT>
 __global__ void __launch_bounds__(256) rescore_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, const float2* __restrict__ cand,
                                                       const int* __restrict__ cand_cnt, int slots, int cap, const int64_t* __restrict__ indptr,
                                                       const int32_t* __restrict__ indices, int filter_previous, float* __restrict__ S2,
-                                                      int32_t* __restrict__ idxmap)
+                                                      int32_t* __restrict__ idxmap, const float* __restrict__ tau2)
 {
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, sub = lane % G, gw = lane / G;
     const int b = blockIdx.y;
     const int u = __ldg(users + b);
     const bool known = u >= 0;
+    const float keep_from = tau2 ? __ldg(tau2 + b) : -INFINITY;        // candidates below the row's n'-th best bf16 score are not re-scored
     UserCtx<QPL> uc;
     load_user<G, QPL, FEAT>(T, known ? u : 0, known, sub, uc);
     user_precompute<G, QPL, FEAT>(T, T.GP, known, sub, uc);
@@ -346,12 +361,14 @@ __global__ void __launch_bounds__(256) rescore_kernel(const Tables T, const int3
     for (long long e = group_global; e < span; e += stride) {
         const bool inb = e < total;
         int item = 0;
+        float approx = 0.f;
         if (inb) {
             int rem = (int)e, sl = 0;
             for (; sl < slots; ++sl) { const int c = min(__ldg(cand_cnt + (size_t)b * slots + sl), cap); if (rem < c) break; rem -= c; }
-            item = __float_as_int(cand[((size_t)b * slots + sl) * cap + rem].y);
+            const float2 ce = cand[((size_t)b * slots + sl) * cap + rem];
+            approx = ce.x; item = __float_as_int(ce.y);
         }
-        const bool ok = inb && item >= 0 && item < T.I;
+        const bool ok = inb && item >= 0 && item < T.I && approx >= keep_from;
         ItemRow<QPL> it;
         load_item<G, QPL, FEAT>(T, ok ? item : 0, ok, sub, it);
         const float s = utility<G, QPL, FEAT>(uc, it);
@@ -365,29 +382,29 @@ __global__ void __launch_bounds__(256) rescore_kernel(const Tables T, const int3
 
 template <int G, int QPL>
 static cudaError_t rescore_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
-                              const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, cudaStream_t st)
+                              const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, const float* tau2, cudaStream_t st)
 {
     const dim3 grid(2, n_users);
     cudaMemsetAsync(S2, 0xff, (size_t)n_users * slots * cap * 4, st);           // 0xffffffff = "removed" marker of topn_select_kernel
-    if (T.x_uf_any || T.x_if_any) rescore_kernel<G, QPL, true><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap);
-    else rescore_kernel<G, QPL, false><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap);
+    if (T.x_uf_any || T.x_if_any) rescore_kernel<G, QPL, true><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2);
+    else rescore_kernel<G, QPL, false><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2);
     return cudaGetLastError();
 }
 
 cudaError_t launch_rescore(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
-                           const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, cudaStream_t st)
+                           const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, const float* tau2, cudaStream_t st)
 {
     int qpl = 1;
     const int G = train_group_size(T, &qpl);
     if (max(T.Pp, T.Qp) > 4 * G || qpl > 4) return cudaErrorInvalidValue;
     switch (G) {
-        case 4:  return rescore_gq<4, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
-        case 8:  return rescore_gq<8, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
-        case 16: return rescore_gq<16, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+        case 4:  return rescore_gq<4, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
+        case 8:  return rescore_gq<8, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
+        case 16: return rescore_gq<16, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
         default:
-            if (qpl == 1) return rescore_gq<32, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
-            if (qpl == 2) return rescore_gq<32, 2>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
-            return rescore_gq<32, 4>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, st);
+            if (qpl == 1) return rescore_gq<32, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
+            if (qpl == 2) return rescore_gq<32, 2>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
+            return rescore_gq<32, 4>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
     }
 }
 
@@ -425,7 +442,16 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int Kp,
 bool gemm_encode_available() { return encode_tiled_fn() != nullptr; }
 int gemm_kraw(const Tables& T) { return T.x_if_any ? 2 * T.Fp : T.Fp; }
 int gemm_kp(const Tables& T) { return (gemm_kraw(T) + 63) / 64 * 64; }
-int gemm_block_n(const Tables& T) { return gemm_kp(T) <= 128 ? 256 : 128; }
+// user sub-tiles per CTA: 2 whenever A (2 x 128 rows) and >= 2 B stages fit shared memory (RANKFM_B200_GEMM_MSUB=1 forces 1)
+int gemm_msub(const Tables& T)
+{
+    const char* e = getenv("RANKFM_B200_GEMM_MSUB");
+    if (e && atoi(e) == 1) return 1;
+    return gemm_kp(T) <= 128 ? 2 : 1;
+}
+int gemm_block_n(const Tables& T) { return gemm_msub(T) == 2 ? 128 : (gemm_kp(T) <= 128 ? 256 : 128); }
+int gemm_m_tile(const Tables& T) { return 128 * gemm_msub(T); }
+int gemm_slots_per_split(const Tables& T) { return gemm_msub(T) == 2 ? 1 : 2; }
 bool gemm_supported(const Tables& T) { return gemm_kp(T) <= 256; }
 
 cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st)
@@ -478,40 +504,97 @@ cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, 
     return cudaGetLastError();
 }
 
-template <int BN, int MODE>
-static cudaError_t launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st)
+// want[row]-th largest bf16-GEMM score among the row's candidates -> tau2[row] (-inf when the row has fewer candidates or
+// an overflowed slot).  Pass 2 over-collects when the pass-1 threshold came from a subset of the item tiles; only the
+// n' best by candidate score need the exact fp32 re-score (the same guarantee a full pass 1 gives).
+__global__ void __launch_bounds__(256) cand_threshold_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_cnt, int slots, int cap,
+                                                             const int* __restrict__ n_target, float* __restrict__ tau2)
 {
-    cudaError_t e = cudaFuncSetAttribute(score_filter_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    score_filter_kernel<BN, MODE><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    __shared__ int s_total, s_over;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float2* c = cand + (size_t)row * slots * cap;
+    const int* cc = cand_cnt + (size_t)row * slots;
+    const int want = n_target[row];
+    if (tid == 0) {
+        int total = 0, over = 0;
+        for (int sl = 0; sl < slots; ++sl) { const int k = cc[sl]; over |= k > cap; total += min(k, cap); }
+        s_total = total; s_over = over; s_prefix = 0u; s_remaining = (uint32_t)want;
+    }
+    __syncthreads();
+    if (s_over || want >= s_total) { if (tid == 0) tau2[row] = -INFINITY; return; }
+    const int width = slots * cap;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int e = tid; e < width; e += 256) {
+            const int sl = e / cap, k = e - sl * cap;
+            if (k < cc[sl]) {
+                const uint32_t key = ord_key(c[e].x);
+                if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t remaining = s_remaining, bin = 0u;
+            for (int d = 255; d >= 0; --d) { if (hist[d] >= remaining) { bin = (uint32_t)d; break; } remaining -= hist[d]; }
+            s_prefix = prefix | (bin << shift);
+            s_remaining = remaining;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { const uint32_t kb = s_prefix; tau2[row] = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb); }
+}
+
+cudaError_t launch_cand_threshold(const float2* cand, const int* cand_cnt, int n_rows, int slots, int cap, const int* n_target, float* tau2, cudaStream_t st)
+{
+    cand_threshold_kernel<<<n_rows, 256, 0, st>>>(cand, cand_cnt, slots, cap, n_target, tau2);
     return cudaGetLastError();
 }
 
-// mode 0: dump dense scores into S [M_pad, I_pad]; 1: block maxima into rowmax [M_pad, I_pad/64];
-// 2: candidates with score >= tau[row] into cand/cand_cnt
-cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
-                                float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st)
+template <int BN, int MSUB, int MODE>
+static cudaError_t launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    const int Kp = gemm_kp(T), BN = gemm_block_n(T);
+    cudaError_t e = cudaFuncSetAttribute(score_filter_kernel<BN, MSUB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    score_filter_kernel<BN, MSUB, MODE><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+template <int BN, int MSUB>
+static cudaError_t launch_modes(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    if (mode == MODE_DUMP) return launch_mode<BN, MSUB, MODE_DUMP>(tmA, tmB, p, grid, smem, st);
+    if (mode == MODE_ROWMAX) return launch_mode<BN, MSUB, MODE_ROWMAX>(tmA, tmB, p, grid, smem, st);
+    return launch_mode<BN, MSUB, MODE_FILTER>(tmA, tmB, p, grid, smem, st);
+}
+
+// mode 0: dump dense scores into S [M_pad, I_pad]; 1: maxima of the 64-item blocks of every tile_stride-th item tile into
+// rowmax [M_pad, ceil(n_tiles/tile_stride) * BN/64]; 2: candidates with score >= tau[row] into cand/cand_cnt.
+// M_pad must be a multiple of gemm_m_tile(T), I_pad of gemm_block_n(T).
+cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
+                                int tile_stride, float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st)
+{
+    const int Kp = gemm_kp(T), BN = gemm_block_n(T), MSUB = gemm_msub(T);
     alignas(64) CUtensorMap tmA, tmB;
     if (!make_map(&tmA, A, M_pad, Kp, 128) || !make_map(&tmB, B, I_pad, Kp, BN)) return cudaErrorNotSupported;
+    if (tile_stride < 1 || M_pad % (128 * MSUB) || I_pad % BN) return cudaErrorInvalidValue;
     GemmParams p{};
-    p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = I_pad / BN; p.n_splits = n_splits; p.n_users = n_users;
+    p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = (I_pad / BN + tile_stride - 1) / tile_stride; p.tile_stride = tile_stride;
+    p.n_splits = n_splits; p.n_users = n_users;
     p.cand = cand; p.cand_cnt = cand_cnt; p.tau = tau; p.cap = cap; p.rowmax = rowmax; p.S = S; p.ldS = I_pad;
-    const size_t a_bytes = (size_t)p.kblocks * 128 * 128, stage_bytes = (size_t)p.kblocks * BN * 128;
+    const size_t a_bytes = (size_t)MSUB * p.kblocks * 128 * 128, stage_bytes = (size_t)p.kblocks * BN * 128;
     int nstage = (int)((196 * 1024 - a_bytes) / stage_bytes);
     nstage = nstage > 4 ? 4 : (nstage < 2 ? 2 : nstage);
     p.nstage = nstage;
     const size_t smem = a_bytes + nstage * stage_bytes + 2 * BN * 4 + 8 * (2 * nstage + 7) + 16 + 1024;
-    const dim3 grid(M_pad / 128, n_splits);
-    if (BN == 256) {
-        if (mode == MODE_DUMP) return launch_mode<256, MODE_DUMP>(tmA, tmB, p, grid, smem, st);
-        if (mode == MODE_ROWMAX) return launch_mode<256, MODE_ROWMAX>(tmA, tmB, p, grid, smem, st);
-        return launch_mode<256, MODE_FILTER>(tmA, tmB, p, grid, smem, st);
-    }
-    if (mode == MODE_DUMP) return launch_mode<128, MODE_DUMP>(tmA, tmB, p, grid, smem, st);
-    if (mode == MODE_ROWMAX) return launch_mode<128, MODE_ROWMAX>(tmA, tmB, p, grid, smem, st);
-    return launch_mode<128, MODE_FILTER>(tmA, tmB, p, grid, smem, st);
+    const dim3 grid(M_pad / (128 * MSUB), n_splits);
+    if (MSUB == 2) return launch_modes<128, 2>(mode, tmA, tmB, p, grid, smem, st);
+    if (BN == 256) return launch_modes<256, 1>(mode, tmA, tmB, p, grid, smem, st);
+    return launch_modes<128, 1>(mode, tmA, tmB, p, grid, smem, st);
 }
 
 }  // namespace rfm

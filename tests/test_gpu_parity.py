@@ -415,11 +415,14 @@ def _scoring_session(U, I, F, P, Q, seed):
     return _rankfm.Session(prob, keep), w, ui, x_uf, x_if, U, I
 
 
+@pytest.mark.parametrize("msub", ["2", "1"])
 @pytest.mark.parametrize("F,P,Q,I", [(16, 0, 0, 1000), (128, 0, 0, 1500), (20, 3, 0, 700), (40, 0, 5, 1100), (100, 4, 6, 900)])
-def test_tcgen05_gemm_scores_match_fp32(gpu_lib, F, P, Q, I):
-    """bf16 x bf16 -> fp32 tensor-core scores (TMA + tcgen05.mma + TMEM) against the fp32 oracle utility"""
+def test_tcgen05_gemm_scores_match_fp32(gpu_lib, F, P, Q, I, msub, monkeypatch):
+    """bf16 x bf16 -> fp32 tensor-core scores (TMA + tcgen05.mma + TMEM) against the fp32 oracle utility; with one and
+    with two 128-row user sub-tiles per CTA (the second only applies while K <= 128)"""
+    monkeypatch.setenv("RANKFM_B200_GEMM_MSUB", msub)
     sess, w, ui, x_uf, x_if, U, I = _scoring_session(300, I, F, P, Q, seed=F)
-    users = np.array([0, 1, 5, U - 1, 17, 200, 131], np.float32)
+    users = np.array([0, 1, 5, U - 1, 17, 200, 131, 128, 255, 256, 299], np.float32)
     S = sess.debug_gemm(users)
     sess.close()
     assert S.shape == (len(users), I)
@@ -431,10 +434,14 @@ def test_tcgen05_gemm_scores_match_fp32(gpu_lib, F, P, Q, I):
         assert np.corrcoef(S[r], ref)[0, 1] > 0.9995
 
 
+@pytest.mark.parametrize("msub,stride", [("2", "4"), ("2", "1"), ("1", "4"), ("1", "1"), ("2", "8")])
 @pytest.mark.parametrize("F,P,Q", [(32, 0, 0), (20, 2, 3)])
 @pytest.mark.parametrize("filt", [False, True])
-def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, monkeypatch):
-    sess, w, ui, x_uf, x_if, U, I = _scoring_session(600, 40000, F, P, Q, seed=7 + F)
+def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, msub, stride, monkeypatch):
+    """tcgen05 candidate GEMM (user sub-tiles per CTA x pass-1 tile stride) + exact re-score against the exact fp32 path"""
+    monkeypatch.setenv("RANKFM_B200_GEMM_MSUB", msub)
+    monkeypatch.setenv("RANKFM_B200_TAU_STRIDE", stride)
+    sess, w, ui, x_uf, x_if, U, I = _scoring_session(600, 60000, F, P, Q, seed=7 + F)
     rng = np.random.default_rng(0)
     users = rng.integers(0, U, 300).astype(np.float32)
     users[5] = np.nan
@@ -442,7 +449,9 @@ def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, m
     exact = sess.recommend(users, 20, filt)
     monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
     fast = sess.recommend(users, 20, filt)
+    tc_rows, tc_redone = sess.recommend_stats()
     sess.close()
+    assert tc_rows > 0 and tc_redone <= tc_rows // 20, (tc_rows, tc_redone)      # the tensor-core path did serve the rows
     assert np.array_equal(np.isnan(fast), np.isnan(exact))
     assert topk_overlap(fast, exact) >= 0.99                      # north_star: top-k set overlap >= 0.99
     assert np.mean(fast[~np.isnan(exact)] == exact[~np.isnan(exact)]) >= 0.97
