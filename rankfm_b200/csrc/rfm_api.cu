@@ -169,7 +169,8 @@ struct rfm_session {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int32_t* d_trace = nullptr;
     // tensor-core recommend: bf16 item operand + bias, rebuilt lazily whenever the weights change
-    void* d_gemm_B = nullptr; float* d_gemm_bias = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
+    // (items in descending bias order: d_gemm_order maps a position of B / bias back to the item index)
+    void* d_gemm_B = nullptr; float* d_gemm_bias = nullptr; int32_t* d_gemm_order = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
     void* scratch[12] = {nullptr}; size_t scratch_bytes[12] = {0};   // grow-only device scratch of the recommend paths
     int64_t tc_rows = 0, tc_redo = 0;   // tensor-core recommend: rows served / rows redone on the exact path (candidate overflow)
     std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
@@ -247,7 +248,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
     cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc); cudaFree(s->d_item_touch); cudaFree(s->d_xuf); cudaFree(s->d_xif);
     cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
-    cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
+    cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias); cudaFree(s->d_gemm_order);
     for (void* q : s->scratch) cudaFree(q);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
@@ -834,15 +835,16 @@ static int ensure_gemm_items(rfm_session* s)
     const int I_pad = (T.I + BN - 1) / BN * BN;
     if (s->gemm_valid && s->gemm_I_pad == I_pad) return RFM_OK;
     if (!s->d_gemm_B || s->gemm_I_pad != I_pad) {
-        cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias);
-        s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr;
+        cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias); cudaFree(s->d_gemm_order);
+        s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr; s->d_gemm_order = nullptr;
         CU(cudaMalloc(&s->d_gemm_B, (size_t)I_pad * Kp * 2));
         int rc = dev_alloc(&s->d_gemm_bias, (size_t)I_pad);
         if (rc) return rc;
+        if ((rc = dev_alloc(&s->d_gemm_order, (size_t)I_pad))) return rc;
         s->gemm_I_pad = I_pad;
     }
-    CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->d_gemm_bias, s->st));
-    s->launches += 1;
+    CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->d_gemm_bias, s->d_gemm_order, s->st));
+    s->launches += 3;
     s->gemm_valid = true;
     return RFM_OK;
 }
@@ -877,8 +879,8 @@ static int tau_blocks(const Tables& T, int stride)
     return (n_tiles + stride - 1) / stride * (BN / 64);
 }
 
-// tensor-core path (rfm_gemm.cu): pass 1 block maxima -> per-row threshold -> pass 2 candidates -> n' best candidates by
-// bf16 score -> exact re-score -> top-n
+// tensor-core path (rfm_gemm.cu): pass 1 block bounds -> per-row threshold -> pass 2 candidates -> shortlist (n' best by
+// bf16 score, exact fp32 re-score) -> top-n
 static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
                         float* d_rec, float* gemm_ms)
 {
@@ -896,7 +898,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
     const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
-    float *d_rowmax = nullptr, *d_tau = nullptr, *d_tau2 = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr;
+    float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr; int* d_flag = nullptr;
     auto done = [&](int code) { cudaFree(d_fix); cudaFree(d_fix_users); return code; };
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
     if ((rc = scratch_get(s, 2, (size_t)rows_alloc, &d_ntgt))) return rc;
@@ -904,10 +906,10 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub1, &d_rowmax))) return rc;
     if ((rc = scratch_get(s, 5, (size_t)rows_alloc * width, &d_cand))) return rc;
     if ((rc = scratch_get(s, 6, (size_t)rows_alloc * split_cap * SPS, &d_cnt))) return rc;
-    if ((rc = scratch_get(s, 7, (size_t)rows_alloc * width, &d_S2))) return rc;
-    if ((rc = scratch_get(s, 8, (size_t)rows_alloc * width, &d_map))) return rc;
-    if ((rc = scratch_get(s, 9, (size_t)rows_alloc, &d_tau2))) return rc;
-    std::vector<int> ntgt((size_t)rows_alloc), cnt_h;
+    if ((rc = scratch_get(s, 7, (size_t)rows_alloc * kShortWidth, &d_S2))) return rc;
+    if ((rc = scratch_get(s, 8, (size_t)rows_alloc * kShortWidth, &d_map))) return rc;
+    if ((rc = scratch_get(s, 9, (size_t)rows_alloc, &d_flag))) return rc;
+    std::vector<int> ntgt((size_t)rows_alloc), flag_h;
     cudaEvent_t a = nullptr, b = nullptr;
     if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
     for (int64_t off = 0; off < n_users; off += rows_alloc) {
@@ -924,22 +926,21 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         CU(launch_row_threshold(d_rowmax, M_pad, n_sub1, d_ntgt, d_tau, s->st));
         e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, d_cand, d_cnt, d_tau, cap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
-        if (stride > 1) { CU(launch_cand_threshold(d_cand, d_cnt, nb, slots, cap, d_ntgt, d_tau2, s->st)); s->launches += 1; }
         if (gemm_ms) CU(cudaEventRecord(b, s->st));
-        e = launch_rescore(T, d_users + off, nb, d_cand, d_cnt, slots, cap, s->d_indptr, s->d_indices, filter_previous, d_S2, d_map, stride > 1 ? d_tau2 : nullptr, s->st);
-        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "rescore launch failed: %s", cudaGetErrorString(e)));
-        e = launch_topn_select(d_S2, slots * cap, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
+        e = launch_shortlist(T, d_users + off, nb, d_cand, d_cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, d_ntgt, s->d_indptr, s->d_indices, filter_previous,
+                             d_S2, d_map, d_flag, s->st);
+        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e)));
+        e = launch_topn_select(d_S2, kShortWidth, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "topn_select launch failed: %s", cudaGetErrorString(e)));
         s->launches += 6;
-        // rows whose candidate buffer overflowed (pathological ties / clustered scores) are redone on the exact path
-        cnt_h.resize((size_t)nb * slots);
-        CU(cudaMemcpyAsync(cnt_h.data(), d_cnt, (size_t)nb * slots * 4, cudaMemcpyDeviceToHost, s->st));
+        // rows whose candidates overflowed (pathological ties / clustered scores) are redone on the exact path
+        flag_h.resize((size_t)nb);
+        CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->st));
         CU(cudaStreamSynchronize(s->st));
         if (gemm_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); *gemm_ms += ms; }
         std::vector<int32_t> redo_users; std::vector<int> redo_rows;
         for (int r = 0; r < nb; ++r)
-            for (int sp = 0; sp < slots; ++sp)
-                if (cnt_h[(size_t)r * slots + sp] > cap) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); break; }
+            if (flag_h[(size_t)r]) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); }
         s->tc_rows += nb; s->tc_redo += (int64_t)redo_users.size();
         if (!redo_users.empty()) {
             cudaFree(d_fix); cudaFree(d_fix_users); d_fix = nullptr; d_fix_users = nullptr;
@@ -1087,8 +1088,14 @@ extern "C" int rfm_session_debug_gemm(rfm_session* s, const float* users, int64_
     CU(launch_pack_gemm_users(T, d_users, (int)n_users, M_pad, Kp, d_A, s->st));
     cudaError_t e = launch_score_filter(T, 0, d_A, s->d_gemm_B, s->d_gemm_bias, (int)n_users, M_pad, I_pad, 1, 1, nullptr, nullptr, nullptr, 0, nullptr, d_S, s->st);
     if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter (tcgen05) launch failed: %s", cudaGetErrorString(e));
-    CU(cudaMemcpy2DAsync(scores_out, (size_t)T.I * 4, d_S, (size_t)I_pad * 4, (size_t)T.I * 4, (size_t)n_users, cudaMemcpyDeviceToHost, s->st));
+    // the kernel's columns are positions of the bias-ordered catalogue: scatter them back to item indexes
+    std::vector<float> tmp((size_t)n_users * I_pad);
+    std::vector<int32_t> order((size_t)T.I);
+    CU(cudaMemcpyAsync(tmp.data(), d_S, (size_t)n_users * I_pad * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(order.data(), s->d_gemm_order, (size_t)T.I * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
+    for (int64_t r = 0; r < n_users; ++r)
+        for (int pos = 0; pos < T.I; ++pos) scores_out[(size_t)r * T.I + order[(size_t)pos]] = tmp[(size_t)r * I_pad + pos];
     return RFM_OK;
 }
 

@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
 #include "rfm_kernels.h"
 #include "rfm_pair.cuh"
 
@@ -36,15 +37,30 @@ namespace rfm {
 // ---------------------------------------------------------------------------------------------------------------
 // operand packing: bf16 A (requested users) / B (all items), fp32 bias
 // ---------------------------------------------------------------------------------------------------------------
-// bf16 operands [rows, Kp] (Kp = factor columns padded to a multiple of 64) and the fp32 item bias
-__global__ void pack_gemm_items_kernel(const Tables T, int Kp, int I_pad, __nv_bfloat16* __restrict__ B, float* __restrict__ bias)
+// The item operand is laid out in DESCENDING BIAS ORDER: position pos of B / bias holds item order[pos].  Inside any run of
+// consecutive positions the largest bias is the first and the smallest the last, which lets the GEMM epilogues work on
+// the raw dot products (one bias per 32- or 64-item run instead of one per score) -- see score_filter_kernel.
+__global__ void item_bias_kernel(const Tables T, float* __restrict__ bias, int32_t* __restrict__ iota)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T.I; i += gridDim.x * blockDim.x) {
+        const float* row = T.IT + (size_t)i * T.ldi;
+        float b = row[T.Fp];
+        if (T.x_if_any) for (int q = 0; q < T.Q; ++q) b += row[T.Fp + 4 + q] * T.GP[q];
+        bias[i] = b;
+        iota[i] = i;
+    }
+}
+
+// bf16 operand [I_pad, Kp] (Kp = factor columns padded to a multiple of 64) in bias order; pads: zero rows, bias -1e30, order -1
+__global__ void pack_gemm_items_kernel(const Tables T, int Kp, int I_pad, const int32_t* __restrict__ order, __nv_bfloat16* __restrict__ B,
+                                       float* __restrict__ bias)
 {
     const long long n = (long long)I_pad * Kp;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(e / Kp), c = (int)(e % Kp);
+        const int pos = (int)(e / Kp), c = (int)(e % Kp);
         float v = 0.f;
-        if (i < T.I) {
-            const float* row = T.IT + (size_t)i * T.ldi;
+        if (pos < T.I) {
+            const float* row = T.IT + (size_t)order[pos] * T.ldi;
             if (c < T.F) v = row[c];
             else if (T.x_if_any && c >= T.Fp && c - T.Fp < T.F) {             // second half: x_if[i] . v_if[:, f]
                 const int f = c - T.Fp;
@@ -53,15 +69,7 @@ __global__ void pack_gemm_items_kernel(const Tables T, int Kp, int I_pad, __nv_b
         }
         B[e] = __float2bfloat16(v);
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I_pad; i += gridDim.x * blockDim.x) {
-        float b = -1e30f;                                                    // padded items never pass any threshold
-        if (i < T.I) {
-            const float* row = T.IT + (size_t)i * T.ldi;
-            b = row[T.Fp];
-            if (T.x_if_any) for (int q = 0; q < T.Q; ++q) b += row[T.Fp + 4 + q] * T.GP[q];
-        }
-        bias[i] = b;
-    }
+    for (int pos = T.I + blockIdx.x * blockDim.x + threadIdx.x; pos < I_pad; pos += gridDim.x * blockDim.x) bias[pos] = -1e30f;
 }
 
 __global__ void pack_gemm_users_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, int M_pad, int Kp, __nv_bfloat16* __restrict__ A)
@@ -112,10 +120,9 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v)
+// 32 consecutive fp32 columns of this thread's TMEM lane: asynchronous issue ...
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
 {
-    uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -124,9 +131,31 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v)
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+// ... and the wait that makes the registers valid.  The registers are in/out operands so that no use of them can be
+// scheduled above the wait (the load of the NEXT 32 columns is issued before this chunk is processed).
+__device__ __forceinline__ void tc_ld32_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+// three-input maximum (SASS FMNMX3): 32 scores fold in 16 instructions instead of 31
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float max8(const uint32_t* r)
+{
+    float m = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+    m = max3(m, __uint_as_float(r[3]), __uint_as_float(r[4]));
+    m = max3(m, __uint_as_float(r[5]), __uint_as_float(r[6]));
+    return fmaxf(m, __uint_as_float(r[7]));
 }
 
 // shared-memory matrix descriptor: K-major tile of 128-byte rows, 128B swizzle, 8-row groups 1024 B apart (sm_100 format)
@@ -143,7 +172,7 @@ __device__ __forceinline__ uint32_t ord_key(float s) { const uint32_t b = __floa
 // the GEMM + running-threshold filter
 // ---------------------------------------------------------------------------------------------------------------
 struct GemmParams {
-    const float* bias;           // [I_pad] fp32 item bias (w_i + x_if.w_if); -1e30 for padded items
+    const float* bias;           // [I_pad] fp32 item bias (w_i + x_if.w_if) in descending order (position order of B); -1e30 for pads
     int kblocks;                 // Kp / 64
     int n_tiles;                 // item tiles this launch visits (pass 1 may visit only every tile_stride-th tile)
     int tile_stride;             // visited tile k is item tile k * tile_stride
@@ -151,12 +180,12 @@ struct GemmParams {
     int n_users;                 // valid rows of A
     int nstage;
     // MODE_FILTER
-    float2* cand;                // [M_pad * n_slots, cap]  (score, item index as int bits); n_slots = n_splits * (MSUB == 1 ? 2 : 1)
+    float2* cand;                // [M_pad * n_slots, cap]  (raw dot product, item POSITION as int bits); n_slots = n_splits * (MSUB == 1 ? 2 : 1)
     int* cand_cnt;               // [M_pad * n_slots]; cap+1 flags an overflowing slot
     const float* tau;            // [M_pad] per-row threshold from pass 1
     int cap;
     // MODE_ROWMAX
-    float* rowmax;               // [M_pad, n_tiles * BLOCK_N/64] maxima of the visited 64-item blocks
+    float* rowmax;               // [M_pad, n_tiles * BLOCK_N/64] lower bounds of the maxima of the visited 64-item blocks
     // MODE_DUMP
     float* S;                    // [M_pad, I_pad]
     long long ldS;
@@ -264,20 +293,30 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread <-> user row (TMEM lane).  Two warps share each TMEM lane quarter: with one user sub-tile
-        // they split the tile's columns, with two sub-tiles each takes all columns of one sub-tile =====
+        // they split the tile's columns, with two sub-tiles each takes all columns of one sub-tile.
+        // The epilogue is the issue-bound part of this kernel (K is only 64..128: 2.3 instructions per score would cost more
+        // issue slots than the MMAs take cycles), so it works on the RAW dot products and touches the bias once per run of
+        // items -- possible because positions are in descending bias order (run maximum = first, minimum = last):
+        //   pass 1  lower bound of a 64-item block's best score = max(dot) + smallest bias of the block  (FMNMX3 tree)
+        //   pass 2  score >= tau can only hold where dot >= tau - largest bias of the 32-item chunk; the four 8-item
+        //           sub-maxima of the tree gate the (rare per row) append of (dot, position)
+        // Both are conservative (candidates form a superset); exact fp32 scores are recomputed from the shortlist. =====
         const int wq = warp & 3;                                    // TMEM lane quarter this warp may access
         const int part = (warp - 4) >> 2;
         constexpr int COLS = MSUB == 1 ? BLOCK_N / 2 : BLOCK_N;     // tile columns this warp reads
+        constexpr int NCH = COLS / 32;
         const int col0 = MSUB == 1 ? part * COLS : 0;               // ... starting at this tile column
         const int tcol0 = MSUB == 1 ? col0 : part * BLOCK_N;        // ... found at this column of the accumulator stage
         const int row = m0 + (MSUB == 1 ? 0 : part * 128) + wq * 32 + lane;
         const bool row_ok = row < p.n_users;
-        const float tau = MODE == MODE_FILTER ? p.tau[row] : 0.f;
-        int cnt = 0;
+        const float tau = MODE == MODE_FILTER ? (row_ok ? p.tau[row] : INFINITY) : 0.f;
         const int cap = p.cap;
         const int n_slots = MSUB == 1 ? 2 * p.n_splits : p.n_splits;
         const int slot = MSUB == 1 ? blockIdx.y * 2 + part : blockIdx.y;
-        float2* my = MODE == MODE_FILTER ? p.cand + ((size_t)row * n_slots + slot) * cap : nullptr;
+        float2* const my = MODE == MODE_FILTER ? p.cand + ((size_t)row * n_slots + slot) * cap : nullptr;
+        float2* wp = my;
+        float2* const wp_room = my + (cap - 8);                     // last write position that still leaves room for 8 entries
+        bool over = false;
         float* rmax = MODE == MODE_ROWMAX ? p.rowmax + (size_t)row * (p.n_tiles * (BLOCK_N / 64)) : nullptr;
 
         for (int it = 0; it < my_tiles; ++it) {
@@ -287,33 +326,46 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             bar_wait(bar_tfull + 8u * as, aph);
             tc_fence_after();
             const int n0 = (t0 + it) * p.tile_stride * BLOCK_N + col0;
-            const float4* bias4 = reinterpret_cast<const float4*>(sBias + as * BLOCK_N + col0);
+            const float* sb = sBias + as * BLOCK_N + col0;
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * ACC_COLS + tcol0);
+            uint32_t ra[32], rb[32];                                // double-buffered: chunk c+1 is in flight while chunk c is processed
             float blockmax = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < COLS / 32; ++c) {
-                float v[32];
-                tc_ld32(taddr + (uint32_t)(c * 32), v);
+            tc_ld32_issue(taddr, ra);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 b = bias4[c * 8 + q];                 // broadcast LDS.128: every row adds the same item biases
-                    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-                }
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t (&v)[32] = (c & 1) ? rb : ra;
+                tc_ld32_wait(v);
+                if (c + 1 < NCH) tc_ld32_issue(taddr + (uint32_t)((c + 1) * 32), (c & 1) ? ra : rb);
                 if (MODE == MODE_DUMP) {
                     float* out = p.S + (size_t)row * p.ldS + n0 + c * 32;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(out)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = reinterpret_cast<const float4*>(sb + c * 32)[q];
+                        reinterpret_cast<float4*>(out)[q] = make_float4(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y,
+                                                                        __uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
+                    }
                 } else {
-                    float mx = v[0];
-#pragma unroll
-                    for (int k = 1; k < 32; ++k) mx = fmaxf(mx, v[k]);
+                    const float m0_ = max8(v), m1_ = max8(v + 8), m2_ = max8(v + 16), m3_ = max8(v + 24);
                     if (MODE == MODE_ROWMAX) {
+                        const float mx = fmaxf(max3(m0_, m1_, m2_), m3_);
                         blockmax = (c & 1) ? fmaxf(blockmax, mx) : mx;
-                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + col0 / 64 + (c >> 1)] = blockmax;
-                    } else if (row_ok && mx >= tau) {
+                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + col0 / 64 + (c >> 1)] = blockmax + sb[c * 32 + 31];
+                    } else {
+                        const float thr = tau - sb[c * 32];
+                        const float msub[4] = {m0_, m1_, m2_, m3_};
 #pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            if (v[k] >= tau) { if (cnt < cap) my[cnt] = make_float2(v[k], __int_as_float(n0 + c * 32 + k)); ++cnt; }
+                        for (int g = 0; g < 4; ++g) {
+                            if (msub[g] >= thr) {                  // rare per row (a warp takes it when any of its 32 rows does)
+                                if (wp > wp_room) over = true;
+                                else {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) {
+                                        const float d = __uint_as_float(v[8 * g + k]);
+                                        if (d >= thr) *wp++ = make_float2(d, __int_as_float(n0 + c * 32 + 8 * g + k));
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -321,7 +373,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) bar_arrive(bar_tempty + 8u * as);
         }
-        if (MODE == MODE_FILTER) p.cand_cnt[(size_t)row * n_slots + slot] = row_ok ? min(cnt, cap + 1) : 0;
+        if (MODE == MODE_FILTER) p.cand_cnt[(size_t)row * n_slots + slot] = !row_ok ? 0 : (over ? cap + 1 : (int)(wp - my));
     }
 
     tc_fence_before();
@@ -330,82 +382,170 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// exact fp32 re-score of the candidates (lane group per (user, candidate)); seen items get the "removed" marker
+// shortlist_kernel: one block per requested user.
+//   1. gather the row's pass-2 candidates (raw dot, position) from its slots into shared memory, bf16-GEMM score =
+//      dot + bias[position]
+//   2. keep the n' best by that score (exact radix select of the n'-th largest + ordered compaction): pass 2
+//      over-collects when the pass-1 threshold came from a subset of the item tiles, and only the n' best need more work
+//   3. exact fp32 utility of the kept items (same lane-group code as predict), seen items get the "removed" marker
+// Output: S2 / idxmap [row, kShortWidth] for topn_select_kernel; flag[row] = 1 when the row must be redone on the exact
+// path (a candidate slot overflowed, or more than kShortWidth candidates tie at the cut).
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kShortThreads = 256;
+
 template <int G, int QPL, bool FEAT>
-__global__ void __launch_bounds__(256) rescore_kernel(const Tables T, const int32_t* __restrict__ users, int n_users, const float2* __restrict__ cand,
-                                                      const int* __restrict__ cand_cnt, int slots, int cap, const int64_t* __restrict__ indptr,
-                                                      const int32_t* __restrict__ indices, int filter_previous, float* __restrict__ S2,
-                                                      int32_t* __restrict__ idxmap, const float* __restrict__ tau2)
+__global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T, const int32_t* __restrict__ users, const float2* __restrict__ cand,
+                                                                  const int* __restrict__ cand_cnt, int slots, int cap, const float* __restrict__ bias,
+                                                                  const int32_t* __restrict__ order, const int* __restrict__ n_target,
+                                                                  const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                                  int filter_previous, float* __restrict__ S2, int32_t* __restrict__ idxmap,
+                                                                  int* __restrict__ flag)
 {
+    extern __shared__ __align__(16) unsigned char short_smem[];
+    uint2* ent = reinterpret_cast<uint2*>(short_smem);               // [slots * cap] (ordered key of the bf16 score, position)
+    __shared__ int32_t kept[kShortWidth];                            // item ids of the shortlist, in position order
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    __shared__ int s_off[65], s_over, s_base, wsum[kShortThreads / 32];
     constexpr int GPW = 32 / G;
-    const int lane = threadIdx.x & 31, sub = lane % G, gw = lane / G;
-    const int b = blockIdx.y;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane % G, gw = lane / G;
     const int u = __ldg(users + b);
     const bool known = u >= 0;
-    const float keep_from = tau2 ? __ldg(tau2 + b) : -INFINITY;        // candidates below the row's n'-th best bf16 score are not re-scored
-    UserCtx<QPL> uc;
-    load_user<G, QPL, FEAT>(T, known ? u : 0, known, sub, uc);
-    user_precompute<G, QPL, FEAT>(T, T.GP, known, sub, uc);
-    const int width = slots * cap;                                      // row length of S2 / idxmap
-    const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
-    const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
-    long long seg = 0; int deg = 0;
-    if (known && filter_previous) { seg = __ldg(indptr + u); deg = (int)(__ldg(indptr + u + 1) - seg); }
-    // dense enumeration of the row's candidates: entry e of the concatenation of the slots' filled prefixes; output is
-    // written densely too (positions >= total are pre-filled with the "removed" marker by the memset in the launcher)
-    int total = 0;
-    for (int sl = 0; sl < slots; ++sl) total += min(__ldg(cand_cnt + (size_t)b * slots + sl), cap);
-    if (!known) total = 0;
-    const long long span = ((long long)total + stride - 1) / stride * stride;
-    for (long long e = group_global; e < span; e += stride) {
-        const bool inb = e < total;
-        int item = 0;
-        float approx = 0.f;
-        if (inb) {
-            int rem = (int)e, sl = 0;
-            for (; sl < slots; ++sl) { const int c = min(__ldg(cand_cnt + (size_t)b * slots + sl), cap); if (rem < c) break; rem -= c; }
-            const float2 ce = cand[((size_t)b * slots + sl) * cap + rem];
-            approx = ce.x; item = __float_as_int(ce.y);
-        }
-        const bool ok = inb && item >= 0 && item < T.I && approx >= keep_from;
-        ItemRow<QPL> it;
-        load_item<G, QPL, FEAT>(T, ok ? item : 0, ok, sub, it);
-        const float s = utility<G, QPL, FEAT>(uc, it);
-        const bool seen = filter_previous ? group_member<G>(item, indices + seg, deg, ok, sub, gw) : false;
-        if (inb && sub == 0) {
-            S2[(size_t)b * width + e] = (ok && !seen) ? s : __uint_as_float(0xffffffffu);
-            idxmap[(size_t)b * width + e] = item;
+    float* out = S2 + (size_t)b * kShortWidth;
+    int32_t* omap = idxmap + (size_t)b * kShortWidth;
+    const int* cc = cand_cnt + (size_t)b * slots;
+    if (tid == 0) {
+        int total = 0, over = 0;
+        for (int sl = 0; sl < slots; ++sl) { const int k = cc[sl]; s_off[sl] = total; over |= k > cap; total += min(k, cap); }
+        s_off[slots] = total; s_over = over; s_prefix = 0u; s_base = 0;
+        s_remaining = (uint32_t)n_target[b];
+    }
+    __syncthreads();
+    const int total = s_off[slots], want = n_target[b];
+    if (!known || s_over) {                                           // unknown user: NaN row from topn_select; overflow: redone by the caller
+        for (int e = tid; e < kShortWidth; e += kShortThreads) { out[e] = __uint_as_float(0xffffffffu); omap[e] = 0; }
+        if (tid == 0) flag[b] = known ? 1 : 0;
+        return;
+    }
+    // 1. gather
+    for (int sl = 0; sl < slots; ++sl) {
+        const int n = s_off[sl + 1] - s_off[sl];
+        const float2* src = cand + ((size_t)b * slots + sl) * cap;
+        for (int k = tid; k < n; k += kShortThreads) {
+            const float2 ce = src[k];
+            const int pos = __float_as_int(ce.y);
+            const bool ok = pos >= 0 && pos < T.I;                    // positions of padded items carry no item
+            ent[s_off[sl] + k] = make_uint2(ok ? max(ord_key(ce.x + __ldg(bias + (ok ? pos : 0))), 1u) : 0u, (uint32_t)pos);
         }
     }
+    __syncthreads();
+    // 2. the n'-th largest key (0 = keep every real entry)
+    uint32_t cut = 1u;
+    if (want < total) {
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[tid] = 0u;
+            __syncthreads();
+            const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            for (int e = tid; e < total; e += kShortThreads) {
+                const uint32_t key = ent[e].x;
+                if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t remaining = s_remaining, bin = 0u;
+                for (int d = 255; d >= 0; --d) { if (hist[d] >= remaining) { bin = (uint32_t)d; break; } remaining -= hist[d]; }
+                s_prefix = prefix | (bin << shift);
+                s_remaining = remaining;
+            }
+            __syncthreads();
+        }
+        cut = max(s_prefix, 1u);
+    }
+    //    ordered compaction (position order keeps the result independent of thread scheduling)
+    for (int base = 0; base < total; base += kShortThreads) {
+        const int e = base + tid;
+        const bool keep = e < total && ent[e].x >= cut;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_base, all = 0;
+        for (int w = 0; w < kShortThreads / 32; ++w) { if (w < warp) before += wsum[w]; all += wsum[w]; }
+        const int mine = before + __popc(bal & ((1u << lane) - 1u));
+        if (keep && mine < kShortWidth) kept[mine] = __ldg(order + ent[e].y);
+        __syncthreads();
+        if (tid == 0) s_base += all;
+        __syncthreads();
+    }
+    const int n_kept = s_base;
+    if (n_kept > kShortWidth) {                                        // > kShortWidth - n' ties at the cut: exact path
+        for (int e = tid; e < kShortWidth; e += kShortThreads) { out[e] = __uint_as_float(0xffffffffu); omap[e] = 0; }
+        if (tid == 0) flag[b] = 1;
+        return;
+    }
+    if (tid == 0) flag[b] = 0;
+    // 3. exact fp32 re-score
+    UserCtx<QPL> uc;
+    load_user<G, QPL, FEAT>(T, u, true, sub, uc);
+    user_precompute<G, QPL, FEAT>(T, T.GP, true, sub, uc);
+    long long seg = 0; int deg = 0;
+    if (filter_previous) { seg = __ldg(indptr + u); deg = (int)(__ldg(indptr + u + 1) - seg); }
+    constexpr int STRIDE = (kShortThreads / 32) * GPW;
+    for (int e0 = 0; e0 < n_kept; e0 += 2 * STRIDE) {                 // warp-uniform trip count; two gathers in flight per group
+        const int ea = e0 + warp * GPW + gw, eb = ea + STRIDE;
+        const bool oka = ea < n_kept, okb = eb < n_kept;
+        const int ia = oka ? kept[ea] : 0, ib = okb ? kept[eb] : 0;
+        ItemRow<QPL> ra, rb;
+        load_item<G, QPL, FEAT>(T, ia, oka, sub, ra);
+        load_item<G, QPL, FEAT>(T, ib, okb, sub, rb);
+        const float sa = utility<G, QPL, FEAT>(uc, ra), sb = utility<G, QPL, FEAT>(uc, rb);
+        const bool seen_a = filter_previous ? group_member<G>(ia, indices + seg, deg, oka, sub, gw) : false;
+        const bool seen_b = filter_previous ? group_member<G>(ib, indices + seg, deg, okb, sub, gw) : false;
+        if (sub == 0) {
+            if (oka) { out[ea] = seen_a ? __uint_as_float(0xffffffffu) : sa; omap[ea] = ia; }
+            if (okb) { out[eb] = seen_b ? __uint_as_float(0xffffffffu) : sb; omap[eb] = ib; }
+        }
+    }
+    for (int e = n_kept + tid; e < kShortWidth; e += kShortThreads) { out[e] = __uint_as_float(0xffffffffu); omap[e] = 0; }
 }
 
 template <int G, int QPL>
-static cudaError_t rescore_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
-                              const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, const float* tau2, cudaStream_t st)
+static cudaError_t shortlist_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
+                                const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, float* S2,
+                                int32_t* idxmap, int* flag, cudaStream_t st)
 {
-    const dim3 grid(2, n_users);
-    cudaMemsetAsync(S2, 0xff, (size_t)n_users * slots * cap * 4, st);           // 0xffffffff = "removed" marker of topn_select_kernel
-    if (T.x_uf_any || T.x_if_any) rescore_kernel<G, QPL, true><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2);
-    else rescore_kernel<G, QPL, false><<<grid, 256, 0, st>>>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2);
+    const size_t smem = (size_t)slots * cap * sizeof(uint2);
+    cudaError_t e;
+    if (T.x_uf_any || T.x_if_any) {
+        e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        shortlist_kernel<G, QPL, true><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, S2, idxmap, flag);
+    } else {
+        e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        shortlist_kernel<G, QPL, false><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, S2, idxmap, flag);
+    }
     return cudaGetLastError();
 }
 
-cudaError_t launch_rescore(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
-                           const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, const float* tau2, cudaStream_t st)
+cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
+                             const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, float* S2,
+                             int32_t* idxmap, int* flag, cudaStream_t st)
 {
     int qpl = 1;
     const int G = train_group_size(T, &qpl);
-    if (max(T.Pp, T.Qp) > 4 * G || qpl > 4) return cudaErrorInvalidValue;
+    if (max(T.Pp, T.Qp) > 4 * G || qpl > 4 || slots > 64 || (size_t)slots * cap * sizeof(uint2) > 160 * 1024) return cudaErrorInvalidValue;
+#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, S2, idxmap, flag, st)
     switch (G) {
-        case 4:  return rescore_gq<4, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
-        case 8:  return rescore_gq<8, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
-        case 16: return rescore_gq<16, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
+        case 4:  RFM_SHORT(4, 1);
+        case 8:  RFM_SHORT(8, 1);
+        case 16: RFM_SHORT(16, 1);
         default:
-            if (qpl == 1) return rescore_gq<32, 1>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
-            if (qpl == 2) return rescore_gq<32, 2>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
-            return rescore_gq<32, 4>(T, users, n_users, cand, cnt, slots, cap, indptr, indices, filt, S2, idxmap, tau2, st);
+            if (qpl == 1) RFM_SHORT(32, 1);
+            if (qpl == 2) RFM_SHORT(32, 2);
+            RFM_SHORT(32, 4);
     }
+#undef RFM_SHORT
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -454,10 +594,26 @@ int gemm_m_tile(const Tables& T) { return 128 * gemm_msub(T); }
 int gemm_slots_per_split(const Tables& T) { return gemm_msub(T) == 2 ? 1 : 2; }
 bool gemm_supported(const Tables& T) { return gemm_kp(T) <= 256; }
 
-cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st)
+// bias[I_pad] (sorted, descending), order[I_pad] (position -> item), B[I_pad, Kp]; once per weight state
+cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, int32_t* order, cudaStream_t st)
 {
-    pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, Kp, I_pad, reinterpret_cast<__nv_bfloat16*>(B), bias);
-    return cudaGetLastError();
+    float* raw = nullptr; int32_t* iota = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+    cudaError_t e = cudaMalloc(&raw, (size_t)T.I * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&iota, (size_t)T.I * 4);
+    if (e == cudaSuccess) {
+        item_bias_kernel<<<148 * 4, 256, 0, st>>>(T, raw, iota);
+        e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, raw, bias, iota, order, T.I, 0, 32, st);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, raw, bias, iota, order, T.I, 0, 32, st);   // stable: ties stay in item order
+    if (e == cudaSuccess) e = cudaMemsetAsync(order + T.I, 0xff, (size_t)(I_pad - T.I) * 4, st);
+    if (e == cudaSuccess) {
+        pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, Kp, I_pad, order, reinterpret_cast<__nv_bfloat16*>(B), bias);
+        e = cudaGetLastError();
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(raw); cudaFree(iota); cudaFree(tmp);
+    return e;
 }
 cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st)
 {
@@ -501,57 +657,6 @@ __global__ void __launch_bounds__(256) row_threshold_kernel(const float* __restr
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st)
 {
     row_threshold_kernel<<<n_rows, 256, 0, st>>>(rowmax, n_blocks, n_target, tau);
-    return cudaGetLastError();
-}
-
-// want[row]-th largest bf16-GEMM score among the row's candidates -> tau2[row] (-inf when the row has fewer candidates or
-// an overflowed slot).  Pass 2 over-collects when the pass-1 threshold came from a subset of the item tiles; only the
-// n' best by candidate score need the exact fp32 re-score (the same guarantee a full pass 1 gives).
-__global__ void __launch_bounds__(256) cand_threshold_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_cnt, int slots, int cap,
-                                                             const int* __restrict__ n_target, float* __restrict__ tau2)
-{
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix, s_remaining;
-    __shared__ int s_total, s_over;
-    const int row = blockIdx.x, tid = threadIdx.x;
-    const float2* c = cand + (size_t)row * slots * cap;
-    const int* cc = cand_cnt + (size_t)row * slots;
-    const int want = n_target[row];
-    if (tid == 0) {
-        int total = 0, over = 0;
-        for (int sl = 0; sl < slots; ++sl) { const int k = cc[sl]; over |= k > cap; total += min(k, cap); }
-        s_total = total; s_over = over; s_prefix = 0u; s_remaining = (uint32_t)want;
-    }
-    __syncthreads();
-    if (s_over || want >= s_total) { if (tid == 0) tau2[row] = -INFINITY; return; }
-    const int width = slots * cap;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        hist[tid] = 0u;
-        __syncthreads();
-        const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int e = tid; e < width; e += 256) {
-            const int sl = e / cap, k = e - sl * cap;
-            if (k < cc[sl]) {
-                const uint32_t key = ord_key(c[e].x);
-                if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t remaining = s_remaining, bin = 0u;
-            for (int d = 255; d >= 0; --d) { if (hist[d] >= remaining) { bin = (uint32_t)d; break; } remaining -= hist[d]; }
-            s_prefix = prefix | (bin << shift);
-            s_remaining = remaining;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) { const uint32_t kb = s_prefix; tau2[row] = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb); }
-}
-
-cudaError_t launch_cand_threshold(const float2* cand, const int* cand_cnt, int n_rows, int slots, int cap, const int* n_target, float* tau2, cudaStream_t st)
-{
-    cand_threshold_kernel<<<n_rows, 256, 0, st>>>(cand, cand_cnt, slots, cap, n_target, tau2);
     return cudaGetLastError();
 }
 

@@ -66,14 +66,15 @@ int gemm_block_n(const Tables& T);
 int gemm_m_tile(const Tables& T);             // user rows per CTA (128 x sub-tiles); M_pad must be a multiple
 int gemm_slots_per_split(const Tables& T);    // candidate slots per (row, item split)
 bool gemm_supported(const Tables& T);
-cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, cudaStream_t st);
+cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, int32_t* order, cudaStream_t st);
 cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st);
 cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
                                 int tile_stride, float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st);
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st);
-cudaError_t launch_cand_threshold(const float2* cand, const int* cand_cnt, int n_rows, int slots, int cap, const int* n_target, float* tau2, cudaStream_t st);
-cudaError_t launch_rescore(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap,
-                           const int64_t* indptr, const int32_t* indices, int filt, float* S2, int32_t* idxmap, const float* tau2, cudaStream_t st);
+constexpr int kShortWidth = 512;               // shortlist entries per row handed to topn_select_kernel (n' <= 256 plus ties)
+cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
+                             const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, float* S2,
+                             int32_t* idxmap, int* flag, cudaStream_t st);
 cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);
 int sgd_epoch_blocks_per_sm(const TrainParams& p);
 
