@@ -274,13 +274,17 @@ def run_ours(args):
             _rankfm.pin(*pinned)
             for _ in range(3):                            # the allocator / lazy module loading settle over the first calls
                 e2e_step()
-            dts = [e2e_step() for _ in range(max(3, min(args.steps, 5)))]
+            dts = [e2e_step() for _ in range(max(7, args.steps))]
+            dt_med = float(np.median(dts))
             h2d = X.nbytes + c["sw"].nbytes + ui.indptr.nbytes + ui.indices.nbytes + sum(v.nbytes for v in c["w0"].values()) + \
                 (c["x_uf"].nbytes if c["P"] else 0) + (c["x_if"].nbytes if c["Q"] else 0)
             d2h = sum(v.nbytes for v in c["w0"].values())
             _rankfm.unpin(*pinned)
-            e2e = {"value": N * epochs / float(np.mean(dts)), "unit": "interactions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": 1e3 * float(np.mean(dts)), "ms_each": [round(1e3 * d, 2) for d in dts], "call": "rankfm_b200._rankfm._fit(page-locked host ndarray buffers) -> ctypes -> rfm_fit"}
+            # wall-clock steps on a shared host see occasional scheduling hiccups (one 470 ms step among 25 ms ones was
+            # observed): the value is the MEDIAN step, every sample and the mean are reported next to it
+            e2e = {"value": N * epochs / dt_med, "unit": "interactions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": 1e3 * dt_med, "statistic": "median of %d steps" % len(dts), "mean_ms_per_step": 1e3 * float(np.mean(dts)),
+                   "ms_each": [round(1e3 * d, 2) for d in dts], "call": "rankfm_b200._rankfm._fit(page-locked host ndarray buffers) -> ctypes -> rfm_fit"}
         recommend = None
         if world == 1 and not args.no_recommend:
             try:

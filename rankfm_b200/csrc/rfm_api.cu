@@ -856,11 +856,14 @@ static int shortlist_target(rfm_session* s, int32_t u, int32_t n_items, int32_t 
     return need;
 }
 
-// Pass 1 (block maxima -> per-row threshold) may visit only every k-th item tile: the n'-th largest block maximum of a
+// Pass 1 (block bounds -> per-row threshold) may visit only 1/k of the item tiles: the n'-th largest block bound of a
 // SUBSET of the items is still a lower bound of the row's n'-th best score, just a looser one -- pass 2 then collects
-// about k x n' candidates instead of ~n', which costs a few KB of writes per row, against (1 - 1/k) of a GEMM pass saved.
-// k is the largest of {4, 2, 1} that leaves >= 4 n' blocks (fewer blocks make the bound collapse).  RANKFM_B200_TAU_STRIDE
-// = 1 | 2 | 4 | 8 caps k.
+// up to k x n' candidates instead of ~n', which costs a few KB of writes per row, against (1 - 1/k) of a GEMM pass saved.
+// k is the largest of {4, 2, 1} that leaves >= 4 n' blocks (fewer blocks make the bound collapse); RANKFM_B200_TAU_STRIDE
+// = 1 | 2 | 4 | 8 caps k.  Which tiles: the catalogue is in descending bias order, so the FIRST 1/k of the tiles hold the
+// items with the largest biases -- where popularity drives the ranking their scores bound the row's best scores almost
+// as tightly as the whole catalogue, and where it does not they are as good as any other sample
+// (RANKFM_B200_TAU_SUBSET=stride takes every k-th tile instead).
 static int tau_stride(const Tables& T, int32_t n_items)
 {
     const char* e = getenv("RANKFM_B200_TAU_STRIDE");
@@ -868,15 +871,21 @@ static int tau_stride(const Tables& T, int32_t n_items)
     const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN, want = 2 * n_items + 16;
     int best = 1;
     for (int k = 2; k <= std::min(cap, 8); k *= 2)
-        if ((int64_t)((n_tiles + k - 1) / k) * (BN / 64) >= (int64_t)4 * want) best = k;
+        if ((int64_t)((n_tiles + k - 1) / k) * BN >= (int64_t)256 * want) best = k;          // the subset keeps >= 256 n' items
     return best;
 }
 
-// 64-item blocks pass 1 produces per row
+static bool tau_subset_head()
+{
+    const char* e = getenv("RANKFM_B200_TAU_SUBSET");
+    return !(e && !strcmp(e, "stride"));
+}
+
+// block bounds (one per kTauBlock items) pass 1 produces per row
 static int tau_blocks(const Tables& T, int stride)
 {
     const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN;
-    return (n_tiles + stride - 1) / stride * (BN / 64);
+    return (n_tiles + stride - 1) / stride * (BN / kTauBlock);
 }
 
 // tensor-core path (rfm_gemm.cu): pass 1 block bounds -> per-row threshold -> pass 2 candidates -> shortlist (n' best by
@@ -889,12 +898,12 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     int rc = ensure_gemm_items(s);
     if (rc) return rc;
     const int Kp = gemm_kp(T), MT = gemm_m_tile(T), SPS = gemm_slots_per_split(T), I_pad = s->gemm_I_pad;
-    const int stride = tau_stride(T, n_items), n_sub1 = tau_blocks(T, stride), n_tiles1 = n_sub1 / (gemm_block_n(T) / 64);
+    const int stride = tau_stride(T, n_items), n_sub1 = tau_blocks(T, stride), n_tiles1 = n_sub1 / (gemm_block_n(T) / kTauBlock);
     // candidate entries per row: ~1-2 n' with a full pass 1, ~stride x n' with a strided one (n' <= kCandCap)
-    const int width = stride == 1 ? 6 * kCandCap : 4 * kCandCap * stride;
+    const int width = stride == 1 ? 8 * kCandCap : 4 * kCandCap * stride;
     // one wave: at most n_sm CTAs (one resident per SM), user tiles x item splits; >= 2 splits keep a partial last batch balanced
     int64_t max_rows = (int64_t)std::max(1, s->n_sm / 2) * MT;
-    max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)2 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
+    max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)4 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
     const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
@@ -921,7 +930,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), (size_t)M_pad * 4, cudaMemcpyHostToDevice, s->st));
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
         if (gemm_ms) CU(cudaEventRecord(a, s->st));
-        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, stride, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
+        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, tau_subset_head() ? -stride : stride, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         CU(launch_row_threshold(d_rowmax, M_pad, n_sub1, d_ntgt, d_tau, s->st));
         e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, d_cand, d_cnt, d_tau, cap, nullptr, nullptr, s->st);
@@ -975,7 +984,7 @@ static int64_t recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, in
     const int mode = recommend_mode();
     const Tables& T = s->T;
     bool tc = mode != 2 && gemm_supported(T) && encode_ok() && (mode == 1 || ((int64_t)T.I >= 32768 && n * (int64_t)T.I >= ((int64_t)1 << 26)));
-    // the per-row threshold is the n'-th largest maximum over 64-item blocks: needs comfortably more blocks than n'
+    // the per-row threshold is the n'-th largest bound over 8-item blocks: needs comfortably more blocks than n'
     const int limit = std::min(kCandCap, tau_blocks(T, tau_stride(T, n_items)) / 2);
     if (2 * n_items + 16 > limit) tc = false;
     int64_t lo = 0, hi = n;

@@ -8,6 +8,7 @@
 // (derived from compute_ui_utility :48-89; there is no user-feature x item-feature cross term), i.e. a dense GEMM whose
 // output (U x I) can never be materialised at cfg5 scale (1M x 1M).  So:
 //
+//   (superseded in the details by the comments at score_filter_kernel: bias-ordered catalogue, 8-item block bounds)
 //   score_filter_kernel   bf16 operands, fp32 accumulation on the 5th-generation tensor cores:
 //       TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma (cta_group::1, M=128, N=256|128,
 //       K=16 per instruction, issued by one elected thread) -> accumulators in TMEM (2 stages) -> tcgen05.ld in the
@@ -185,7 +186,7 @@ struct GemmParams {
     const float* tau;            // [M_pad] per-row threshold from pass 1
     int cap;
     // MODE_ROWMAX
-    float* rowmax;               // [M_pad, n_tiles * BLOCK_N/64] lower bounds of the maxima of the visited 64-item blocks
+    float* rowmax;               // [M_pad, n_tiles * BLOCK_N/kTauBlock] lower bounds of the best score of every visited 8-item block
     // MODE_DUMP
     float* S;                    // [M_pad, I_pad]
     long long ldS;
@@ -215,12 +216,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t bar_tfull = bar_a + 8u, bar_tempty = bar_tfull + 16u, bar_bias = bar_tempty + 16u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 8 * (2 * nstage + 7));
 
-    // this CTA: user tile blockIdx.x, item tiles [t0, t1)
+    // this CTA: user tile blockIdx.x, visited item tiles blockIdx.y, blockIdx.y + n_splits, ... (round robin: in bias order
+    // a contiguous range would hand one split all of a row's best items and overflow its candidate slot)
     const int m0 = blockIdx.x * (128 * MSUB);
     constexpr int ACC_COLS = MSUB * BLOCK_N;           // TMEM columns of one accumulator stage
-    const int per = (p.n_tiles + p.n_splits - 1) / p.n_splits;
-    const int t0 = blockIdx.y * per, t1 = min(p.n_tiles, t0 + per);
-    const int my_tiles = max(0, t1 - t0);
+    const int t0 = blockIdx.y, tstep = p.n_splits;
+    const int my_tiles = t0 < p.n_tiles ? (p.n_tiles - t0 + tstep - 1) / tstep : 0;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < nstage; ++s) { bar_init(bar_full + 8u * s, 1); bar_init(bar_empty + 8u * s, 1); }
@@ -249,7 +250,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t ph = (uint32_t)(it / nstage) & 1u;
                 bar_wait(bar_empty + 8u * s, ph ^ 1u);
                 bar_expect_tx(bar_full + 8u * s, (uint32_t)kb_n * B_KB_BYTES);
-                const int n0 = (t0 + it) * p.tile_stride * BLOCK_N;
+                const int n0 = (t0 + it * tstep) * p.tile_stride * BLOCK_N;
                 for (int kb = 0; kb < kb_n; ++kb)
                     tma_load_2d(s32(sB + ((size_t)s * kb_n + kb) * B_KB_BYTES), &tmB, kb * 64, n0, bar_full + 8u * s);
             }
@@ -288,7 +289,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t aph = (uint32_t)(it >> 1) & 1u;
                 bar_wait(bar_tempty + 8u * as, aph ^ 1u);           // the epilogue is done with this slot
                 bar_expect_tx(bar_bias + 8u * as, BLOCK_N * 4u);
-                bulk_load_1d(s32(sBias + as * BLOCK_N), p.bias + (size_t)(t0 + it) * p.tile_stride * BLOCK_N, BLOCK_N * 4u, bar_bias + 8u * as);
+                bulk_load_1d(s32(sBias + as * BLOCK_N), p.bias + (size_t)(t0 + it * tstep) * p.tile_stride * BLOCK_N, BLOCK_N * 4u, bar_bias + 8u * as);
             }
         }
     } else if (warp >= 4) {
@@ -297,7 +298,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // The epilogue is the issue-bound part of this kernel (K is only 64..128: 2.3 instructions per score would cost more
         // issue slots than the MMAs take cycles), so it works on the RAW dot products and touches the bias once per run of
         // items -- possible because positions are in descending bias order (run maximum = first, minimum = last):
-        //   pass 1  lower bound of a 64-item block's best score = max(dot) + smallest bias of the block  (FMNMX3 tree)
+        //   pass 1  lower bound of an 8-item block's best score = max(dot) + smallest bias of the block  (FMNMX3 tree).
+        //           Small blocks because bias order CLUSTERS a row's best items (one bound per block must not hide them)
         //   pass 2  score >= tau can only hold where dot >= tau - largest bias of the 32-item chunk; the four 8-item
         //           sub-maxima of the tree gate the (rare per row) append of (dot, position)
         // Both are conservative (candidates form a superset); exact fp32 scores are recomputed from the shortlist. =====
@@ -317,7 +319,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float2* wp = my;
         float2* const wp_room = my + (cap - 8);                     // last write position that still leaves room for 8 entries
         bool over = false;
-        float* rmax = MODE == MODE_ROWMAX ? p.rowmax + (size_t)row * (p.n_tiles * (BLOCK_N / 64)) : nullptr;
+        float* rmax = MODE == MODE_ROWMAX ? p.rowmax + (size_t)row * (p.n_tiles * (BLOCK_N / kTauBlock)) : nullptr;
 
         for (int it = 0; it < my_tiles; ++it) {
             const int as = it & 1;
@@ -325,11 +327,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             bar_wait(bar_bias + 8u * as, aph);
             bar_wait(bar_tfull + 8u * as, aph);
             tc_fence_after();
-            const int n0 = (t0 + it) * p.tile_stride * BLOCK_N + col0;
+            const int n0 = (t0 + it * tstep) * p.tile_stride * BLOCK_N + col0;
             const float* sb = sBias + as * BLOCK_N + col0;
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * ACC_COLS + tcol0);
             uint32_t ra[32], rb[32];                                // double-buffered: chunk c+1 is in flight while chunk c is processed
-            float blockmax = -INFINITY;
             tc_ld32_issue(taddr, ra);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -347,9 +348,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 } else {
                     const float m0_ = max8(v), m1_ = max8(v + 8), m2_ = max8(v + 16), m3_ = max8(v + 24);
                     if (MODE == MODE_ROWMAX) {
-                        const float mx = fmaxf(max3(m0_, m1_, m2_), m3_);
-                        blockmax = (c & 1) ? fmaxf(blockmax, mx) : mx;
-                        if (c & 1) rmax[(size_t)(t0 + it) * (BLOCK_N / 64) + col0 / 64 + (c >> 1)] = blockmax + sb[c * 32 + 31];
+                        // one bound per 8-item block: its best dot product + its smallest (= last) bias
+                        const float4 lb = make_float4(m0_ + sb[c * 32 + 7], m1_ + sb[c * 32 + 15], m2_ + sb[c * 32 + 23], m3_ + sb[c * 32 + 31]);
+                        *reinterpret_cast<float4*>(rmax + (size_t)(t0 + it * tstep) * (BLOCK_N / kTauBlock) + (col0 + c * 32) / kTauBlock) = lb;
                     } else {
                         const float thr = tau - sb[c * 32];
                         const float msub[4] = {m0_, m1_, m2_, m3_};
@@ -621,10 +622,14 @@ cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_
     return cudaGetLastError();
 }
 
-// n_target[row]-th largest of the row's block maxima -> tau[row]  (one block per row, radix select over ordered keys)
-__global__ void __launch_bounds__(256) row_threshold_kernel(const float* __restrict__ rowmax, int n_blocks, const int* __restrict__ n_target,
-                                                            float* __restrict__ tau)
+// n_target[row]-th largest of the row's block bounds -> tau[row]  (one block per row, exact radix select over ordered keys;
+// the row is staged in shared memory once when it fits, so HBM sees it once instead of four times)
+constexpr int kThrThreads = 1024;
+__global__ void __launch_bounds__(kThrThreads) row_threshold_kernel(const float* __restrict__ rowmax, int n_blocks, const int* __restrict__ n_target,
+                                                                    float* __restrict__ tau, int staged)
 {
+    extern __shared__ __align__(16) unsigned char thr_smem[];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(thr_smem);
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining;
     const int row = blockIdx.x, tid = threadIdx.x;
@@ -632,14 +637,21 @@ __global__ void __launch_bounds__(256) row_threshold_kernel(const float* __restr
     const int want = n_target[row];
     if (want > n_blocks) { if (tid == 0) tau[row] = -INFINITY; return; }
     if (tid == 0) { s_prefix = 0u; s_remaining = (uint32_t)want; }
+    if (staged) {
+        const float4* v4 = reinterpret_cast<const float4*>(v);               // n_blocks is a multiple of 4 (16 bounds per 128-item tile)
+        for (int k = tid; k < n_blocks / 4; k += kThrThreads) {
+            const float4 x = __ldg(v4 + k);
+            reinterpret_cast<uint4*>(keys)[k] = make_uint4(ord_key(x.x), ord_key(x.y), ord_key(x.z), ord_key(x.w));
+        }
+    }
     __syncthreads();
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        hist[tid] = 0u;
+        if (tid < 256) hist[tid] = 0u;
         __syncthreads();
         const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int k = tid; k < n_blocks; k += 256) {
-            const uint32_t key = ord_key(v[k]);
+        for (int k = tid; k < n_blocks; k += kThrThreads) {
+            const uint32_t key = staged ? keys[k] : ord_key(v[k]);
             if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
         }
         __syncthreads();
@@ -656,7 +668,13 @@ __global__ void __launch_bounds__(256) row_threshold_kernel(const float* __restr
 
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st)
 {
-    row_threshold_kernel<<<n_rows, 256, 0, st>>>(rowmax, n_blocks, n_target, tau);
+    const size_t smem = (size_t)n_blocks * 4;
+    const int staged = smem <= 200 * 1024 && n_blocks % 4 == 0;
+    if (staged) {
+        cudaError_t e = cudaFuncSetAttribute(row_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    row_threshold_kernel<<<n_rows, kThrThreads, staged ? smem : 0, st>>>(rowmax, n_blocks, n_target, tau, staged);
     return cudaGetLastError();
 }
 
@@ -677,8 +695,9 @@ static cudaError_t launch_modes(int mode, const CUtensorMap& tmA, const CUtensor
     return launch_mode<BN, MSUB, MODE_FILTER>(tmA, tmB, p, grid, smem, st);
 }
 
-// mode 0: dump dense scores into S [M_pad, I_pad]; 1: maxima of the 64-item blocks of every tile_stride-th item tile into
-// rowmax [M_pad, ceil(n_tiles/tile_stride) * BN/64]; 2: candidates with score >= tau[row] into cand/cand_cnt.
+// mode 0: dump dense scores into S [M_pad, I_pad]; 1: lower bounds of the best score of every 64-item block of a subset of
+// the item tiles (see tile_stride below) into rowmax [M_pad, ceil(n_tiles/|tile_stride|) * BN/64]; 2: candidates that can
+// reach tau[row] into cand/cand_cnt.
 // M_pad must be a multiple of gemm_m_tile(T), I_pad of gemm_block_n(T).
 cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
                                 int tile_stride, float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st)
@@ -686,9 +705,11 @@ cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const 
     const int Kp = gemm_kp(T), BN = gemm_block_n(T), MSUB = gemm_msub(T);
     alignas(64) CUtensorMap tmA, tmB;
     if (!make_map(&tmA, A, M_pad, Kp, 128) || !make_map(&tmB, B, I_pad, Kp, BN)) return cudaErrorNotSupported;
-    if (tile_stride < 1 || M_pad % (128 * MSUB) || I_pad % BN) return cudaErrorInvalidValue;
+    if (tile_stride == 0 || M_pad % (128 * MSUB) || I_pad % BN) return cudaErrorInvalidValue;
     GemmParams p{};
-    p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = (I_pad / BN + tile_stride - 1) / tile_stride; p.tile_stride = tile_stride;
+    // tile_stride = k > 0: every k-th item tile; k < 0: the first 1/|k| of the tiles (the highest-bias items of the catalogue)
+    const int frac = tile_stride < 0 ? -tile_stride : tile_stride;
+    p.bias = bias; p.kblocks = Kp / 64; p.n_tiles = (I_pad / BN + frac - 1) / frac; p.tile_stride = tile_stride < 0 ? 1 : tile_stride;
     p.n_splits = n_splits; p.n_users = n_users;
     p.cand = cand; p.cand_cnt = cand_cnt; p.tau = tau; p.cap = cap; p.rowmax = rowmax; p.S = S; p.ldS = I_pad;
     const size_t a_bytes = (size_t)MSUB * p.kblocks * 128 * 128, stage_bytes = (size_t)p.kblocks * BN * 128;

@@ -71,6 +71,7 @@ cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_
 cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
                                 int tile_stride, float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st);
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st);
+constexpr int kTauBlock = 8;                   // items per pass-1 block bound
 constexpr int kShortWidth = 512;               // shortlist entries per row handed to topn_select_kernel (n' <= 256 plus ties)
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, float* S2,

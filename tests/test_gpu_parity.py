@@ -434,13 +434,16 @@ def test_tcgen05_gemm_scores_match_fp32(gpu_lib, F, P, Q, I, msub, monkeypatch):
         assert np.corrcoef(S[r], ref)[0, 1] > 0.9995
 
 
-@pytest.mark.parametrize("msub,stride", [("2", "4"), ("2", "1"), ("1", "4"), ("1", "1"), ("2", "8")])
+@pytest.mark.parametrize("msub,stride,subset", [("2", "4", "head"), ("2", "1", "head"), ("1", "4", "head"), ("1", "1", "head"), ("2", "8", "head"),
+                                                ("2", "4", "stride"), ("1", "2", "stride")])
 @pytest.mark.parametrize("F,P,Q", [(32, 0, 0), (20, 2, 3)])
 @pytest.mark.parametrize("filt", [False, True])
-def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, msub, stride, monkeypatch):
-    """tcgen05 candidate GEMM (user sub-tiles per CTA x pass-1 tile stride) + exact re-score against the exact fp32 path"""
+def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, msub, stride, subset, monkeypatch):
+    """tcgen05 candidate GEMM (user sub-tiles per CTA x pass-1 tile fraction x which tiles) + exact re-score against the
+    exact fp32 path"""
     monkeypatch.setenv("RANKFM_B200_GEMM_MSUB", msub)
     monkeypatch.setenv("RANKFM_B200_TAU_STRIDE", stride)
+    monkeypatch.setenv("RANKFM_B200_TAU_SUBSET", subset)
     sess, w, ui, x_uf, x_if, U, I = _scoring_session(600, 60000, F, P, Q, seed=7 + F)
     rng = np.random.default_rng(0)
     users = rng.integers(0, U, 300).astype(np.float32)
