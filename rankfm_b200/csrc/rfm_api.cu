@@ -859,15 +859,15 @@ static int shortlist_target(rfm_session* s, int32_t u, int32_t n_items, int32_t 
 // Pass 1 (block bounds -> per-row threshold) may visit only 1/k of the item tiles: the n'-th largest block bound of a
 // SUBSET of the items is still a lower bound of the row's n'-th best score, just a looser one -- pass 2 then collects
 // up to k x n' candidates instead of ~n', which costs a few KB of writes per row, against (1 - 1/k) of a GEMM pass saved.
-// k is the largest of {4, 2, 1} that leaves >= 4 n' blocks (fewer blocks make the bound collapse); RANKFM_B200_TAU_STRIDE
-// = 1 | 2 | 4 | 8 caps k.  Which tiles: the catalogue is in descending bias order, so the FIRST 1/k of the tiles hold the
+// k is the largest of {8, 4, 2, 1} that leaves the subset >= 256 n' items (a smaller sample makes the bound collapse);
+// RANKFM_B200_TAU_STRIDE = 1 | 2 | 4 | 8 caps k.  Which tiles: the catalogue is in descending bias order, so the FIRST 1/k of the tiles hold the
 // items with the largest biases -- where popularity drives the ranking their scores bound the row's best scores almost
 // as tightly as the whole catalogue, and where it does not they are as good as any other sample
 // (RANKFM_B200_TAU_SUBSET=stride takes every k-th tile instead).
 static int tau_stride(const Tables& T, int32_t n_items)
 {
     const char* e = getenv("RANKFM_B200_TAU_STRIDE");
-    const int cap = e ? std::max(1, atoi(e)) : 4;
+    const int cap = e ? std::max(1, atoi(e)) : 8;
     const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN, want = 2 * n_items + 16;
     int best = 1;
     for (int k = 2; k <= std::min(cap, 8); k *= 2)
@@ -906,7 +906,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)4 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
     const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
-    __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr; float* d_S2 = nullptr; int32_t* d_map = nullptr;
+    __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr;
     float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr; int* d_flag = nullptr;
     auto done = [&](int code) { cudaFree(d_fix); cudaFree(d_fix_users); return code; };
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
@@ -915,8 +915,6 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub1, &d_rowmax))) return rc;
     if ((rc = scratch_get(s, 5, (size_t)rows_alloc * width, &d_cand))) return rc;
     if ((rc = scratch_get(s, 6, (size_t)rows_alloc * split_cap * SPS, &d_cnt))) return rc;
-    if ((rc = scratch_get(s, 7, (size_t)rows_alloc * kShortWidth, &d_S2))) return rc;
-    if ((rc = scratch_get(s, 8, (size_t)rows_alloc * kShortWidth, &d_map))) return rc;
     if ((rc = scratch_get(s, 9, (size_t)rows_alloc, &d_flag))) return rc;
     std::vector<int> ntgt((size_t)rows_alloc), flag_h;
     cudaEvent_t a = nullptr, b = nullptr;
@@ -937,11 +935,9 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         if (gemm_ms) CU(cudaEventRecord(b, s->st));
         e = launch_shortlist(T, d_users + off, nb, d_cand, d_cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, d_ntgt, s->d_indptr, s->d_indices, filter_previous,
-                             d_S2, d_map, d_flag, s->st);
+                             n_items, d_rec + (size_t)off * n_items, d_flag, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e)));
-        e = launch_topn_select(d_S2, kShortWidth, d_users + off, nb, nullptr, nullptr, 0, n_items, d_rec + (size_t)off * n_items, nullptr, s->st, d_map);
-        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "topn_select launch failed: %s", cudaGetErrorString(e)));
-        s->launches += 6;
+        s->launches += 5;
         // rows whose candidates overflowed (pathological ties / clustered scores) are redone on the exact path
         flag_h.resize((size_t)nb);
         CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->st));

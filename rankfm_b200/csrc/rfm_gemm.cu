@@ -169,6 +169,44 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int n) { return (1u << 4) 
 
 __device__ __forceinline__ uint32_t ord_key(float s) { const uint32_t b = __float_as_uint(s); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 
+// Radix-select helpers shared by the threshold / shortlist kernels (256-bin histograms in shared memory).
+// hist_add: warp-aggregated increment -- keys of one row share their leading byte (sign + 7 exponent bits), so plain
+// shared-memory atomics of the first pass serialise on two or three addresses.  Every lane of the warp must call.
+__device__ __forceinline__ void hist_add(uint32_t* hist, bool valid, uint32_t bin)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? bin : 0x100u);
+    if (valid && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+}
+// radix_pick (one full warp): the bin, scanning from 255 down, where the running count first reaches `remaining`, and how
+// many of that bin's keys are still wanted.  Lane l owns bins [8l, 8l+8); suffix sums over lanes by shuffles.
+__device__ __forceinline__ void radix_pick(const uint32_t* hist, uint32_t remaining, uint32_t& bin, uint32_t& left)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t c[8], mine = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = hist[8 * lane + k]; mine += c[k]; }
+    uint32_t suf = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, off);
+        if (lane + off < 32) suf += t;
+    }
+    const uint32_t above = suf - mine;                                   // keys in bins owned by higher lanes
+    const bool here = above < remaining && suf >= remaining;
+    const unsigned m = __ballot_sync(0xffffffffu, here);
+    uint32_t b = 0u, l = 0u;
+    if (here) {
+        uint32_t rem = remaining - above;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            if (l == 0u) { if (c[k] >= rem) { b = (uint32_t)(8 * lane + k); l = rem; } else rem -= c[k]; }
+        }
+    }
+    const int src = m ? __ffs(m) - 1 : 0;                                // m == 0: fewer keys than wanted -> bin 0, nothing left
+    bin = __shfl_sync(0xffffffffu, b, src);
+    left = __shfl_sync(0xffffffffu, l, src);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // the GEMM + running-threshold filter
 // ---------------------------------------------------------------------------------------------------------------
@@ -331,6 +369,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float* sb = sBias + as * BLOCK_N + col0;
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * ACC_COLS + tcol0);
             uint32_t ra[32], rb[32];                                // double-buffered: chunk c+1 is in flight while chunk c is processed
+            float4 lb_even = zero4();
+            static_assert(NCH % 2 == 0, "block bounds are stored per pair of 32-column chunks");
             tc_ld32_issue(taddr, ra);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -350,7 +390,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (MODE == MODE_ROWMAX) {
                         // one bound per 8-item block: its best dot product + its smallest (= last) bias
                         const float4 lb = make_float4(m0_ + sb[c * 32 + 7], m1_ + sb[c * 32 + 15], m2_ + sb[c * 32 + 23], m3_ + sb[c * 32 + 31]);
-                        *reinterpret_cast<float4*>(rmax + (size_t)(t0 + it * tstep) * (BLOCK_N / kTauBlock) + (col0 + c * 32) / kTauBlock) = lb;
+                        if (c & 1) {                                 // two chunks' bounds leave together: one full 32-byte sector per row
+                            float4* dst = reinterpret_cast<float4*>(rmax + (size_t)(t0 + it * tstep) * (BLOCK_N / kTauBlock) + (col0 + (c - 1) * 32) / kTauBlock);
+                            dst[0] = lb_even; dst[1] = lb;
+                        } else lb_even = lb;
                     } else {
                         const float thr = tau - sb[c * 32];
                         const float msub[4] = {m0_, m1_, m2_, m3_};
@@ -383,14 +426,16 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// shortlist_kernel: one block per requested user.
-//   1. gather the row's pass-2 candidates (raw dot, position) from its slots into shared memory, bf16-GEMM score =
+// shortlist_kernel: one block per requested user, from the pass-2 candidates to the final recommendation row.
+//   1. gather the row's candidates (raw dot, position) from its slots into shared memory, bf16-GEMM score =
 //      dot + bias[position]
 //   2. keep the n' best by that score (exact radix select of the n'-th largest + ordered compaction): pass 2
 //      over-collects when the pass-1 threshold came from a subset of the item tiles, and only the n' best need more work
-//   3. exact fp32 utility of the kept items (same lane-group code as predict), seen items get the "removed" marker
-// Output: S2 / idxmap [row, kShortWidth] for topn_select_kernel; flag[row] = 1 when the row must be redone on the exact
-// path (a candidate slot overflowed, or more than kShortWidth candidates tie at the cut).
+//   3. exact fp32 utility of the kept items (same lane-group code as predict); seen items are dropped (:450)
+//   4. bitonic sort of the (at most kShortWidth) exact scores, best n_items out -- `np.argsort(...)[::-1]` + the walk
+//      of `_rankfm.pyx:444-456`, on the shortlist
+// flag[row] = 1 when the row must be redone on the exact path (a candidate slot overflowed, or more than kShortWidth
+// candidates tie at the cut); unknown users (-1) get the reference's NaN row (:437-438).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kShortThreads = 256;
 
@@ -399,12 +444,12 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
                                                                   const int* __restrict__ cand_cnt, int slots, int cap, const float* __restrict__ bias,
                                                                   const int32_t* __restrict__ order, const int* __restrict__ n_target,
                                                                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                                                  int filter_previous, float* __restrict__ S2, int32_t* __restrict__ idxmap,
-                                                                  int* __restrict__ flag)
+                                                                  int filter_previous, int n_items, float* __restrict__ rec, int* __restrict__ flag)
 {
     extern __shared__ __align__(16) unsigned char short_smem[];
     uint2* ent = reinterpret_cast<uint2*>(short_smem);               // [slots * cap] (ordered key of the bf16 score, position)
     __shared__ int32_t kept[kShortWidth];                            // item ids of the shortlist, in position order
+    __shared__ unsigned long long sel[kShortWidth];                  // (ordered key of the exact score << 32) | shortlist slot
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining;
     __shared__ int s_off[65], s_over, s_base, wsum[kShortThreads / 32];
@@ -412,8 +457,7 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane % G, gw = lane / G;
     const int u = __ldg(users + b);
     const bool known = u >= 0;
-    float* out = S2 + (size_t)b * kShortWidth;
-    int32_t* omap = idxmap + (size_t)b * kShortWidth;
+    float* out = rec + (size_t)b * n_items;
     const int* cc = cand_cnt + (size_t)b * slots;
     if (tid == 0) {
         int total = 0, over = 0;
@@ -423,8 +467,8 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
     }
     __syncthreads();
     const int total = s_off[slots], want = n_target[b];
-    if (!known || s_over) {                                           // unknown user: NaN row from topn_select; overflow: redone by the caller
-        for (int e = tid; e < kShortWidth; e += kShortThreads) { out[e] = __uint_as_float(0xffffffffu); omap[e] = 0; }
+    if (!known || s_over) {                                           // overflow: the caller redoes the row on the exact path
+        if (!known) for (int k = tid; k < n_items; k += kShortThreads) out[k] = __int_as_float(0x7fc00000);
         if (tid == 0) flag[b] = known ? 1 : 0;
         return;
     }
@@ -440,7 +484,7 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
         }
     }
     __syncthreads();
-    // 2. the n'-th largest key (0 = keep every real entry)
+    // 2. the n'-th largest key (1 = keep every real entry)
     uint32_t cut = 1u;
     if (want < total) {
         for (int pass = 0; pass < 4; ++pass) {
@@ -448,16 +492,18 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
             hist[tid] = 0u;
             __syncthreads();
             const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-            for (int e = tid; e < total; e += kShortThreads) {
-                const uint32_t key = ent[e].x;
-                if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+            for (int e0 = 0; e0 < total; e0 += kShortThreads) {      // warp-uniform trip count (hist_add is warp-collective)
+                const int e = e0 + tid;
+                const uint32_t key = e < total ? ent[e].x : 0u;
+                const bool match = e < total && (key & pmask) == prefix;
+                if (pass == 0) hist_add(hist, match, (key >> shift) & 0xffu);
+                else if (match) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                uint32_t remaining = s_remaining, bin = 0u;
-                for (int d = 255; d >= 0; --d) { if (hist[d] >= remaining) { bin = (uint32_t)d; break; } remaining -= hist[d]; }
-                s_prefix = prefix | (bin << shift);
-                s_remaining = remaining;
+            if (tid < 32) {
+                uint32_t bin, left;
+                radix_pick(hist, s_remaining, bin, left);
+                if (tid == 0) { s_prefix = prefix | (bin << shift); s_remaining = left; }
             }
             __syncthreads();
         }
@@ -480,11 +526,12 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
     }
     const int n_kept = s_base;
     if (n_kept > kShortWidth) {                                        // > kShortWidth - n' ties at the cut: exact path
-        for (int e = tid; e < kShortWidth; e += kShortThreads) { out[e] = __uint_as_float(0xffffffffu); omap[e] = 0; }
         if (tid == 0) flag[b] = 1;
         return;
     }
     if (tid == 0) flag[b] = 0;
+    for (int e = tid; e < kShortWidth; e += kShortThreads) sel[e] = 0ull;                   // key 0 sorts last
+    __syncthreads();
     // 3. exact fp32 re-score
     UserCtx<QPL> uc;
     load_user<G, QPL, FEAT>(T, u, true, sub, uc);
@@ -503,40 +550,59 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
         const bool seen_a = filter_previous ? group_member<G>(ia, indices + seg, deg, oka, sub, gw) : false;
         const bool seen_b = filter_previous ? group_member<G>(ib, indices + seg, deg, okb, sub, gw) : false;
         if (sub == 0) {
-            if (oka) { out[ea] = seen_a ? __uint_as_float(0xffffffffu) : sa; omap[ea] = ia; }
-            if (okb) { out[eb] = seen_b ? __uint_as_float(0xffffffffu) : sb; omap[eb] = ib; }
+            if (oka && !seen_a) sel[ea] = ((unsigned long long)max(ord_key(sa), 1u) << 32) | (uint32_t)ea;
+            if (okb && !seen_b) sel[eb] = ((unsigned long long)max(ord_key(sb), 1u) << 32) | (uint32_t)eb;
         }
     }
-    for (int e = n_kept + tid; e < kShortWidth; e += kShortThreads) { out[e] = __uint_as_float(0xffffffffu); omap[e] = 0; }
+    __syncthreads();
+    // 4. bitonic sort, descending by (exact score, shortlist slot)
+    for (int k = 2; k <= kShortWidth; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < kShortWidth; t += kShortThreads) {
+                const int x = t ^ j;
+                if (x > t) {
+                    const unsigned long long a = sel[t], c = sel[x];
+                    const bool desc = (t & k) == 0;
+                    if (desc ? (a < c) : (a > c)) { sel[t] = c; sel[x] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int k = tid; k < n_items; k += kShortThreads) {
+        const unsigned long long e = k < kShortWidth ? sel[k] : 0ull;
+        out[k] = (e >> 32) == 0ull ? __int_as_float(0x7fc00000) : (float)kept[(uint32_t)(e & 0xffffffffull)];
+    }
 }
 
 template <int G, int QPL>
 static cudaError_t shortlist_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
-                                const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, float* S2,
-                                int32_t* idxmap, int* flag, cudaStream_t st)
+                                const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
+                                int* flag, cudaStream_t st)
 {
     const size_t smem = (size_t)slots * cap * sizeof(uint2);
     cudaError_t e;
     if (T.x_uf_any || T.x_if_any) {
         e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, true><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, S2, idxmap, flag);
+        shortlist_kernel<G, QPL, true><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag);
     } else {
         e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, false><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, S2, idxmap, flag);
+        shortlist_kernel<G, QPL, false><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag);
     }
     return cudaGetLastError();
 }
 
+// rec [n_users, n_items]: final rows (float item indexes, NaN-padded like topn_select_kernel); flag [n_users]
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
-                             const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, float* S2,
-                             int32_t* idxmap, int* flag, cudaStream_t st)
+                             const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
+                             int* flag, cudaStream_t st)
 {
     int qpl = 1;
     const int G = train_group_size(T, &qpl);
     if (max(T.Pp, T.Qp) > 4 * G || qpl > 4 || slots > 64 || (size_t)slots * cap * sizeof(uint2) > 160 * 1024) return cudaErrorInvalidValue;
-#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, S2, idxmap, flag, st)
+#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, st)
     switch (G) {
         case 4:  RFM_SHORT(4, 1);
         case 8:  RFM_SHORT(8, 1);
@@ -650,16 +716,19 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_kernel(const float*
         if (tid < 256) hist[tid] = 0u;
         __syncthreads();
         const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int k = tid; k < n_blocks; k += kThrThreads) {
-            const uint32_t key = staged ? keys[k] : ord_key(v[k]);
-            if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+        for (int k0 = 0; k0 < n_blocks; k0 += kThrThreads) {               // warp-uniform trip count (hist_add is warp-collective)
+            const int k = k0 + tid;
+            const bool inb = k < n_blocks;
+            const uint32_t key = !inb ? 0u : (staged ? keys[k] : ord_key(v[k]));
+            const bool match = inb && (key & pmask) == prefix;
+            if (pass == 0) hist_add(hist, match, (key >> shift) & 0xffu);
+            else if (match) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t remaining = s_remaining, bin = 0u;
-            for (int d = 255; d >= 0; --d) { if (hist[d] >= remaining) { bin = (uint32_t)d; break; } remaining -= hist[d]; }
-            s_prefix = prefix | (bin << shift);
-            s_remaining = remaining;
+        if (tid < 32) {
+            uint32_t bin, left;
+            radix_pick(hist, s_remaining, bin, left);
+            if (tid == 0) { s_prefix = prefix | (bin << shift); s_remaining = left; }
         }
         __syncthreads();
     }

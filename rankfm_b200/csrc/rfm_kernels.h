@@ -72,10 +72,10 @@ cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const 
                                 int tile_stride, float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st);
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st);
 constexpr int kTauBlock = 8;                   // items per pass-1 block bound
-constexpr int kShortWidth = 512;               // shortlist entries per row handed to topn_select_kernel (n' <= 256 plus ties)
+constexpr int kShortWidth = 512;               // shortlist entries per row (n' <= 256 plus ties at the cut)
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
-                             const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, float* S2,
-                             int32_t* idxmap, int* flag, cudaStream_t st);
+                             const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
+                             int* flag, cudaStream_t st);
 cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);
 int sgd_epoch_blocks_per_sm(const TrainParams& p);
 
