@@ -343,18 +343,26 @@ def dram_resident_probe(device=0, steps=2):
     for _ in range(steps):
         sess.restore(); sess.flush_l2()
         flat += sess.train(epochs)
+    # predict() on the same DRAM-resident tables: 8M random (user, item) pairs, one fat-row gather each side per pair
+    rng = np.random.default_rng(3)
+    n_pairs = 8_000_000
+    pairs = np.stack([rng.integers(0, c["U_global"], n_pairs), rng.integers(0, c["I"], n_pairs)], axis=1).astype(np.float32)
+    predict_ms = sess.time_predict(np.ascontiguousarray(pairs), iters=3)
     sess.close()
     kern_ms = sum(s["kernel_ms"] for s in flat)
     alg = sum(N * algorithmic_bytes_per_positive(c["F"], s["draws"] / N) for s in flat)
     peak, src = measured_peaks()
     achieved = alg / (kern_ms / 1e3) / 1e9
+    predict_bytes = n_pairs * (8.0 * c["F"] + 4.0 + 8.0 + 4.0)           # v_u row + v_i row + w_i + the pair + the score
+    predict = {"workload": "predict(): %d random pairs on the same tables" % n_pairs, "ms": predict_ms, "pairs_per_s": n_pairs / (predict_ms * 1e-3),
+               "achieved": predict_bytes / (predict_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": predict_bytes / (predict_ms * 1e-3) / 1e9 / peak, "kernel": "predict_kernel"}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_cfg4m.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     return {"workload": c["label"], "bound": "hbm", "kernel": "sgd_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": src, "algorithmic_bytes_per_launch": alg / len(flat), "launch_ms": kern_ms / len(flat),
-            "interactions_per_s": N * len(flat) / (kern_ms / 1e3)}
+            "interactions_per_s": N * len(flat) / (kern_ms / 1e3), "predict": predict}
 
 
 def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, device=0, iters=3, exact_users=4096):

@@ -530,7 +530,8 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
         return;
     }
     if (tid == 0) flag[b] = 0;
-    for (int e = tid; e < kShortWidth; e += kShortThreads) sel[e] = 0ull;                   // key 0 sorts last
+    const int n_sort = n_kept <= kShortWidth / 2 ? kShortWidth / 2 : kShortWidth;             // power of two >= n_kept
+    for (int e = tid; e < n_sort; e += kShortThreads) sel[e] = 0ull;                            // key 0 sorts last
     __syncthreads();
     // 3. exact fp32 re-score
     UserCtx<QPL> uc;
@@ -539,26 +540,29 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
     long long seg = 0; int deg = 0;
     if (filter_previous) { seg = __ldg(indptr + u); deg = (int)(__ldg(indptr + u + 1) - seg); }
     constexpr int STRIDE = (kShortThreads / 32) * GPW;
-    for (int e0 = 0; e0 < n_kept; e0 += 2 * STRIDE) {                 // warp-uniform trip count; two gathers in flight per group
-        const int ea = e0 + warp * GPW + gw, eb = ea + STRIDE;
-        const bool oka = ea < n_kept, okb = eb < n_kept;
-        const int ia = oka ? kept[ea] : 0, ib = okb ? kept[eb] : 0;
-        ItemRow<QPL> ra, rb;
-        load_item<G, QPL, FEAT>(T, ia, oka, sub, ra);
-        load_item<G, QPL, FEAT>(T, ib, okb, sub, rb);
-        const float sa = utility<G, QPL, FEAT>(uc, ra), sb = utility<G, QPL, FEAT>(uc, rb);
-        const bool seen_a = filter_previous ? group_member<G>(ia, indices + seg, deg, oka, sub, gw) : false;
-        const bool seen_b = filter_previous ? group_member<G>(ib, indices + seg, deg, okb, sub, gw) : false;
-        if (sub == 0) {
-            if (oka && !seen_a) sel[ea] = ((unsigned long long)max(ord_key(sa), 1u) << 32) | (uint32_t)ea;
-            if (okb && !seen_b) sel[eb] = ((unsigned long long)max(ord_key(sb), 1u) << 32) | (uint32_t)eb;
+    constexpr int INFL = QPL <= 2 ? 4 : 2;                            // item rows in flight per lane group
+    for (int e0 = 0; e0 < n_kept; e0 += INFL * STRIDE) {              // warp-uniform trip count
+        int ee[INFL], ii[INFL];
+        ItemRow<QPL> rr[INFL];
+#pragma unroll
+        for (int w = 0; w < INFL; ++w) {
+            ee[w] = e0 + w * STRIDE + warp * GPW + gw;
+            ii[w] = ee[w] < n_kept ? kept[ee[w]] : 0;
+            load_item<G, QPL, FEAT>(T, ii[w], ee[w] < n_kept, sub, rr[w]);
+        }
+#pragma unroll
+        for (int w = 0; w < INFL; ++w) {
+            const bool ok = ee[w] < n_kept;
+            const float sc = utility<G, QPL, FEAT>(uc, rr[w]);
+            const bool seen = filter_previous ? group_member<G>(ii[w], indices + seg, deg, ok, sub, gw) : false;
+            if (sub == 0 && ok && !seen) sel[ee[w]] = ((unsigned long long)max(ord_key(sc), 1u) << 32) | (uint32_t)ee[w];
         }
     }
     __syncthreads();
     // 4. bitonic sort, descending by (exact score, shortlist slot)
-    for (int k = 2; k <= kShortWidth; k <<= 1) {
+    for (int k = 2; k <= n_sort; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < kShortWidth; t += kShortThreads) {
+            for (int t = tid; t < n_sort; t += kShortThreads) {
                 const int x = t ^ j;
                 if (x > t) {
                     const unsigned long long a = sel[t], c = sel[x];
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
         }
     }
     for (int k = tid; k < n_items; k += kShortThreads) {
-        const unsigned long long e = k < kShortWidth ? sel[k] : 0ull;
+        const unsigned long long e = k < n_sort ? sel[k] : 0ull;
         out[k] = (e >> 32) == 0ull ? __int_as_float(0x7fc00000) : (float)kept[(uint32_t)(e & 0xffffffffull)];
     }
 }
@@ -735,8 +739,69 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_kernel(const float*
     if (tid == 0) { const uint32_t kb = s_prefix; tau[row] = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb); }
 }
 
+// Register-resident variant for rows of at most 1024 * KPT bounds (the common case): every thread keeps its KPT keys in
+// registers for all four passes, so a pass costs ~5 instructions per key (the kernel is issue-bound, not memory-bound).
+// Pass 0 folds a thread's run of equal leading bytes locally and then once per warp (match_any + redux): the leading
+// byte (sign + 7 exponent bits) is shared by almost all keys of a row and would serialise plain shared-memory atomics.
+template <int KPT>
+__global__ void __launch_bounds__(kThrThreads) row_threshold_reg_kernel(const float* __restrict__ rowmax, int n_blocks, const int* __restrict__ n_target,
+                                                                        float* __restrict__ tau)
+{
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int want = n_target[row];
+    if (want > n_blocks) { if (tid == 0) tau[row] = -INFINITY; return; }
+    const float4* v4 = reinterpret_cast<const float4*>(rowmax + (size_t)row * n_blocks);     // n_blocks % 4 == 0
+    uint32_t key[KPT];
+#pragma unroll
+    for (int j = 0; j < KPT / 4; ++j) {
+        const int q = j * kThrThreads + tid;
+        const bool inb = q < n_blocks / 4;
+        const float4 x = inb ? __ldg(v4 + q) : zero4();
+        key[4 * j] = inb ? ord_key(x.x) : 0u; key[4 * j + 1] = inb ? ord_key(x.y) : 0u;      // 0 sorts below every real key
+        key[4 * j + 2] = inb ? ord_key(x.z) : 0u; key[4 * j + 3] = inb ? ord_key(x.w) : 0u;
+    }
+    if (tid == 0) { s_prefix = 0u; s_remaining = (uint32_t)want; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) hist[tid] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        if (pass == 0) {
+            uint32_t cur = key[0] >> 24, n = 1u;
+#pragma unroll
+            for (int j = 1; j < KPT; ++j) {
+                const uint32_t bin = key[j] >> 24;
+                if (bin == cur) ++n; else { atomicAdd(&hist[cur], n); cur = bin; n = 1u; }
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, cur);
+            const uint32_t total = __reduce_add_sync(peers, n);
+            if (lane == __ffs(peers) - 1) atomicAdd(&hist[cur], total);
+        } else {
+#pragma unroll
+            for (int j = 0; j < KPT; ++j)
+                if ((key[j] & pmask) == prefix) atomicAdd(&hist[(key[j] >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t bin, left;
+            radix_pick(hist, s_remaining, bin, left);
+            if (tid == 0) { s_prefix = prefix | (bin << shift); s_remaining = left; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { const uint32_t kb = s_prefix; tau[row] = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb); }
+}
+
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st)
 {
+    if (n_blocks % 4 == 0 && n_blocks <= 32 * kThrThreads) {
+        if (n_blocks <= 8 * kThrThreads) row_threshold_reg_kernel<8><<<n_rows, kThrThreads, 0, st>>>(rowmax, n_blocks, n_target, tau);
+        else if (n_blocks <= 16 * kThrThreads) row_threshold_reg_kernel<16><<<n_rows, kThrThreads, 0, st>>>(rowmax, n_blocks, n_target, tau);
+        else row_threshold_reg_kernel<32><<<n_rows, kThrThreads, 0, st>>>(rowmax, n_blocks, n_target, tau);
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)n_blocks * 4;
     const int staged = smem <= 200 * 1024 && n_blocks % 4 == 0;
     if (staged) {
