@@ -1,9 +1,10 @@
 """Summarise an ncu report per CUDA source line (stall samples + warp instructions executed).
-usage: python profiles/ncu_by_line.py report.ncu-rep [top]      (needs -lineinfo and --import-source on)"""
+usage: python profiles/ncu_by_line.py report.ncu-rep [top] [kernel-name-substring]   (needs -lineinfo and --import-source on)"""
 import csv, io, os, subprocess, sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+only = sys.argv[3] if len(sys.argv) > 3 else None
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur_file, hdr, agg, seen_fn = "?", None, [], None
@@ -13,7 +14,7 @@ for r in rows:
     if r[0] == "File Path":
         cur_file = os.path.basename(r[1]); continue
     if r[0] == "Function Name":
-        if seen_fn is None:
+        if seen_fn is None and (only is None or only in r[1]):
             seen_fn = r[1]
         fn = r[1]; continue
     if r[0] == "Line No":

@@ -741,13 +741,14 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_kernel(const float*
 
 // Register-resident variant for rows of at most 1024 * KPT bounds (the common case): every thread keeps its KPT keys in
 // registers for all four passes, so a pass costs ~5 instructions per key (the kernel is issue-bound, not memory-bound).
-// Pass 0 folds a thread's run of equal leading bytes locally and then once per warp (match_any + redux): the leading
-// byte (sign + 7 exponent bits) is shared by almost all keys of a row and would serialise plain shared-memory atomics.
+// Pass 0 folds a thread's run of equal leading bytes locally and counts into per-warp private histograms: the leading
+// byte (sign + 7 exponent bits) is shared by almost all keys of a row and would serialise block-wide atomics.
 template <int KPT>
 __global__ void __launch_bounds__(kThrThreads) row_threshold_reg_kernel(const float* __restrict__ rowmax, int n_blocks, const int* __restrict__ n_target,
                                                                         float* __restrict__ tau)
 {
     __shared__ uint32_t hist[256];
+    __shared__ uint32_t whist[(kThrThreads / 32) * 256];
     __shared__ uint32_t s_prefix, s_remaining;
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int want = n_target[row];
@@ -769,15 +770,24 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_reg_kernel(const fl
         __syncthreads();
         const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
         if (pass == 0) {
+            // per-warp private histograms: same-bin updates only ever meet the 31 other lanes of their own warp
+            uint32_t* mine = whist + (tid >> 5) * 256;
+            for (int k = lane; k < 256; k += 32) mine[k] = 0u;
+            __syncwarp();
             uint32_t cur = key[0] >> 24, n = 1u;
 #pragma unroll
             for (int j = 1; j < KPT; ++j) {
                 const uint32_t bin = key[j] >> 24;
-                if (bin == cur) ++n; else { atomicAdd(&hist[cur], n); cur = bin; n = 1u; }
+                if (bin == cur) ++n; else { atomicAdd(&mine[cur], n); cur = bin; n = 1u; }
             }
-            const unsigned peers = __match_any_sync(0xffffffffu, cur);
-            const uint32_t total = __reduce_add_sync(peers, n);
-            if (lane == __ffs(peers) - 1) atomicAdd(&hist[cur], total);
+            atomicAdd(&mine[cur], n);
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t sum = 0u;
+#pragma unroll 8
+                for (int w = 0; w < kThrThreads / 32; ++w) sum += whist[w * 256 + tid];
+                hist[tid] = sum;
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < KPT; ++j)
