@@ -395,7 +395,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             dst[0] = lb_even; dst[1] = lb;
                         } else lb_even = lb;
                     } else {
-                        const float thr = tau - sb[c * 32];
+                        // fl(fl(m + b) - b) can exceed m by an ulp: the slack keeps every item that set a pass-1 bound
+                        const float bmax = sb[c * 32];
+                        const float thr = (tau - bmax) - 4.8e-7f * (fabsf(tau) + fabsf(bmax));
                         const float msub[4] = {m0_, m1_, m2_, m3_};
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -739,16 +741,18 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_kernel(const float*
     if (tid == 0) { const uint32_t kb = s_prefix; tau[row] = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb); }
 }
 
-// Register-resident variant for rows of at most 1024 * KPT bounds (the common case): every thread keeps its KPT keys in
-// registers for all four passes, so a pass costs ~5 instructions per key (the kernel is issue-bound, not memory-bound).
+// Register-resident variant (the common case): every thread keeps its KPT keys in registers for all passes, so a pass
+// costs ~5 instructions per key.  The kernel is latency-bound (barriers and the serial bin pick between passes), hence
+// small blocks -- several rows in flight per SM -- and three 8-bit passes instead of four: tau is the lower edge of the
+// 24-bit bucket of the n'-th largest bound, i.e. smaller by < 2^-15 relative, which only makes it more conservative.
 // Pass 0 folds a thread's run of equal leading bytes locally and counts into per-warp private histograms: the leading
 // byte (sign + 7 exponent bits) is shared by almost all keys of a row and would serialise block-wide atomics.
-template <int KPT>
-__global__ void __launch_bounds__(kThrThreads) row_threshold_reg_kernel(const float* __restrict__ rowmax, int n_blocks, const int* __restrict__ n_target,
-                                                                        float* __restrict__ tau)
+template <int THREADS, int KPT>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) row_threshold_reg_kernel(const float* __restrict__ rowmax, int n_blocks, const int* __restrict__ n_target,
+                                                                    float* __restrict__ tau)
 {
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t whist[(kThrThreads / 32) * 256];
+    __shared__ uint32_t whist[(THREADS / 32) * 256];
     __shared__ uint32_t s_prefix, s_remaining;
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int want = n_target[row];
@@ -757,20 +761,19 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_reg_kernel(const fl
     uint32_t key[KPT];
 #pragma unroll
     for (int j = 0; j < KPT / 4; ++j) {
-        const int q = j * kThrThreads + tid;
+        const int q = j * THREADS + tid;
         const bool inb = q < n_blocks / 4;
         const float4 x = inb ? __ldg(v4 + q) : zero4();
         key[4 * j] = inb ? ord_key(x.x) : 0u; key[4 * j + 1] = inb ? ord_key(x.y) : 0u;      // 0 sorts below every real key
         key[4 * j + 2] = inb ? ord_key(x.z) : 0u; key[4 * j + 3] = inb ? ord_key(x.w) : 0u;
     }
     if (tid == 0) { s_prefix = 0u; s_remaining = (uint32_t)want; }
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < 3; ++pass) {
         const int shift = 24 - 8 * pass;
-        if (tid < 256) hist[tid] = 0u;
+        for (int k = tid; k < 256; k += THREADS) hist[k] = 0u;
         __syncthreads();
         const uint32_t prefix = s_prefix, pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
         if (pass == 0) {
-            // per-warp private histograms: same-bin updates only ever meet the 31 other lanes of their own warp
             uint32_t* mine = whist + (tid >> 5) * 256;
             for (int k = lane; k < 256; k += 32) mine[k] = 0u;
             __syncwarp();
@@ -782,11 +785,11 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_reg_kernel(const fl
             }
             atomicAdd(&mine[cur], n);
             __syncthreads();
-            if (tid < 256) {
+            for (int k = tid; k < 256; k += THREADS) {
                 uint32_t sum = 0u;
 #pragma unroll 8
-                for (int w = 0; w < kThrThreads / 32; ++w) sum += whist[w * 256 + tid];
-                hist[tid] = sum;
+                for (int w = 0; w < THREADS / 32; ++w) sum += whist[w * 256 + k];
+                hist[k] = sum;
             }
         } else {
 #pragma unroll
@@ -801,15 +804,16 @@ __global__ void __launch_bounds__(kThrThreads) row_threshold_reg_kernel(const fl
         }
         __syncthreads();
     }
+    // low 8 key bits left at zero: for either sign that decodes to a value <= every float of the bucket
     if (tid == 0) { const uint32_t kb = s_prefix; tau[row] = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb); }
 }
 
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st)
 {
-    if (n_blocks % 4 == 0 && n_blocks <= 32 * kThrThreads) {
-        if (n_blocks <= 8 * kThrThreads) row_threshold_reg_kernel<8><<<n_rows, kThrThreads, 0, st>>>(rowmax, n_blocks, n_target, tau);
-        else if (n_blocks <= 16 * kThrThreads) row_threshold_reg_kernel<16><<<n_rows, kThrThreads, 0, st>>>(rowmax, n_blocks, n_target, tau);
-        else row_threshold_reg_kernel<32><<<n_rows, kThrThreads, 0, st>>>(rowmax, n_blocks, n_target, tau);
+    if (n_blocks % 4 == 0 && n_blocks <= 32 * 1024) {
+        if (n_blocks <= 32 * 256) row_threshold_reg_kernel<256, 32><<<n_rows, 256, 0, st>>>(rowmax, n_blocks, n_target, tau);
+        else if (n_blocks <= 32 * 512) row_threshold_reg_kernel<512, 32><<<n_rows, 512, 0, st>>>(rowmax, n_blocks, n_target, tau);
+        else row_threshold_reg_kernel<1024, 32><<<n_rows, 1024, 0, st>>>(rowmax, n_blocks, n_target, tau);
         return cudaGetLastError();
     }
     const size_t smem = (size_t)n_blocks * 4;

@@ -464,19 +464,38 @@ def test_recommend_tensor_core_path_matches_exact_path(gpu_lib, F, P, Q, filt, m
                 assert not set(row.astype(int).tolist()) & set(ui[int(u)].tolist())
 
 
+def _sparse_scoring_session(U, I, F, seed, mutate=None):
+    """like _scoring_session, but with short user histories (the planner sends users with long ones to the exact path)"""
+    rng = np.random.default_rng(seed)
+    w = init_weights(U, I, F, seed=seed, sigma=0.3)
+    w['w_i'][:] = rng.normal(0, 0.5, I).astype(np.float32)
+    if mutate:
+        mutate(w)
+    x_uf, x_if = features(U, I, 0, 0)
+    X = np.unique(np.stack([rng.integers(0, U, 10 * U), rng.integers(0, I, 10 * U)], 1), axis=0).astype(np.int32)
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    keep = []
+    prob = _rankfm.fit_problem(X, np.ones(len(X), np.float32), ui, x_uf, x_if, *[w[k] for k in WEIGHTS], 0.01, 0.1, 0.1, 'constant', 0.25, 1, keep=keep)
+    return _rankfm.Session(prob, keep), ui
+
+
 def test_recommend_tensor_core_eighth_of_catalogue(gpu_lib, monkeypatch):
     """a catalogue large enough for pass 1 to visit only the highest-bias 1/8 of the item tiles"""
-    sess, w, ui, x_uf, x_if, U, I = _scoring_session(400, 130000, 24, 0, 0, seed=3)
-    users = np.arange(0, 400, dtype=np.float32)
+    U = 400
+    sess, ui = _sparse_scoring_session(U, 130000, 24, seed=3)
+    users = np.arange(0, U, dtype=np.float32)
     monkeypatch.setenv("RANKFM_B200_RECOMMEND", "exact")
     exact = sess.recommend(users, 20, True)
     monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
     fast = sess.recommend(users, 20, True)
     tc_rows, tc_redone = sess.recommend_stats()
     sess.close()
-    assert tc_rows == 400 and tc_redone == 0, (tc_rows, tc_redone)
+    assert tc_rows == U and tc_redone == 0, (tc_rows, tc_redone)
     assert topk_overlap(fast, exact) >= 0.99
     assert np.mean(fast == exact) >= 0.97
+    for row, u in zip(fast, users):
+        assert not set(row.astype(int).tolist()) & set(ui[int(u)].tolist())
 
 
 @pytest.mark.parametrize("case", ["flat_bias", "all_tied"])
@@ -485,18 +504,12 @@ def test_recommend_tensor_core_degenerate_scores(gpu_lib, case, monkeypatch):
     all_tied: every item identical -> every candidate ties at the cut, slots overflow, rows are redone on the exact path
     and the answer is the exact path's (largest item indexes first, like the reference's reversed argsort)"""
     U, I, F = 200, 40000, 16
-    rng = np.random.default_rng(1)
-    w = init_weights(U, I, F, seed=1, sigma=0.3)
-    w['w_i'][:] = 0.25
-    if case == "all_tied":
-        w['v_i'][:] = w['v_i'][0]
-    x_uf, x_if = features(U, I, 0, 0)
-    X = np.unique(np.stack([rng.integers(0, U, 2000), rng.integers(0, I, 2000)], 1), axis=0).astype(np.int32)
-    indptr, indices = csr_of(X, U)
-    keep = []
-    prob = _rankfm.fit_problem(X, np.ones(len(X), np.float32), CSRItems(indptr, indices), x_uf, x_if, *[w[k] for k in WEIGHTS],
-                               0.01, 0.1, 0.1, 'constant', 0.25, 1, keep=keep)
-    sess = _rankfm.Session(prob, keep)
+
+    def mutate(w):
+        w['w_i'][:] = 0.25
+        if case == "all_tied":
+            w['v_i'][:] = w['v_i'][0]
+    sess, _ = _sparse_scoring_session(U, I, F, seed=1, mutate=mutate)
     users = np.arange(U, dtype=np.float32)
     monkeypatch.setenv("RANKFM_B200_RECOMMEND", "exact")
     exact = sess.recommend(users, 10, False)
