@@ -153,6 +153,9 @@ int rfm_session_trace_enable(rfm_session *s);
 int rfm_session_trace_read(rfm_session *s, int32_t *neg_and_sampled /* [N,2] */);
 /* debugging / parity: dense bf16 tensor-core scores (A.B^T + bias) of the requested users against all items */
 int rfm_session_debug_gemm(rfm_session *s, const float *users, int64_t n_users, float *scores_out /* [n_users, I] */);
+/* (re)attach the user_items CSR a scoring session filters with (`filter_previous`, `_rankfm.pyx:450`): lets a caller keep
+ * one session resident across `_predict` / `_recommend` calls instead of re-uploading the weights every call */
+int rfm_session_attach_csr(rfm_session *s, const int64_t *csr_indptr /* [U+1] */, const int32_t *csr_indices /* [nnz] */);
 /* tensor-core recommend bookkeeping since session creation: rows served by the tcgen05 path, and how many of those had to
  * be redone on the exact fp32 path because a candidate slot overflowed */
 int rfm_session_recommend_stats(rfm_session *s, int64_t *tc_rows, int64_t *tc_redone);

@@ -1,5 +1,5 @@
 import sys, time, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
 import numpy as np
 from bench import make_workload, fresh_weights, HYPER, WEIGHTS
 from rankfm_b200 import _rankfm
@@ -11,7 +11,9 @@ def step():
     _rankfm._fit(X, c["sw"], ui, c["x_uf"], c["x_if"], *[ww[k] for k in WEIGHTS], HYPER["alpha"], HYPER["beta"], HYPER["learning_rate"],
                  HYPER["learning_schedule"], HYPER["learning_exponent"], c["max_samples"], c['epochs'], False)
     return time.perf_counter() - t0
-print([round(step()*1e3,1) for _ in range(6)])
-import cProfile, pstats
-cProfile.run('step()', '/tmp/prof.out')
-pstats.Stats('/tmp/prof.out').sort_stats('cumtime').print_stats(12)
+n = int(os.environ.get('E2E_PROBE_STEPS', 6))
+print([round(step()*1e3,1) for _ in range(n)])
+if os.environ.get('E2E_PROBE_PROFILE'):
+    import cProfile, pstats
+    cProfile.run('step()', '/tmp/prof.out')
+    pstats.Stats('/tmp/prof.out').sort_stats('cumtime').print_stats(12)

@@ -1207,6 +1207,17 @@ static int attach_csr(rfm_session* s, const rfm_problem* p)
     return RFM_OK;
 }
 
+extern "C" int rfm_session_attach_csr(rfm_session* s, const int64_t* indptr, const int32_t* indices)
+{
+    if (!s || !indptr || !indices) return fail(RFM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    cudaFree(s->d_indptr); cudaFree(s->d_indices);
+    s->d_indptr = nullptr; s->d_indices = nullptr;
+    rfm_problem q = s->p;
+    q.csr_indptr = indptr; q.csr_indices = indices;
+    return attach_csr(s, &q);
+}
+
 extern "C" int rfm_recommend(const rfm_problem* p, const float* users, int64_t n_users, int32_t n_items, int32_t filter_previous, float* rec_items)
 {
     rfm_problem q = *p;

@@ -526,6 +526,33 @@ def test_recommend_tensor_core_degenerate_scores(gpu_lib, case, monkeypatch):
         assert topk_overlap(fast, exact) >= 0.99
 
 
+def test_resident_scoring_session_across_calls(gpu_lib):
+    """opt-in resident mode: predict/recommend reuse ONE upload of the model until `_fit` changes it"""
+    from rankfm_b200 import RankFM
+    rng = np.random.default_rng(4)
+    X = np.unique(np.stack([rng.integers(0, 300, 6000), rng.integers(100, 500, 6000)], 1), axis=0)
+    model = RankFM(factors=8, loss='warp', max_samples=5)
+    np.random.seed(1)
+    model.fit(X, epochs=2)
+    users = list(range(0, 300, 7)) + [10_000]                        # one unknown user
+    base_p, base_r = model.predict(X[:500]), model.recommend(users, 5, True)
+    _rankfm.set_resident(True)
+    try:
+        n0 = _rankfm._scoring["uploads"]
+        p1, r1 = model.predict(X[:500]), model.recommend(users, 5, True)
+        p2, r2 = model.predict(X[:500]), model.recommend(users, 5, False)
+        assert _rankfm._scoring["uploads"] == n0 + 1
+        assert np.array_equal(p1, base_p) and np.array_equal(p2, base_p)
+        assert r1.equals(base_r) and not r2.equals(base_r)
+        model.fit_partial(X, epochs=1)                                  # trains in place -> the resident copy is dropped
+        p3 = model.predict(X[:500])
+        assert _rankfm._scoring["uploads"] == n0 + 2 and not np.allclose(p3, p1)
+        _rankfm.set_resident(False)
+        assert np.array_equal(model.predict(X[:500]), p3)
+    finally:
+        _rankfm.set_resident(False)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # model quality at the benchmark workload: the Hogwild-trained model ranks held-out interactions like the reference's
 # ---------------------------------------------------------------------------------------------------------------
