@@ -159,6 +159,9 @@ int rfm_session_attach_csr(rfm_session *s, const int64_t *csr_indptr /* [U+1] */
 /* tensor-core recommend bookkeeping since session creation: rows served by the tcgen05 path, and how many of those had to
  * be redone on the exact fp32 path because a candidate slot overflowed */
 int rfm_session_recommend_stats(rfm_session *s, int64_t *tc_rows, int64_t *tc_redone);
+/* the library keeps freed device blocks for the next call of the same shape (one-shot calls create and destroy a session
+ * each; see rfm_api.cu "Device block cache"; limit RANKFM_B200_CACHE_MB, default 4096): give them back to the driver */
+int rfm_trim_device_cache(void);
 int rfm_session_flush_l2(rfm_session *s);                                    /* overwrite a >L2-sized scratch buffer */
 int rfm_session_launch_count(rfm_session *s, int64_t *launches);             /* kernels launched by this session */
 int rfm_session_destroy(rfm_session *s);

@@ -18,7 +18,7 @@ SAMPLER_PHILOX, SAMPLER_MT = 0, 1
 SCHED_PARALLEL, SCHED_SERIAL = 0, 1
 
 EXPORTS = [
-    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_host_register", "rfm_host_unregister", "rfm_debug_philox", "rfm_debug_feistel",
+    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_host_register", "rfm_host_unregister", "rfm_debug_philox", "rfm_debug_feistel", "rfm_trim_device_cache",
     "rfm_fit", "rfm_predict", "rfm_recommend", "rfm_similar",
     "rfm_session_create", "rfm_session_train", "rfm_session_set_weights", "rfm_session_download",
     "rfm_session_snapshot", "rfm_session_restore", "rfm_session_timer_start", "rfm_session_timer_stop",

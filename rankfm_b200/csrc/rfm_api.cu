@@ -9,7 +9,10 @@
 #include <cstring>
 #include <ctime>
 #include <dlfcn.h>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rankfm_b200.h"
@@ -51,6 +54,92 @@ extern "C" int rfm_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device block cache.  The one-shot entry points (`rfm_fit`, `rfm_predict`, `rfm_recommend`: the reference's stateless
+// `_fit` / `_predict` / `_recommend`) create and destroy a session per call; cudaMalloc + cudaFree of its ~15 buffers cost
+// 6-40 ms per call on the cfg2 workload and cudaFree stalled for 100-230 ms every few calls (profiles/: e2e probe,
+// RANKFM_B200_TIMING=1) -- against 22 ms of training.  Freed blocks are therefore kept (exact size classes, up to
+// RANKFM_B200_CACHE_MB, default 4096 MiB per process) and handed back to the next call of the same shape.
+// dev_free() synchronises the device like cudaFree does, so a cached block is never still in use by queued work.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> idle;                   // (device, bytes) -> block
+    std::unordered_map<void*, std::pair<int, size_t>> owner;             // every block handed out or idle
+    size_t idle_bytes = 0;
+    size_t limit() const
+    {
+        static const size_t v = [] { const char* e = getenv("RANKFM_B200_CACHE_MB"); return (size_t)(e ? atoll(e) : 4096) << 20; }();
+        return v;
+    }
+};
+BlockCache g_blocks;
+
+size_t size_class(size_t bytes) { const size_t g = bytes >= ((size_t)1 << 20) ? ((size_t)1 << 20) : 4096; return (bytes + g - 1) / g * g; }
+
+void trim_locked(int dev)
+{
+    for (auto it = g_blocks.idle.begin(); it != g_blocks.idle.end();) {
+        if (dev >= 0 && it->first.first != dev) { ++it; continue; }
+        g_blocks.idle_bytes -= it->first.second;
+        g_blocks.owner.erase(it->second);
+        cudaFree(it->second);
+        it = g_blocks.idle.erase(it);
+    }
+}
+}  // namespace
+
+static cudaError_t dev_malloc(void** out, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t cls = size_class(bytes ? bytes : 1);
+    std::lock_guard<std::mutex> lock(g_blocks.mu);
+    auto it = g_blocks.idle.find({dev, cls});
+    if (it != g_blocks.idle.end()) {
+        *out = it->second;
+        g_blocks.idle_bytes -= cls;
+        g_blocks.idle.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, cls);
+    if (e == cudaErrorMemoryAllocation) {                                // give the idle blocks back and try once more
+        cudaGetLastError();
+        trim_locked(dev);
+        e = cudaMalloc(out, cls);
+    }
+    if (e == cudaSuccess) g_blocks.owner[*out] = {dev, cls};
+    return e;
+}
+
+static void dev_free(void* p)
+{
+    if (!p) return;
+    std::unique_lock<std::mutex> lock(g_blocks.mu);
+    auto it = g_blocks.owner.find(p);
+    if (it == g_blocks.owner.end()) { lock.unlock(); cudaFree(p); return; }
+    const int dev = it->second.first;
+    const size_t cls = it->second.second;
+    if (g_blocks.idle_bytes + cls > g_blocks.limit()) { g_blocks.owner.erase(it); lock.unlock(); cudaFree(p); return; }
+    lock.unlock();
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != dev) cudaSetDevice(dev);
+    cudaDeviceSynchronize();                                              // what cudaFree would have waited for
+    if (cur != dev) cudaSetDevice(cur);
+    lock.lock();
+    g_blocks.idle.insert({{dev, cls}, p});
+    g_blocks.idle_bytes += cls;
+}
+
+extern "C" int rfm_trim_device_cache(void)
+{
+    std::lock_guard<std::mutex> lock(g_blocks.mu);
+    trim_locked(-1);
+    return RFM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -191,7 +280,7 @@ static int dev_alloc(T** out, size_t n)
 {
     *out = nullptr;
     if (n == 0) n = 1;
-    CU(cudaMalloc((void**)out, n * sizeof(T)));
+    CU(dev_malloc((void**)out, n * sizeof(T)));
     return RFM_OK;
 }
 
@@ -202,7 +291,7 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) dev_free(p); }
     int alloc(size_t n) { return dev_alloc(&p, n); }
     operator T*() const { return p; }
 };
@@ -243,13 +332,13 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     cudaSetDevice(s->device);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (auto e : s->ev) cudaEventDestroy(e);
-    cudaFree(s->T.UT); cudaFree(s->T.IT); cudaFree(s->T.GP);
-    cudaFree(s->d_inter); cudaFree(s->d_sw); cudaFree(s->d_indptr); cudaFree(s->d_indices);
-    cudaFree(s->d_bitmap); cudaFree(s->d_perm); cudaFree(s->d_mult); cudaFree(s->d_mt); cudaFree(s->d_acc);
-    cudaFree(s->d_it_snap); cudaFree(s->d_gp_snap); cudaFree(s->d_ut_init); cudaFree(s->d_flush); cudaFree(s->d_gp_acc); cudaFree(s->d_item_touch); cudaFree(s->d_xuf); cudaFree(s->d_xif);
-    cudaFree(s->d_snap_ut); cudaFree(s->d_snap_it); cudaFree(s->d_snap_gp); cudaFree(s->d_trace);
-    cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias); cudaFree(s->d_gemm_order);
-    for (void* q : s->scratch) cudaFree(q);
+    dev_free(s->T.UT); dev_free(s->T.IT); dev_free(s->T.GP);
+    dev_free(s->d_inter); dev_free(s->d_sw); dev_free(s->d_indptr); dev_free(s->d_indices);
+    dev_free(s->d_bitmap); dev_free(s->d_perm); dev_free(s->d_mult); dev_free(s->d_mt); dev_free(s->d_acc);
+    dev_free(s->d_it_snap); dev_free(s->d_gp_snap); dev_free(s->d_ut_init); dev_free(s->d_flush); dev_free(s->d_gp_acc); dev_free(s->d_item_touch); dev_free(s->d_xuf); dev_free(s->d_xif);
+    dev_free(s->d_snap_ut); dev_free(s->d_snap_it); dev_free(s->d_snap_gp); dev_free(s->d_trace);
+    dev_free(s->d_gemm_B); dev_free(s->d_gemm_bias); dev_free(s->d_gemm_order);
+    for (void* q : s->scratch) dev_free(q);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
     if (s->st) cudaStreamDestroy(s->st);
@@ -594,7 +683,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     if (p.schedule != RFM_SCHEDULE_CONSTANT && p.schedule != RFM_SCHEDULE_INVSCALING) return fail(RFM_ERR_ARG, "unknown [learning_schedule]");
     CU(cudaSetDevice(s->device));
     if (s->acc_cap < epochs) {
-        cudaFree(s->d_acc);
+        dev_free(s->d_acc);
         int rc = dev_alloc(&s->d_acc, (size_t)epochs);
         if (rc) return rc;
         s->acc_cap = epochs;
@@ -781,9 +870,9 @@ static int scratch_get(rfm_session* s, int slot, size_t count, T** out)
 {
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     if (s->scratch_bytes[slot] < bytes) {
-        cudaFree(s->scratch[slot]);
+        dev_free(s->scratch[slot]);
         s->scratch[slot] = nullptr; s->scratch_bytes[slot] = 0;
-        CU(cudaMalloc(&s->scratch[slot], bytes));
+        CU(dev_malloc(&s->scratch[slot], bytes));
         s->scratch_bytes[slot] = bytes;
     }
     *out = reinterpret_cast<T*>(s->scratch[slot]);
@@ -835,9 +924,9 @@ static int ensure_gemm_items(rfm_session* s)
     const int I_pad = (T.I + BN - 1) / BN * BN;
     if (s->gemm_valid && s->gemm_I_pad == I_pad) return RFM_OK;
     if (!s->d_gemm_B || s->gemm_I_pad != I_pad) {
-        cudaFree(s->d_gemm_B); cudaFree(s->d_gemm_bias); cudaFree(s->d_gemm_order);
+        dev_free(s->d_gemm_B); dev_free(s->d_gemm_bias); dev_free(s->d_gemm_order);
         s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr; s->d_gemm_order = nullptr;
-        CU(cudaMalloc(&s->d_gemm_B, (size_t)I_pad * Kp * 2));
+        CU(dev_malloc(&s->d_gemm_B, (size_t)I_pad * Kp * 2));
         int rc = dev_alloc(&s->d_gemm_bias, (size_t)I_pad);
         if (rc) return rc;
         if ((rc = dev_alloc(&s->d_gemm_order, (size_t)I_pad))) return rc;
@@ -908,7 +997,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr;
     float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr; int* d_flag = nullptr;
-    auto done = [&](int code) { cudaFree(d_fix); cudaFree(d_fix_users); return code; };
+    auto done = [&](int code) { dev_free(d_fix); dev_free(d_fix_users); return code; };
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
     if ((rc = scratch_get(s, 2, (size_t)rows_alloc, &d_ntgt))) return rc;
     if ((rc = scratch_get(s, 3, (size_t)rows_alloc, &d_tau))) return rc;
@@ -948,7 +1037,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
             if (flag_h[(size_t)r]) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); }
         s->tc_rows += nb; s->tc_redo += (int64_t)redo_users.size();
         if (!redo_users.empty()) {
-            cudaFree(d_fix); cudaFree(d_fix_users); d_fix = nullptr; d_fix_users = nullptr;
+            dev_free(d_fix); dev_free(d_fix_users); d_fix = nullptr; d_fix_users = nullptr;
             if ((rc = dev_alloc(&d_fix_users, redo_users.size()))) return done(rc);
             if ((rc = dev_alloc(&d_fix, redo_users.size() * n_items))) return done(rc);
             CU(cudaMemcpyAsync(d_fix_users, redo_users.data(), redo_users.size() * 4, cudaMemcpyHostToDevice, s->st));
@@ -1135,7 +1224,7 @@ extern "C" int rfm_session_flush_l2(rfm_session* s)
     CU(cudaSetDevice(s->device));
     if (!s->d_flush) {
         s->flush_bytes = (size_t)512 << 20;   // 4x the 126 MB L2
-        CU(cudaMalloc((void**)&s->d_flush, s->flush_bytes));
+        CU(dev_malloc((void**)&s->d_flush, s->flush_bytes));
     }
     CU(cudaMemsetAsync(s->d_flush, 0x5a, s->flush_bytes, s->st));
     CU(cudaStreamSynchronize(s->st));
@@ -1211,7 +1300,7 @@ extern "C" int rfm_session_attach_csr(rfm_session* s, const int64_t* indptr, con
 {
     if (!s || !indptr || !indices) return fail(RFM_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
-    cudaFree(s->d_indptr); cudaFree(s->d_indices);
+    dev_free(s->d_indptr); dev_free(s->d_indices);
     s->d_indptr = nullptr; s->d_indices = nullptr;
     rfm_problem q = s->p;
     q.csr_indptr = indptr; q.csr_indices = indices;
@@ -1245,7 +1334,7 @@ extern "C" int rfm_similar(const rfm_problem* p, int32_t which, int32_t index, i
     if (rc) return rc;
     float *qvec = nullptr, *S = nullptr, *d_rec = nullptr;
     int32_t *d_one = nullptr, *d_ex = nullptr;
-    auto done = [&](int code) { cudaFree(qvec); cudaFree(S); cudaFree(d_rec); cudaFree(d_one); cudaFree(d_ex); rfm_session_destroy(s); return code; };
+    auto done = [&](int code) { dev_free(qvec); dev_free(S); dev_free(d_rec); dev_free(d_one); dev_free(d_ex); rfm_session_destroy(s); return code; };
     if ((rc = dev_alloc(&qvec, (size_t)s->T.Fp))) return done(rc);
     if ((rc = dev_alloc(&S, (size_t)rows))) return done(rc);
     if ((rc = dev_alloc(&d_rec, (size_t)n))) return done(rc);
