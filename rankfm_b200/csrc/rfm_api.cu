@@ -234,7 +234,7 @@ struct rfm_session {
     rfm_problem p{};            // host pointers are NOT retained past create (copied fields only)
     Tables T{};
     int device = 0, n_sm = 148;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;   // st2: second stream of the recommend pipeline (shortlist of batch b || GEMM of batch b+1)
     // data
     int2* d_inter = nullptr; float* d_sw = nullptr; int64_t* d_indptr = nullptr; int32_t* d_indices = nullptr;
     int64_t N = 0, nnz = 0;
@@ -341,6 +341,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     for (void* q : s->scratch) dev_free(q);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
+    if (s->st2) cudaStreamDestroy(s->st2);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return RFM_OK;
@@ -995,59 +996,86 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)4 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
     const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
+    // Two-deep software pipeline over the user batches: the shortlist kernel of batch b (gathers and per-row selection,
+    // memory- and latency-bound) runs on a second stream while the tensor cores work on batch b+1.  Candidate buffers are
+    // double-buffered; targets of all batches are uploaded once and the redo flags of all rows read once, so the loop
+    // never synchronises with the host.
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr;
     float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr; int* d_flag = nullptr;
-    auto done = [&](int code) { dev_free(d_fix); dev_free(d_fix_users); return code; };
+    const int64_t n_batches = (n_users + rows_alloc - 1) / rows_alloc;
+    const size_t cand_per_buf = (size_t)rows_alloc * width, cnt_per_buf = (size_t)rows_alloc * split_cap * SPS;
+    std::vector<cudaEvent_t> ev;                                     // [0..1] GEMM of buffer done, [2..3] shortlist of buffer done, then timing pairs
+    auto done = [&](int code) { dev_free(d_fix); dev_free(d_fix_users); for (auto e : ev) cudaEventDestroy(e); return code; };
+    if (!s->st2) CU(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
-    if ((rc = scratch_get(s, 2, (size_t)rows_alloc, &d_ntgt))) return rc;
+    if ((rc = scratch_get(s, 2, (size_t)n_batches * rows_alloc, &d_ntgt))) return rc;
     if ((rc = scratch_get(s, 3, (size_t)rows_alloc, &d_tau))) return rc;
     if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub1, &d_rowmax))) return rc;
-    if ((rc = scratch_get(s, 5, (size_t)rows_alloc * width, &d_cand))) return rc;
-    if ((rc = scratch_get(s, 6, (size_t)rows_alloc * split_cap * SPS, &d_cnt))) return rc;
-    if ((rc = scratch_get(s, 9, (size_t)rows_alloc, &d_flag))) return rc;
-    std::vector<int> ntgt((size_t)rows_alloc), flag_h;
-    cudaEvent_t a = nullptr, b = nullptr;
-    if (gemm_ms) { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
-    for (int64_t off = 0; off < n_users; off += rows_alloc) {
+    if ((rc = scratch_get(s, 5, 2 * cand_per_buf, &d_cand))) return rc;
+    if ((rc = scratch_get(s, 6, 2 * cnt_per_buf, &d_cnt))) return rc;
+    if ((rc = scratch_get(s, 9, (size_t)n_users, &d_flag))) return rc;
+    std::vector<int> ntgt((size_t)(n_batches * rows_alloc));
+    for (int64_t bi = 0; bi < n_batches; ++bi)
+        for (int64_t r = 0; r < rows_alloc; ++r) {
+            const int64_t k = bi * rows_alloc + r;
+            ntgt[(size_t)k] = shortlist_target(s, k < n_users ? h_users[k] : -1, n_items, filter_previous);
+        }
+    CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), ntgt.size() * 4, cudaMemcpyHostToDevice, s->st));
+    for (int k = 0; k < 4; ++k) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return done(fail(RFM_ERR_CUDA, "cudaEventCreate failed")); ev.push_back(e); }
+    for (int64_t bi = 0; bi < n_batches; ++bi) {
+        const int64_t off = bi * rows_alloc;
+        const int buf = (int)(bi & 1);
         const int nb = (int)std::min<int64_t>(rows_alloc, n_users - off);
         const int M_pad = (nb + MT - 1) / MT * MT;
         const int n_splits = std::max(1, std::min(split_cap, s->n_sm / (M_pad / MT)));
         const int slots = n_splits * SPS, cap = width / slots;
-        for (int r = 0; r < M_pad; ++r) ntgt[(size_t)r] = shortlist_target(s, r < nb ? h_users[off + r] : -1, n_items, filter_previous);
-        CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), (size_t)M_pad * 4, cudaMemcpyHostToDevice, s->st));
+        float2* cand = d_cand + (size_t)buf * cand_per_buf;
+        int* cnt = d_cnt + (size_t)buf * cnt_per_buf;
+        const int* tgt = d_ntgt + (size_t)off;
+        if (bi >= 2) CU(cudaStreamWaitEvent(s->st, ev[2 + buf], 0));            // the shortlist of batch bi-2 has drained this buffer
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
-        if (gemm_ms) CU(cudaEventRecord(a, s->st));
+        if (gemm_ms) {
+            cudaEvent_t ta, tb;
+            if (cudaEventCreate(&ta) != cudaSuccess || cudaEventCreate(&tb) != cudaSuccess) return done(fail(RFM_ERR_CUDA, "cudaEventCreate failed"));
+            ev.push_back(ta); ev.push_back(tb);
+            CU(cudaEventRecord(ta, s->st));
+        }
         cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, tau_subset_head() ? -stride : stride, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
-        CU(launch_row_threshold(d_rowmax, M_pad, n_sub1, d_ntgt, d_tau, s->st));
-        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, d_cand, d_cnt, d_tau, cap, nullptr, nullptr, s->st);
+        e = launch_row_threshold(d_rowmax, M_pad, n_sub1, tgt, d_tau, s->st);
+        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "row_threshold launch failed: %s", cudaGetErrorString(e)));
+        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, cand, cnt, d_tau, cap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
-        if (gemm_ms) CU(cudaEventRecord(b, s->st));
-        e = launch_shortlist(T, d_users + off, nb, d_cand, d_cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, d_ntgt, s->d_indptr, s->d_indices, filter_previous,
-                             n_items, d_rec + (size_t)off * n_items, d_flag, s->st);
+        if (gemm_ms) CU(cudaEventRecord(ev.back(), s->st));
+        CU(cudaEventRecord(ev[buf], s->st));
+        CU(cudaStreamWaitEvent(s->st2, ev[buf], 0));
+        e = launch_shortlist(T, d_users + off, nb, cand, cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
+                             n_items, d_rec + (size_t)off * n_items, d_flag + off, s->st2);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e)));
+        CU(cudaEventRecord(ev[2 + buf], s->st2));
         s->launches += 5;
-        // rows whose candidates overflowed (pathological ties / clustered scores) are redone on the exact path
-        flag_h.resize((size_t)nb);
-        CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->st));
-        CU(cudaStreamSynchronize(s->st));
-        if (gemm_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); *gemm_ms += ms; }
-        std::vector<int32_t> redo_users; std::vector<int> redo_rows;
-        for (int r = 0; r < nb; ++r)
-            if (flag_h[(size_t)r]) { redo_users.push_back(h_users[off + r]); redo_rows.push_back(r); }
-        s->tc_rows += nb; s->tc_redo += (int64_t)redo_users.size();
-        if (!redo_users.empty()) {
-            dev_free(d_fix); dev_free(d_fix_users); d_fix = nullptr; d_fix_users = nullptr;
-            if ((rc = dev_alloc(&d_fix_users, redo_users.size()))) return done(rc);
-            if ((rc = dev_alloc(&d_fix, redo_users.size() * n_items))) return done(rc);
-            CU(cudaMemcpyAsync(d_fix_users, redo_users.data(), redo_users.size() * 4, cudaMemcpyHostToDevice, s->st));
-            if ((rc = recommend_exact(s, d_fix_users, (int64_t)redo_users.size(), n_items, filter_previous, d_fix, nullptr))) return done(rc);
-            for (size_t k = 0; k < redo_rows.size(); ++k)
-                CU(cudaMemcpyAsync(d_rec + (size_t)(off + redo_rows[k]) * n_items, d_fix + k * n_items, (size_t)n_items * 4, cudaMemcpyDeviceToDevice, s->st));
-            CU(cudaStreamSynchronize(s->st));
-        }
     }
-    if (gemm_ms) { cudaEventDestroy(a); cudaEventDestroy(b); }
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaStreamSynchronize(s->st2));
+    if (gemm_ms)
+        for (size_t k = 4; k + 1 < ev.size(); k += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); *gemm_ms += ms; }
+    // rows whose candidates overflowed (pathological ties / clustered scores) are redone on the exact path
+    std::vector<int> flag_h((size_t)n_users);
+    CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)n_users * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    std::vector<int32_t> redo_users; std::vector<int64_t> redo_rows;
+    for (int64_t r = 0; r < n_users; ++r)
+        if (flag_h[(size_t)r]) { redo_users.push_back(h_users[r]); redo_rows.push_back(r); }
+    s->tc_rows += n_users; s->tc_redo += (int64_t)redo_users.size();
+    if (!redo_users.empty()) {
+        if ((rc = dev_alloc(&d_fix_users, redo_users.size()))) return done(rc);
+        if ((rc = dev_alloc(&d_fix, redo_users.size() * n_items))) return done(rc);
+        CU(cudaMemcpyAsync(d_fix_users, redo_users.data(), redo_users.size() * 4, cudaMemcpyHostToDevice, s->st));
+        if ((rc = recommend_exact(s, d_fix_users, (int64_t)redo_users.size(), n_items, filter_previous, d_fix, nullptr))) return done(rc);
+        for (size_t k = 0; k < redo_rows.size(); ++k)
+            CU(cudaMemcpyAsync(d_rec + (size_t)redo_rows[k] * n_items, d_fix + k * n_items, (size_t)n_items * 4, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));
+    }
     return done(RFM_OK);
 }
 

@@ -498,6 +498,27 @@ def test_recommend_tensor_core_eighth_of_catalogue(gpu_lib, monkeypatch):
         assert not set(row.astype(int).tolist()) & set(ui[int(u)].tolist())
 
 
+def test_recommend_tensor_core_many_batches(gpu_lib, monkeypatch):
+    """more users than one wave of CTAs holds: the batches are pipelined over two streams (shortlist of batch b next to the
+    GEMM of batch b+1, double-buffered candidates); rows from every batch must match the exact path"""
+    U = 45000
+    sess, ui = _sparse_scoring_session(U, 33000, 16, seed=11)
+    users = np.arange(U, dtype=np.float32)
+    users[[7, 20000, 44999]] = np.nan
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    fast = sess.recommend(users, 10, True)
+    tc_rows, tc_redone = sess.recommend_stats()
+    sample = np.concatenate([np.arange(0, 300), np.arange(18800, 19100), np.arange(37700, 38000), np.arange(U - 300, U)])
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "exact")
+    exact = sess.recommend(users[sample], 10, True)
+    sess.close()
+    assert tc_rows == U and tc_redone <= U // 100, (tc_rows, tc_redone)
+    assert np.array_equal(np.isnan(fast[sample]), np.isnan(exact))
+    assert topk_overlap(fast[sample], exact) >= 0.99
+    assert np.mean(fast[sample][~np.isnan(exact)] == exact[~np.isnan(exact)]) >= 0.97
+    assert np.isnan(fast[[7, 20000, 44999]]).all()
+
+
 @pytest.mark.parametrize("case", ["flat_bias", "all_tied"])
 def test_recommend_tensor_core_degenerate_scores(gpu_lib, case, monkeypatch):
     """flat_bias: every item bias equal (bias order degenerates to item order) -> still served by the tensor-core path;
