@@ -234,7 +234,7 @@ struct rfm_session {
     rfm_problem p{};            // host pointers are NOT retained past create (copied fields only)
     Tables T{};
     int device = 0, n_sm = 148;
-    cudaStream_t st = nullptr, st2 = nullptr;   // st2: second stream of the recommend pipeline (shortlist of batch b || GEMM of batch b+1)
+    cudaStream_t st = nullptr;
     // data
     int2* d_inter = nullptr; float* d_sw = nullptr; int64_t* d_indptr = nullptr; int32_t* d_indices = nullptr;
     int64_t N = 0, nnz = 0;
@@ -341,7 +341,6 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     for (void* q : s->scratch) dev_free(q);
     if (s->t0) cudaEventDestroy(s->t0);
     if (s->t1) cudaEventDestroy(s->t1);
-    if (s->st2) cudaStreamDestroy(s->st2);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return RFM_OK;
@@ -996,23 +995,22 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)4 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
     const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
-    // Two-deep software pipeline over the user batches: the shortlist kernel of batch b (gathers and per-row selection,
-    // memory- and latency-bound) runs on a second stream while the tensor cores work on batch b+1.  Candidate buffers are
-    // double-buffered; targets of all batches are uploaded once and the redo flags of all rows read once, so the loop
-    // never synchronises with the host.
+    // The user batches run back to back on the session's stream; targets of all batches are uploaded once and the redo
+    // flags of all rows are read once, so the loop never synchronises with the host.  (Running the shortlist kernel of
+    // batch b on a second stream next to the GEMM of batch b+1 was measured and bought nothing: a GEMM CTA holds ~200 KB
+    // of an SM's shared memory, so shortlist blocks cannot co-reside with it and only delay the next wave -- GEMM + filter
+    // 6.2 -> 8.3 ms per 65,536 users for the same 9.0 ms total.)
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr;
     float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr; int* d_flag = nullptr;
     const int64_t n_batches = (n_users + rows_alloc - 1) / rows_alloc;
-    const size_t cand_per_buf = (size_t)rows_alloc * width, cnt_per_buf = (size_t)rows_alloc * split_cap * SPS;
-    std::vector<cudaEvent_t> ev;                                     // [0..1] GEMM of buffer done, [2..3] shortlist of buffer done, then timing pairs
+    std::vector<cudaEvent_t> ev;                                     // timing pairs (GEMM + filter of each batch)
     auto done = [&](int code) { dev_free(d_fix); dev_free(d_fix_users); for (auto e : ev) cudaEventDestroy(e); return code; };
-    if (!s->st2) CU(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
     if ((rc = scratch_get(s, 2, (size_t)n_batches * rows_alloc, &d_ntgt))) return rc;
     if ((rc = scratch_get(s, 3, (size_t)rows_alloc, &d_tau))) return rc;
     if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub1, &d_rowmax))) return rc;
-    if ((rc = scratch_get(s, 5, 2 * cand_per_buf, &d_cand))) return rc;
-    if ((rc = scratch_get(s, 6, 2 * cnt_per_buf, &d_cnt))) return rc;
+    if ((rc = scratch_get(s, 5, (size_t)rows_alloc * width, &d_cand))) return rc;
+    if ((rc = scratch_get(s, 6, (size_t)rows_alloc * split_cap * SPS, &d_cnt))) return rc;
     if ((rc = scratch_get(s, 9, (size_t)n_users, &d_flag))) return rc;
     std::vector<int> ntgt((size_t)(n_batches * rows_alloc));
     for (int64_t bi = 0; bi < n_batches; ++bi)
@@ -1021,18 +1019,15 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
             ntgt[(size_t)k] = shortlist_target(s, k < n_users ? h_users[k] : -1, n_items, filter_previous);
         }
     CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), ntgt.size() * 4, cudaMemcpyHostToDevice, s->st));
-    for (int k = 0; k < 4; ++k) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return done(fail(RFM_ERR_CUDA, "cudaEventCreate failed")); ev.push_back(e); }
     for (int64_t bi = 0; bi < n_batches; ++bi) {
         const int64_t off = bi * rows_alloc;
-        const int buf = (int)(bi & 1);
         const int nb = (int)std::min<int64_t>(rows_alloc, n_users - off);
         const int M_pad = (nb + MT - 1) / MT * MT;
         const int n_splits = std::max(1, std::min(split_cap, s->n_sm / (M_pad / MT)));
         const int slots = n_splits * SPS, cap = width / slots;
-        float2* cand = d_cand + (size_t)buf * cand_per_buf;
-        int* cnt = d_cnt + (size_t)buf * cnt_per_buf;
+        float2* cand = d_cand;
+        int* cnt = d_cnt;
         const int* tgt = d_ntgt + (size_t)off;
-        if (bi >= 2) CU(cudaStreamWaitEvent(s->st, ev[2 + buf], 0));            // the shortlist of batch bi-2 has drained this buffer
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
         if (gemm_ms) {
             cudaEvent_t ta, tb;
@@ -1047,18 +1042,14 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, cand, cnt, d_tau, cap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
         if (gemm_ms) CU(cudaEventRecord(ev.back(), s->st));
-        CU(cudaEventRecord(ev[buf], s->st));
-        CU(cudaStreamWaitEvent(s->st2, ev[buf], 0));
         e = launch_shortlist(T, d_users + off, nb, cand, cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
-                             n_items, d_rec + (size_t)off * n_items, d_flag + off, s->st2);
+                             n_items, d_rec + (size_t)off * n_items, d_flag + off, s->st);
         if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e)));
-        CU(cudaEventRecord(ev[2 + buf], s->st2));
         s->launches += 5;
     }
     CU(cudaStreamSynchronize(s->st));
-    CU(cudaStreamSynchronize(s->st2));
     if (gemm_ms)
-        for (size_t k = 4; k + 1 < ev.size(); k += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); *gemm_ms += ms; }
+        for (size_t k = 0; k + 1 < ev.size(); k += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); *gemm_ms += ms; }
     // rows whose candidates overflowed (pathological ties / clustered scores) are redone on the exact path
     std::vector<int> flag_h((size_t)n_users);
     CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)n_users * 4, cudaMemcpyDeviceToHost, s->st));

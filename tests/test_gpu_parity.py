@@ -499,8 +499,8 @@ def test_recommend_tensor_core_eighth_of_catalogue(gpu_lib, monkeypatch):
 
 
 def test_recommend_tensor_core_many_batches(gpu_lib, monkeypatch):
-    """more users than one wave of CTAs holds: the batches are pipelined over two streams (shortlist of batch b next to the
-    GEMM of batch b+1, double-buffered candidates); rows from every batch must match the exact path"""
+    """more users than one wave of CTAs holds: several batches back to back (targets uploaded once, redo flags read once);
+    rows from every batch must match the exact path"""
     U = 45000
     sess, ui = _sparse_scoring_session(U, 33000, 16, seed=11)
     users = np.arange(U, dtype=np.float32)
