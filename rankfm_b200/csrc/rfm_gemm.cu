@@ -4,27 +4,28 @@
 // (:444).  Mathematically that is S = A . B^T + bias with
 //     A[u]  = [ v_u + x_uf.v_uf  |  v_u ]            (second half only with item features)
 //     B[i]  = [ v_i              |  x_if[i].v_if ]
-//     bias  = w_i + x_if[i].w_if                     (fp32, added in the epilogue from a shared-memory tile)
+//     bias  = w_i + x_if[i].w_if                     (fp32)
 // (derived from compute_ui_utility :48-89; there is no user-feature x item-feature cross term), i.e. a dense GEMM whose
 // output (U x I) can never be materialised at cfg5 scale (1M x 1M).  So:
 //
-//   (superseded in the details by the comments at score_filter_kernel: bias-ordered catalogue, 8-item block bounds)
-//   score_filter_kernel   bf16 operands, fp32 accumulation on the 5th-generation tensor cores:
-//       TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma (cta_group::1, M=128, N=256|128,
+//   pack_gemm_items_kernel  B / bias / order in DESCENDING BIAS ORDER (once per weight state): the epilogues below work on
+//                           raw dot products and touch the bias once per run of consecutive positions.
+//   score_filter_kernel     bf16 operands, fp32 accumulation on the 5th-generation tensor cores:
+//       TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma (cta_group::1, M=128, N=128|256,
 //       K=16 per instruction, issued by one elected thread) -> accumulators in TMEM (2 stages) -> tcgen05.ld in the
-//       epilogue warps.  One CTA owns 128 users (A stays resident in shared memory) and streams its slice of item
-//       tiles; warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
-//       The epilogue never writes scores.  Two passes over the same GEMM (thread r of the epilogue owns user row r):
-//         pass 1 (MODE_ROWMAX)  only the maximum of every 64-item block is kept (one FMNMX per score).  The n'-th
-//                               largest block maximum of a row is a valid lower bound tau_r of its n'-th best score
-//                               (row_threshold_kernel, exact radix select over the block maxima).
-//         pass 2 (MODE_FILTER)  (score, item) is appended to the row's candidate buffer only when score >= tau_r:
-//                               a superset of the row's n' best items, typically 1-2x n' entries.
-//   rescore_kernel        exact fp32 utility of the surviving candidates (same code as predict), seen items masked
-//   topn_select_kernel    (rfm_score.cu) exact top-n of the shortlist.
+//       epilogue warps (double-buffered in registers).  One CTA owns 128 or 256 users (A stays resident in shared memory)
+//       and streams its share of the item tiles; warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+//       allocator, warp 3 bias producer, warps 4-11 epilogue (thread <-> user row).  The epilogue never writes scores:
+//         pass 1 (MODE_ROWMAX)  a lower bound of the best score of every 8-item block of the highest-bias 1/k of the
+//                               catalogue; row_threshold_*_kernel takes the n'-th largest bound of a row: a valid lower
+//                               bound tau_r of the row's n'-th best score.
+//         pass 2 (MODE_FILTER)  (dot, position) is appended to the row's candidate buffer wherever the score can reach
+//                               tau_r: a superset of the row's n' best items, ~2-4 n' entries.
+//   shortlist_kernel        per user: n' best candidates by bf16 score, their exact fp32 utility (same code as predict),
+//                           seen items dropped, bitonic sort, final top-n row.
 //
-// n' = 2*n_items (+ the user's number of seen items when filtering) absorbs the bf16 rounding of the candidate scores;
-// the final ranking is exact fp32.
+// n' = 2*n_items + 16 (+ the user's number of seen items when filtering) absorbs the bf16 rounding of the candidate
+// scores; the final ranking is exact fp32.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdio>
