@@ -280,9 +280,9 @@ def run_ours(args):
         e2e = None
         if world == 1:
             _rankfm.pin(*pinned)
-            for _ in range(3):                            # the allocator / lazy module loading settle over the first calls
+            for _ in range(5):                            # the block cache / lazy module loading settle over the first calls
                 e2e_step()
-            dts = [e2e_step() for _ in range(max(7, args.steps))]
+            dts = [e2e_step() for _ in range(max(15, args.steps))]
             dt_med = float(np.median(dts))
             h2d = X.nbytes + c["sw"].nbytes + ui.indptr.nbytes + ui.indices.nbytes + sum(v.nbytes for v in c["w0"].values()) + \
                 (c["x_uf"].nbytes if c["P"] else 0) + (c["x_if"].nbytes if c["Q"] else 0)
