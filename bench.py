@@ -383,7 +383,9 @@ def run_ours(args):
                 line["e2e"] = {"value": N * epochs * world / dt_med, "unit": "interactions/s", "h2d_bytes_per_step": int(per_rank * world),
                                "d2h_bytes_per_step": int(sum(v.nbytes for v in c["w0"].values()) * world), "ms_per_step": 1e3 * dt_med,
                                "statistic": "median of %d steps, max over ranks" % len(dts), "ms_each": [round(1e3 * d, 2) for d in dts],
-                               "call": "rankfm_b200._rankfm._fit on every rank (pageable host ndarrays; includes ncclCommInitRank/Destroy of the call's communicator)"}
+                               "call": "rankfm_b200._rankfm._fit on every rank (pageable host ndarrays)",
+                               "note": "a one-shot call builds and destroys its own NCCL communicator: ~1.3 s of every call at N=2 (profiles/r01_bench_cfg2_2gpu_final.json) "
+                                       "against %.0f ms of training -- callers that train repeatedly keep a Session (and its communicator), which is what `value` times" % (ms / args.steps)}
         except Exception as exc:
             if line is not None:
                 line["e2e"] = {"error": repr(exc)}
