@@ -1001,10 +1001,10 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     // of an SM's shared memory, so shortlist blocks cannot co-reside with it and only delay the next wave -- GEMM + filter
     // 6.2 -> 8.3 ms per 65,536 users for the same 9.0 ms total.)
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr;
-    float *d_rowmax = nullptr, *d_tau = nullptr, *d_fix = nullptr; int32_t* d_fix_users = nullptr; int* d_flag = nullptr;
+    float *d_rowmax = nullptr, *d_tau = nullptr; int* d_flag = nullptr;
+    DevBuf<float> d_fix; DevBuf<int32_t> d_fix_users;               // rows redone on the exact path
     const int64_t n_batches = (n_users + rows_alloc - 1) / rows_alloc;
-    std::vector<cudaEvent_t> ev;                                     // timing pairs (GEMM + filter of each batch)
-    auto done = [&](int code) { dev_free(d_fix); dev_free(d_fix_users); for (auto e : ev) cudaEventDestroy(e); return code; };
+    struct Events : std::vector<cudaEvent_t> { ~Events() { for (auto e : *this) cudaEventDestroy(e); } } ev;    // timing pairs (GEMM + filter of each batch)
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
     if ((rc = scratch_get(s, 2, (size_t)n_batches * rows_alloc, &d_ntgt))) return rc;
     if ((rc = scratch_get(s, 3, (size_t)rows_alloc, &d_tau))) return rc;
@@ -1031,20 +1031,20 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
         if (gemm_ms) {
             cudaEvent_t ta, tb;
-            if (cudaEventCreate(&ta) != cudaSuccess || cudaEventCreate(&tb) != cudaSuccess) return done(fail(RFM_ERR_CUDA, "cudaEventCreate failed"));
+            if (cudaEventCreate(&ta) != cudaSuccess || cudaEventCreate(&tb) != cudaSuccess) return fail(RFM_ERR_CUDA, "cudaEventCreate failed");
             ev.push_back(ta); ev.push_back(tb);
             CU(cudaEventRecord(ta, s->st));
         }
         cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, tau_subset_head() ? -stride : stride, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
-        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e));
         e = launch_row_threshold(d_rowmax, M_pad, n_sub1, tgt, d_tau, s->st);
-        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "row_threshold launch failed: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "row_threshold launch failed: %s", cudaGetErrorString(e));
         e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, cand, cnt, d_tau, cap, nullptr, nullptr, s->st);
-        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e));
         if (gemm_ms) CU(cudaEventRecord(ev.back(), s->st));
         e = launch_shortlist(T, d_users + off, nb, cand, cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
                              n_items, d_rec + (size_t)off * n_items, d_flag + off, s->st);
-        if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
         s->launches += 5;
     }
     CU(cudaStreamSynchronize(s->st));
@@ -1059,15 +1059,15 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         if (flag_h[(size_t)r]) { redo_users.push_back(h_users[r]); redo_rows.push_back(r); }
     s->tc_rows += n_users; s->tc_redo += (int64_t)redo_users.size();
     if (!redo_users.empty()) {
-        if ((rc = dev_alloc(&d_fix_users, redo_users.size()))) return done(rc);
-        if ((rc = dev_alloc(&d_fix, redo_users.size() * n_items))) return done(rc);
+        if ((rc = d_fix_users.alloc(redo_users.size()))) return rc;
+        if ((rc = d_fix.alloc(redo_users.size() * n_items))) return rc;
         CU(cudaMemcpyAsync(d_fix_users, redo_users.data(), redo_users.size() * 4, cudaMemcpyHostToDevice, s->st));
-        if ((rc = recommend_exact(s, d_fix_users, (int64_t)redo_users.size(), n_items, filter_previous, d_fix, nullptr))) return done(rc);
+        if ((rc = recommend_exact(s, d_fix_users, (int64_t)redo_users.size(), n_items, filter_previous, d_fix, nullptr))) return rc;
         for (size_t k = 0; k < redo_rows.size(); ++k)
             CU(cudaMemcpyAsync(d_rec + (size_t)redo_rows[k] * n_items, d_fix + k * n_items, (size_t)n_items * 4, cudaMemcpyDeviceToDevice, s->st));
         CU(cudaStreamSynchronize(s->st));
     }
-    return done(RFM_OK);
+    return RFM_OK;
 }
 
 // 0 = auto, 1 = force tensor-core path where it applies, 2 = force the exact path       (RANKFM_B200_RECOMMEND=auto|tc|exact)
