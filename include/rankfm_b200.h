@@ -153,6 +153,8 @@ int rfm_session_trace_enable(rfm_session *s);
 int rfm_session_trace_read(rfm_session *s, int32_t *neg_and_sampled /* [N,2] */);
 /* debugging / parity: dense bf16 tensor-core scores (A.B^T + bias) of the requested users against all items */
 int rfm_session_debug_gemm(rfm_session *s, const float *users, int64_t n_users, float *scores_out /* [n_users, I] */);
+/* `rfm_similar` on a resident session (same arguments and result) */
+int rfm_session_similar(rfm_session *s, int32_t which, int32_t index, int32_t n, int32_t *out);
 /* (re)attach the user_items CSR a scoring session filters with (`filter_previous`, `_rankfm.pyx:450`): lets a caller keep
  * one session resident across `_predict` / `_recommend` calls instead of re-uploading the weights every call */
 int rfm_session_attach_csr(rfm_session *s, const int64_t *csr_indptr /* [U+1] */, const int32_t *csr_indices /* [nnz] */);

@@ -332,6 +332,8 @@ def _recommend(users, user_items, n_items, filter_previous, x_uf, x_if, w_i, w_i
 
 def _similar(which, index, n, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if):
     """top-n most similar rows by latent inner product (``rankfm.py:405-454``); which=0 items, 1 users"""
+    if _RESIDENT:
+        return _resident_session((x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if)).similar(which, index, n)
     keep = []
     p = _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep)
     out = np.empty(n, dtype=np.int32)
@@ -418,6 +420,11 @@ class Session:
     def debug_gemm(self, users):
         out = np.empty((users.shape[0], self._p.I), dtype=np.float32)
         check(_lib.lib().rfm_session_debug_gemm(self._h, ptr(users), users.shape[0], ptr(out)))
+        return out
+
+    def similar(self, which, index, n):
+        out = np.empty(n, dtype=np.int32)
+        check(_lib.lib().rfm_session_similar(self._h, int(which), int(index), int(n), ptr(out)))
         return out
 
     def attach_csr(self, indptr, indices):

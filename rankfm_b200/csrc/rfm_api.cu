@@ -1339,36 +1339,44 @@ extern "C" int rfm_recommend(const rfm_problem* p, const float* users, int64_t n
     return rc;
 }
 
+extern "C" int rfm_session_similar(rfm_session* s, int32_t which, int32_t index, int32_t n, int32_t* out)
+{
+    if (!s || !out) return fail(RFM_ERR_ARG, "NULL argument");
+    if (which != 0 && which != 1) return fail(RFM_ERR_ARG, "which must be 0 (items) or 1 (users)");
+    const int rows = which == 0 ? s->T.I : s->T.U;
+    if (index < 0 || index >= rows) return fail(RFM_ERR_ARG, "index out of range");
+    if (n < 1 || n > 16384) return fail(RFM_ERR_ARG, "n out of range");
+    CU(cudaSetDevice(s->device));
+    DevBuf<float> qc, S, d_rec; DevBuf<int32_t> d_one, d_ex;
+    int rc;
+    if ((rc = qc.alloc((size_t)s->T.Fp + (size_t)std::max(s->T.Pp, s->T.Qp) + 4))) return rc;
+    if ((rc = S.alloc((size_t)rows))) return rc;
+    if ((rc = d_rec.alloc((size_t)n))) return rc;
+    if ((rc = d_one.alloc(1))) return rc;
+    if ((rc = d_ex.alloc(1))) return rc;
+    const int32_t zero = 0;
+    CU(cudaMemcpyAsync(d_one, &zero, 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(d_ex, &index, 4, cudaMemcpyHostToDevice, s->st));
+    cudaError_t e = launch_latent_scores(s->T, which, index, qc, S, s->st);
+    if (e == cudaSuccess) e = launch_topn_select(S, rows, d_one, 1, nullptr, nullptr, 0, n, d_rec, d_ex, s->st);
+    if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "similar launch failed: %s", cudaGetErrorString(e));
+    s->launches += 3;
+    std::vector<float> rec((size_t)n);
+    CU(cudaMemcpyAsync(rec.data(), d_rec, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    for (int k = 0; k < n; ++k) out[k] = std::isnan(rec[(size_t)k]) ? -1 : (int32_t)rec[(size_t)k];
+    return RFM_OK;
+}
+
 extern "C" int rfm_similar(const rfm_problem* p, int32_t which, int32_t index, int32_t n, int32_t* out)
 {
     if (!p || !out) return fail(RFM_ERR_ARG, "NULL argument");
-    const int rows = which == 0 ? p->I : p->U;
-    if (which != 0 && which != 1) return fail(RFM_ERR_ARG, "which must be 0 (items) or 1 (users)");
-    if (index < 0 || index >= rows) return fail(RFM_ERR_ARG, "index out of range");
-    if (n < 1 || n > 16384) return fail(RFM_ERR_ARG, "n out of range");
     rfm_problem q = *p;
     q.n_interactions = 0;
     rfm_session* s = nullptr;
     int rc = rfm_session_create(&q, &s);
     if (rc) return rc;
-    float *qvec = nullptr, *S = nullptr, *d_rec = nullptr;
-    int32_t *d_one = nullptr, *d_ex = nullptr;
-    auto done = [&](int code) { dev_free(qvec); dev_free(S); dev_free(d_rec); dev_free(d_one); dev_free(d_ex); rfm_session_destroy(s); return code; };
-    if ((rc = dev_alloc(&qvec, (size_t)s->T.Fp))) return done(rc);
-    if ((rc = dev_alloc(&S, (size_t)rows))) return done(rc);
-    if ((rc = dev_alloc(&d_rec, (size_t)n))) return done(rc);
-    if ((rc = dev_alloc(&d_one, 1))) return done(rc);
-    if ((rc = dev_alloc(&d_ex, 1))) return done(rc);
-    const int32_t zero = 0;
-    cudaMemcpyAsync(d_one, &zero, 4, cudaMemcpyHostToDevice, s->st);
-    cudaMemcpyAsync(d_ex, &index, 4, cudaMemcpyHostToDevice, s->st);
-    cudaError_t e = launch_latent_scores(s->T, which, index, qvec, S, s->st);
-    if (e == cudaSuccess) e = launch_topn_select(S, rows, d_one, 1, nullptr, nullptr, 0, n, d_rec, d_ex, s->st);
-    if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "similar launch failed: %s", cudaGetErrorString(e)));
-    std::vector<float> rec((size_t)n);
-    cudaMemcpyAsync(rec.data(), d_rec, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st);
-    e = cudaStreamSynchronize(s->st);
-    if (e != cudaSuccess) return done(fail(RFM_ERR_CUDA, "similar failed: %s", cudaGetErrorString(e)));
-    for (int k = 0; k < n; ++k) out[k] = std::isnan(rec[(size_t)k]) ? -1 : (int32_t)rec[(size_t)k];
-    return done(RFM_OK);
+    rc = rfm_session_similar(s, which, index, n, out);
+    rfm_session_destroy(s);
+    return rc;
 }

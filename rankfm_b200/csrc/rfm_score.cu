@@ -273,27 +273,73 @@ __device__ __forceinline__ float latent_elem(const Tables& T, int which, int row
     return v;
 }
 
-__global__ void latent_query_kernel(const Tables T, int which, int index, float* __restrict__ qvec)
+// qc = [ q (Fp floats): latent representation of the query row | c (Pp or Qp floats): c[k] = v_f[k] . q ]
+// so that  rep(row) . rep(query) = v[row] . q + x[row] . c  -- one fat-row gather and one group reduction per row,
+// exactly the shape of the FM utility without the item bias.
+__global__ void latent_query_kernel(const Tables T, int which, int index, float* __restrict__ qc)
 {
-    for (int f = threadIdx.x; f < T.F; f += blockDim.x) qvec[f] = latent_elem(T, which, index, f);
-}
-
-__global__ void latent_scores_kernel(const Tables T, int which, const float* __restrict__ qvec, float* __restrict__ S)
-{
-    const int n = which == 0 ? T.I : T.U;
-    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    for (int f = threadIdx.x; f < T.Fp; f += blockDim.x) qc[f] = f < T.F ? latent_elem(T, which, index, f) : 0.f;
+    __syncthreads();
+    const int nc = which == 0 ? T.Qp : T.Pp;
+    const int n_real = which == 0 ? (T.x_if_any ? T.Q : 0) : (T.x_uf_any ? T.P : 0);
+    const int base = which == 0 ? T.gp_vif : T.gp_vuf;
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) {
         float acc = 0.f;
-        for (int f = 0; f < T.F; ++f) acc += latent_elem(T, which, row, f) * qvec[f];
-        S[row] = acc;
+        if (k < n_real) for (int f = 0; f < T.F; ++f) acc += T.GP[base + (size_t)k * T.Fp + f] * qc[f];
+        qc[T.Fp + k] = acc;
     }
 }
 
-cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st)
+template <int G, int QPL, bool FEAT>
+__global__ void __launch_bounds__(256) latent_scores_kernel(const Tables T, int which, const float* __restrict__ qc, float* __restrict__ S)
 {
-    latent_query_kernel<<<1, 128, 0, st>>>(T, which, index, qvec);
-    const int n = which == 0 ? T.I : T.U;
-    latent_scores_kernel<<<min(1184, (n + 127) / 128), 128, 0, st>>>(T, which, qvec, S);
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31, sub = lane % G, gw = lane / G;
+    float4 a[QPL];
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) { const int q = sub + k * G; a[k] = q < T.NQ ? reinterpret_cast<const float4*>(qc)[q] : zero4(); }
+    float4 c = zero4();
+    if (FEAT) { const int nc4 = (which == 0 ? T.Qp : T.Pp) / 4; if (sub < nc4) c = reinterpret_cast<const float4*>(qc + T.Fp)[sub]; }
+    const long long n = which == 0 ? T.I : T.U;
+    const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
+    const long long span = (n + stride - 1) / stride * stride;          // warp-uniform trip count
+    for (long long row = group_global; row < span; row += stride) {
+        const bool ok = row < n;
+        float part = 0.f;
+        if (which == 0) {
+            ItemRow<QPL> r;
+            load_item<G, QPL, FEAT>(T, ok ? (int)row : 0, ok, sub, r);
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) part = dot4(a[k], r.v[k], part);
+            if (FEAT) part = dot4(c, r.x, part);
+        } else {
+            UserCtx<QPL> u;
+            load_user<G, QPL, FEAT>(T, ok ? (int)row : 0, ok, sub, u);
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) part = dot4(a[k], u.vu[k], part);
+            if (FEAT) part = dot4(c, u.xu, part);
+        }
+        const float sc = group_sum<G>(part);
+        if (ok && sub == 0) S[row] = sc;
+    }
+}
+
+template <int G, int QPL>
+static cudaError_t latent_scores_gq(const Tables& T, int which, const float* qc, float* S, cudaStream_t st)
+{
+    const long long n = which == 0 ? T.I : T.U;
+    const int grid = (int)max(1LL, min(148LL * 8, (n * G + 255) / 256));
+    if (T.x_uf_any || T.x_if_any) latent_scores_kernel<G, QPL, true><<<grid, 256, 0, st>>>(T, which, qc, S);
+    else latent_scores_kernel<G, QPL, false><<<grid, 256, 0, st>>>(T, which, qc, S);
     return cudaGetLastError();
+}
+
+// qc: scratch of Fp + max(Pp, Qp) floats
+cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qc, float* S, cudaStream_t st)
+{
+    latent_query_kernel<<<1, 128, 0, st>>>(T, which, index, qc);
+    RFM_DISPATCH_GQ(latent_scores_gq, T, which, qc, S, st);
 }
 
 }  // namespace rfm

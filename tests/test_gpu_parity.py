@@ -557,11 +557,13 @@ def test_resident_scoring_session_across_calls(gpu_lib):
     model.fit(X, epochs=2)
     users = list(range(0, 300, 7)) + [10_000]                        # one unknown user
     base_p, base_r = model.predict(X[:500]), model.recommend(users, 5, True)
+    base_s = model.similar_items(X[0, 1], 5), model.similar_users(X[0, 0], 5)
     _rankfm.set_resident(True)
     try:
         n0 = _rankfm._scoring["uploads"]
         p1, r1 = model.predict(X[:500]), model.recommend(users, 5, True)
         p2, r2 = model.predict(X[:500]), model.recommend(users, 5, False)
+        assert np.array_equal(model.similar_items(X[0, 1], 5), base_s[0]) and np.array_equal(model.similar_users(X[0, 0], 5), base_s[1])
         assert _rankfm._scoring["uploads"] == n0 + 1
         assert np.array_equal(p1, base_p) and np.array_equal(p2, base_p)
         assert r1.equals(base_r) and not r2.equals(base_r)
