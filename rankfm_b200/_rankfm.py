@@ -173,8 +173,8 @@ class UserItems(dict):
         """CSR of the items of each user, sorted ascending, duplicates kept (like ``rankfm.py:174``)"""
         inter = np.asarray(interactions)
         n_items = int(inter[:, 1].max()) + 1 if len(inter) else 1
-        keys = inter[:, 0].astype(np.int64) * n_items + inter[:, 1]        # one radix sort instead of a 2-key lexsort
-        keys.sort(kind='stable')
+        keys = inter[:, 0].astype(np.int64) * n_items + inter[:, 1]        # one key sort instead of a 2-key lexsort
+        keys.sort()                                                         # equal keys are identical: stability is moot
         counts = np.bincount(inter[:, 0], minlength=n_users)
         indptr = np.zeros(n_users + 1, dtype=np.int64)
         np.cumsum(counts, out=indptr[1:])

@@ -12,7 +12,7 @@ import pandas as pd
 
 from rankfm_b200 import _rankfm
 from rankfm_b200._rankfm import _fit, _predict, _recommend, _similar, UserItems
-from rankfm_b200.utils import get_data
+from rankfm_b200.utils import get_data, lookup_ids, unique_ids
 
 _LOSSES = ('bpr', 'warp')
 _SCHEDULES = ('constant', 'invscaling')
@@ -63,14 +63,14 @@ class RankFM():
     @staticmethod
     def _lookup(ids, known):
         """index of each id in the unique array ``known`` (-1 when absent); any id dtype"""
-        return pd.Index(known).get_indexer(pd.Index(np.asarray(ids))).astype(np.int64)
+        return lookup_ids(ids, known)
 
     def _init_all(self, interactions, user_features=None, item_features=None, sample_weight=None):
         """first fit: build the id <-> index maps, then interactions, features, weights (``rankfm.py:100-137``)"""
         self._check_interactions(interactions)
         raw = get_data(interactions)
-        self.user_id = pd.Series(np.unique(raw[:, 0]))          # np.unique sorts
-        self.item_id = pd.Series(np.unique(raw[:, 1]))
+        self.user_id = pd.Series(unique_ids(raw[:, 0]))         # sorted, like np.unique
+        self.item_id = pd.Series(unique_ids(raw[:, 1]))
         self.index_to_user, self.index_to_item = self.user_id, self.item_id
         self.user_to_index = pd.Series(data=self.index_to_user.index, index=self.index_to_user.values)
         self.item_to_index = pd.Series(data=self.index_to_item.index, index=self.index_to_item.values)
