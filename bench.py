@@ -174,10 +174,42 @@ def reference_fit_rate(c, epochs, repeats=1):
     return best, kind
 
 
+def run_reference_recommend(args):
+    """reference arm of `--workload cfg5`: the reference's own `_recommend` (scalar scoring loop + full argsort per user,
+    `_rankfm.pyx:393-460`) on a bounded sample of users of the same synthetic model; users/s scale-free in the user count"""
+    from oracle import oracle
+    ref = oracle.load_reference(build_if_possible=True)
+    kind, rec = ("reference", ref._recommend) if ref is not None else ("port", oracle._recommend)
+    U = int(os.environ.get("BENCH_CFG5_USERS", 1_000_000))
+    I = int(os.environ.get("BENCH_CFG5_ITEMS", 1_000_000))
+    F, topn, sample = 128, 100, int(os.environ.get("BENCH_CFG5_REF_SAMPLE", 24))
+    rng = np.random.default_rng(0)                           # same draws as recommend_probe
+    w_i = rng.normal(0, 0.3, I).astype(np.float32)
+    v_u = rng.standard_normal((U, F), dtype=np.float32) * np.float32(0.1)
+    v_i = rng.standard_normal((I, F), dtype=np.float32) * np.float32(0.1)
+    zeros = lambda *shape: np.zeros(shape, np.float32)
+    users = np.arange(min(sample, U), dtype=np.float32)
+    times = []
+    for k in range(args.warmup + max(1, args.steps)):
+        t0 = time.perf_counter()
+        rec(users, {}, topn, False, zeros(U, 1), zeros(I, 1), w_i, zeros(1), v_u, v_i, zeros(1, F), zeros(1, F))
+        if k >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    value = len(users) / float(np.mean(times))
+    emit({"impl": "reference", "metric": "recommend users/sec", "value": value, "unit": "users/s", "n_gpus": args.gpus, "steps": max(1, args.steps),
+          "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic", "config": {"workload": "recommend top-%d, %d users x %d items, factors=%d" % (topn, U, I, F),
+                                          "sample": "%d users per step (the reference's per-user cost does not depend on the number of users)" % len(users)},
+          "cpu_baseline": {"value": value, "unit": "users/s", "cores": 1, "kind": kind, "sample": "%d users x %d items per step; single-threaded by construction, 1 thread of %d" % (len(users), I, os.cpu_count())},
+          "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "cfg5":
+        return run_reference_recommend(args)
     c = make_workload(args.workload)
     # bounded sample: as many of the workload's epochs per step as fit in ~2 minutes of single-thread CPU time overall
     per_epoch_s = 1.3 * len(c["X"]) / 1e6 * max(1.0, c["F"] / 20.0)

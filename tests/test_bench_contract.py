@@ -27,3 +27,15 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "0", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_of_the_recommend_workload():
+    env = dict(os.environ, BENCH_CFG5_USERS="500", BENCH_CFG5_ITEMS="3000", BENCH_CFG5_REF_SAMPLE="8")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg5", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "recommend users/sec" and d["unit"] == "users/s" and d["value"] > 0
+    assert d["cpu_baseline"]["cores"] == 1 and d["e2e"]["h2d_bytes_per_step"] == 0
