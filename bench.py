@@ -211,23 +211,34 @@ def run_reference(args):
     if args.workload == "cfg5":
         return run_reference_recommend(args)
     c = make_workload(args.workload)
-    # bounded sample: as many of the workload's epochs per step as fit in ~2 minutes of single-thread CPU time overall
-    per_epoch_s = 1.3 * len(c["X"]) / 1e6 * max(1.0, c["F"] / 20.0)
-    sample_epochs = int(min(c["epochs"], max(2, 120.0 / per_epoch_s / (args.steps + args.warmup))))
-    for _ in range(args.warmup):
-        reference_fit_rate(c, sample_epochs)
+    # bounded sample: a quick probe gives this box's rate for the workload's row shape, then each step runs as
+    # many epochs over as many interactions (same U, I, F, features -- the per-interaction cost is scale-free apart from
+    # cache effects) as fit the time budget; the first epochs are also the reference's fastest (fewest WARP draws)
+    budget = float(os.environ.get("BENCH_REF_BUDGET_S", 120.0)) / (args.steps + args.warmup)
+    N = len(c["X"])
+    probe_n = min(N, 100_000)
+    probe = dict(c, X=np.ascontiguousarray(c["X"][:probe_n]), sw=c["sw"][:probe_n])
     t0 = time.perf_counter()
-    rates = [reference_fit_rate(c, sample_epochs) for _ in range(args.steps)]
+    reference_fit_rate(probe, 1)
+    probe_rate = probe_n / (time.perf_counter() - t0)                       # includes the Python set-up over all U users
+    sample_epochs = int(min(c["epochs"], max(2, budget * probe_rate / N)))
+    sample_n = int(min(N, max(probe_n, budget * probe_rate / sample_epochs)))
+    cs = c if sample_n == N else dict(c, X=np.ascontiguousarray(c["X"][:sample_n]), sw=c["sw"][:sample_n])
+    for _ in range(args.warmup):
+        reference_fit_rate(cs, sample_epochs)
+    t0 = time.perf_counter()
+    rates = [reference_fit_rate(cs, sample_epochs) for _ in range(args.steps)]
     dt = time.perf_counter() - t0
     kind = rates[0][1]
     value = float(np.mean([r[0] for r in rates]))
+    what = "all %d interactions" % N if sample_n == N else "the first %d of %d interactions (same users, items, factors, features; extrapolated)" % (sample_n, N)
     line = {
         "impl": "reference", "metric": "training interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": vs_published(value, args.workload), "dtype": "f32", "data": "synthetic",
-        "config": {"workload": c["label"], "sample": "%d of %d epochs per step, all %d interactions" % (sample_epochs, c["epochs"], len(c["X"]))},
+        "config": {"workload": c["label"], "sample": "%d of %d epochs per step, %s" % (sample_epochs, c["epochs"], what)},
         "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": 1, "kind": kind,
-                         "sample": "%d epochs x %d interactions per step; the reference holds the GIL and has no OpenMP: 1 thread of %d" % (sample_epochs, len(c["X"]), os.cpu_count())},
+                         "sample": "%d epochs x %d interactions per step; the reference holds the GIL and has no OpenMP: 1 thread of %d" % (sample_epochs, sample_n, os.cpu_count())},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
