@@ -174,6 +174,23 @@ def reference_fit_rate(c, epochs, repeats=1):
     return best, kind
 
 
+def bounded_reference_sample(c, budget_s):
+    """bounded sample of a workload for the single-threaded reference: a quick probe gives this box's rate for
+    the workload's row shape, then a run is as many epochs over as many interactions (same U, I, F, features -- the
+    per-interaction cost is scale-free apart from cache effects) as fit `budget_s`.  The first epochs are also the
+    reference's fastest (fewest WARP draws).  -> (workload dict of the sample, epochs, interactions)"""
+    N = len(c["X"])
+    probe_n = min(N, 100_000)
+    probe = dict(c, X=np.ascontiguousarray(c["X"][:probe_n]), sw=c["sw"][:probe_n])
+    t0 = time.perf_counter()
+    reference_fit_rate(probe, 1)
+    probe_rate = probe_n / (time.perf_counter() - t0)                       # includes the Python set-up over all U users
+    sample_epochs = int(min(c["epochs"], max(2, budget_s * probe_rate / N)))
+    sample_n = int(min(N, max(probe_n, budget_s * probe_rate / sample_epochs)))
+    cs = c if sample_n == N else dict(c, X=np.ascontiguousarray(c["X"][:sample_n]), sw=c["sw"][:sample_n])
+    return cs, sample_epochs, sample_n
+
+
 def run_reference_recommend(args):
     """reference arm of `--workload cfg5`: the reference's own `_recommend` (scalar scoring loop + full argsort per user,
     `_rankfm.pyx:393-460`) on a bounded sample of users of the same synthetic model; users/s scale-free in the user count"""
@@ -211,19 +228,8 @@ def run_reference(args):
     if args.workload == "cfg5":
         return run_reference_recommend(args)
     c = make_workload(args.workload)
-    # bounded sample: a quick probe gives this box's rate for the workload's row shape, then each step runs as
-    # many epochs over as many interactions (same U, I, F, features -- the per-interaction cost is scale-free apart from
-    # cache effects) as fit the time budget; the first epochs are also the reference's fastest (fewest WARP draws)
-    budget = float(os.environ.get("BENCH_REF_BUDGET_S", 120.0)) / (args.steps + args.warmup)
+    cs, sample_epochs, sample_n = bounded_reference_sample(c, float(os.environ.get("BENCH_REF_BUDGET_S", 120.0)) / (args.steps + args.warmup))
     N = len(c["X"])
-    probe_n = min(N, 100_000)
-    probe = dict(c, X=np.ascontiguousarray(c["X"][:probe_n]), sw=c["sw"][:probe_n])
-    t0 = time.perf_counter()
-    reference_fit_rate(probe, 1)
-    probe_rate = probe_n / (time.perf_counter() - t0)                       # includes the Python set-up over all U users
-    sample_epochs = int(min(c["epochs"], max(2, budget * probe_rate / N)))
-    sample_n = int(min(N, max(probe_n, budget * probe_rate / sample_epochs)))
-    cs = c if sample_n == N else dict(c, X=np.ascontiguousarray(c["X"][:sample_n]), sw=c["sw"][:sample_n])
     for _ in range(args.warmup):
         reference_fit_rate(cs, sample_epochs)
     t0 = time.perf_counter()
@@ -372,10 +378,10 @@ def run_ours(args):
                 roofline_large = {"error": repr(exc)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sample_epochs = 3
-            rate, kind = reference_fit_rate(c, sample_epochs)
+            cs, sample_epochs, sample_n = bounded_reference_sample(c, float(os.environ.get("BENCH_CPU_BASELINE_S", 20.0)))
+            rate, kind = reference_fit_rate(cs, sample_epochs)
             cpu = {"value": rate, "unit": "interactions/s", "cores": 1, "kind": kind,
-                   "sample": "%d epochs x %d interactions (of %d epochs); single-threaded by construction, %d host cores present" % (sample_epochs, N, epochs, os.cpu_count())}
+                   "sample": "%d of %d epochs x %d of %d interactions; single-threaded by construction, %d host cores present" % (sample_epochs, epochs, sample_n, N, os.cpu_count())}
         line = {
             "metric": "training interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": vs_published(value, args.workload), "dtype": "f32", "data": "synthetic",
