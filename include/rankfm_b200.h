@@ -78,6 +78,13 @@ typedef struct rfm_problem {
     /* multi-GPU (one process per GPU).  world==1: single GPU, nccl_id ignored. */
     int32_t  rank, world;
     const uint8_t *nccl_id;          /* 128 bytes from rfm_nccl_unique_id() on rank 0, broadcast by the caller */
+    /* multi-GPU partition: this rank owns users [user_lo, user_hi) -- only their rows of v_u / x_uf are
+     * uploaded, trained and written back (the host arrays keep their global [U, .] shape; rows of other users are never
+     * touched) and every interaction passed to this rank must belong to one of them.  0,0 = all users (world == 1). */
+    int32_t  user_lo, user_hi;
+    /* epochs this model has already been trained for by EARLIER calls: offsets the Philox / Feistel keys so that a
+     * sequence of warm-start calls (`fit_partial`, rankfm.py:269-327) does not replay the same order and negatives */
+    int32_t  epoch_offset;
 } rfm_problem;
 
 /* Per-epoch report, the device-side equivalent of `_rankfm.pyx:328-336` (assert_finite, reg_penalty, log-lik). */
@@ -90,12 +97,19 @@ typedef struct rfm_epoch_stats {
     float   kernel_ms;               /* CUDA-event time of the SGD kernel launch(es) of this epoch */
     float   sync_ms;                 /* CUDA-event time of the multi-GPU delta exchange (0 when world==1) */
 } rfm_epoch_stats;
+/* With world > 1 log_likelihood, draws, penalty and finite[] are those of the WHOLE job (summed over the ranks' shards
+ * after the last epoch), like the single `ll` the reference prints (`_rankfm.pyx:332-336`). */
 
 /* ---- library / device ---- */
 const char *rfm_version(void);
 const char *rfm_last_error(void);
 int rfm_device_count(void);                                      /* number of CUDA devices, 0 if none */
 int rfm_nccl_unique_id(uint8_t *out128);                         /* rank 0 calls, caller broadcasts */
+/* Multi-GPU communicators (NCCL communicator + the peer-memory window the fused delta exchange runs over) are created by
+ * the first session that names a (nccl_id, rank, world, device) and are KEPT by the library for later sessions of the same
+ * job -- a one-shot `rfm_fit` per `fit_partial` call pays ncclCommInitRank + the IPC handshake once.  This call destroys
+ * every cached communicator that no live session uses (collective: every rank of the job must call it). */
+int rfm_comm_release_all(void);
 
 /* page-lock / unlock a caller-owned host buffer (cudaHostRegister) so that the one-shot calls below copy it at full PCIe
  * speed; optional -- every entry point also accepts pageable memory */
@@ -129,6 +143,11 @@ int rfm_similar(const rfm_problem *p, int32_t which, int32_t index, int32_t n, i
 /* ---- resident sessions: upload once, train / score many times (bench.py, RankFM class) ---- */
 int rfm_session_create(const rfm_problem *p, rfm_session **out);             /* allocates HBM, copies H2D */
 int rfm_session_train(rfm_session *s, int32_t epochs, const int32_t *perms, rfm_epoch_stats *stats);
+/* called on the training thread after every epoch of rfm_session_train with that epoch's record (the reference prints the
+ * log-likelihood of every epoch as it completes when verbose, `_rankfm.pyx:332-336`); costs one stream synchronisation per
+ * epoch, so it is only installed by verbose callers.  NULL removes it. */
+typedef void (*rfm_epoch_callback)(int32_t epoch, const rfm_epoch_stats *stats, void *user);
+int rfm_session_set_epoch_callback(rfm_session *s, rfm_epoch_callback cb, void *user);
 int rfm_session_set_weights(rfm_session *s, const float *w_i, const float *w_if, const float *v_u, const float *v_i,
                             const float *v_uf, const float *v_if);           /* H2D of the weights only */
 /* device-side copy of the current weights, and restoring it (D2D only): lets a benchmark restart training from
@@ -166,6 +185,9 @@ int rfm_session_recommend_stats(rfm_session *s, int64_t *tc_rows, int64_t *tc_re
 int rfm_trim_device_cache(void);
 int rfm_session_flush_l2(rfm_session *s);                                    /* overwrite a >L2-sized scratch buffer */
 int rfm_session_launch_count(rfm_session *s, int64_t *launches);             /* kernels launched by this session */
+/* multi-GPU: which path the per-epoch item-delta exchange of this session takes: 0 = none (world == 1), 1 = fused
+ * peer-memory kernel over NVLink (cudaIpc-mapped windows, no NCCL on the data path), 2 = ncclAllReduce (fallback) */
+int rfm_session_exchange_path(rfm_session *s, int32_t *path);
 int rfm_session_destroy(rfm_session *s);
 
 #ifdef __cplusplus

@@ -18,12 +18,12 @@ SAMPLER_PHILOX, SAMPLER_MT = 0, 1
 SCHED_PARALLEL, SCHED_SERIAL = 0, 1
 
 EXPORTS = [
-    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_host_register", "rfm_host_unregister", "rfm_debug_philox", "rfm_debug_feistel", "rfm_trim_device_cache",
+    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_comm_release_all", "rfm_host_register", "rfm_host_unregister", "rfm_debug_philox", "rfm_debug_feistel", "rfm_trim_device_cache",
     "rfm_fit", "rfm_predict", "rfm_recommend", "rfm_similar",
-    "rfm_session_create", "rfm_session_train", "rfm_session_set_weights", "rfm_session_download",
+    "rfm_session_create", "rfm_session_train", "rfm_session_set_epoch_callback", "rfm_session_set_weights", "rfm_session_download",
     "rfm_session_snapshot", "rfm_session_restore", "rfm_session_timer_start", "rfm_session_timer_stop",
     "rfm_session_predict", "rfm_session_recommend", "rfm_session_time_predict", "rfm_session_time_recommend",
-    "rfm_session_trace_enable", "rfm_session_trace_read", "rfm_session_debug_gemm", "rfm_session_recommend_stats", "rfm_session_attach_csr", "rfm_session_similar", "rfm_session_flush_l2", "rfm_session_launch_count", "rfm_session_destroy",
+    "rfm_session_trace_enable", "rfm_session_trace_read", "rfm_session_debug_gemm", "rfm_session_recommend_stats", "rfm_session_attach_csr", "rfm_session_similar", "rfm_session_flush_l2", "rfm_session_launch_count", "rfm_session_exchange_path", "rfm_session_destroy",
 ]
 
 
@@ -39,6 +39,7 @@ class Problem(C.Structure):
         ("order", C.c_int32), ("sampler", C.c_int32), ("sched", C.c_int32),
         ("mt_seed", C.c_uint32), ("seed", C.c_uint64), ("max_rejects", C.c_int32), ("device", C.c_int32),
         ("rank", C.c_int32), ("world", C.c_int32), ("nccl_id", C.c_void_p),
+        ("user_lo", C.c_int32), ("user_hi", C.c_int32), ("epoch_offset", C.c_int32),
     ]
 
 
@@ -48,6 +49,8 @@ class EpochStats(C.Structure):
         ("eta", C.c_float), ("kernel_ms", C.c_float), ("sync_ms", C.c_float),
     ]
 
+
+EPOCH_CALLBACK = C.CFUNCTYPE(None, C.c_int32, C.POINTER(EpochStats), C.c_void_p)
 
 _lib = None
 
@@ -76,6 +79,7 @@ def lib():
     L.rfm_similar.argtypes = [pp, i32, i32, i32, vp]
     L.rfm_session_create.argtypes = [pp, C.POINTER(vp)]
     L.rfm_session_train.argtypes = [vp, i32, vp, vp]
+    L.rfm_session_set_epoch_callback.argtypes = [vp, EPOCH_CALLBACK, vp]
     L.rfm_session_set_weights.argtypes = [vp] + [vp] * 6
     L.rfm_session_download.argtypes = [vp] + [vp] * 6
     L.rfm_session_snapshot.argtypes = [vp]
@@ -94,6 +98,8 @@ def lib():
     L.rfm_session_similar.argtypes = [vp, i32, i32, i32, vp]
     L.rfm_session_flush_l2.argtypes = [vp]
     L.rfm_session_launch_count.argtypes = [vp, vp]
+    L.rfm_session_exchange_path.argtypes = [vp, vp]
+    L.rfm_comm_release_all.argtypes = []
     L.rfm_session_destroy.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("rfm_version", "rfm_last_error"):

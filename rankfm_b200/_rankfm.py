@@ -17,17 +17,27 @@ Execution modes of ``_fit`` (``set_mode`` / env ``RANKFM_B200_MODE``):
 """
 import ctypes as C
 import os
+import zlib
 
 import numpy as np
 
 from . import _lib
 from ._lib import Problem, EpochStats, as_buffer, check, ptr
 
+WEIGHT_NAMES = ("w_i", "w_if", "v_u", "v_i", "v_uf", "v_if")
 _MODE = os.environ.get("RANKFM_B200_MODE", "production")
 _SEED = int(os.environ.get("RANKFM_B200_SEED", "1492"))
 _DEVICE = int(os.environ.get("RANKFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-_COMM = {"rank": 0, "world": 1, "nccl_id": None}
+_COMM = {"rank": 0, "world": 1, "nccl_id": None, "user_range": None}
 last_stats = None       # list of per-epoch dicts of the most recent _fit
+# Resident TRAINING session (the reference's warm-start contract is `fit_partial`, rankfm.py:269-327):
+# `_fit` keeps the session of its last call -- interactions, sample weights, user_items CSR, membership bitmap, side
+# features and (multi-GPU) the communicator stay in HBM -- and a following `_fit` on the SAME data and hyper-parameters
+# only uploads the weight arrays it is given, trains, and writes them back.  Any other data builds a new session.
+# RANKFM_B200_RESIDENT_TRAIN=0 (or set_resident_training(False)) restores one throw-away session per call.
+_RESIDENT_TRAIN = os.environ.get("RANKFM_B200_RESIDENT_TRAIN", "1") == "1"
+_training = {"key": None, "sess": None, "hits": 0, "builds": 0}
+_EPOCHS = {"done": 0}   # epochs trained by earlier production-mode `_fit` calls: offsets the Philox / Feistel keys of new sessions
 # opt-in: keep one scoring session (packed weights, bf16 item operand, user_items CSR) resident in HBM across
 # _predict / _recommend calls.  The stateless functions of the reference re-read the weight arrays on
 # every call; with this switch on they are re-uploaded only when a DIFFERENT set of arrays is passed or after `_fit`
@@ -70,20 +80,46 @@ def _resident_session(weights, user_items=None):
         _scoring["uploads"] += 1
     sess = _scoring["sess"]
     if user_items is not None:
+        from_csr = hasattr(user_items, "indptr") and hasattr(user_items, "indices")
         indptr, indices = user_items_to_csr(user_items, weights[4].shape[0])
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.int32)
-        csr_key = (indptr.ctypes.data, indices.ctypes.data, len(indices))
+        csr_key = (_fingerprint(indptr, from_csr), _fingerprint(indices, from_csr))
         if _scoring["csr"] != csr_key:
-            sess.attach_csr(indptr, indices)
+            sess.attach_csr(indptr, indices)          # copied to the device: nothing of the old or new CSR has to stay alive
             _scoring["csr"] = csr_key
-            sess._keep.extend([indptr, indices])
     return sess
+
+
+def set_resident_training(flag):
+    global _RESIDENT_TRAIN
+    _RESIDENT_TRAIN = bool(flag)
+    if not _RESIDENT_TRAIN:
+        drop_training()
+
+
+def drop_training():
+    """free the resident training session (its HBM goes back to the library's block cache)"""
+    if _training["sess"] is not None:
+        _training["sess"].close()
+    _training.update(key=None, sess=None)
+
+
+def _fingerprint(a, with_address=True):
+    """cheap identity of a (large, read-only) input array: shape, dtype, [address,] CRC of <= 64k strided samples"""
+    if a is None:
+        return None
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 65536)
+    crc = zlib.crc32(np.ascontiguousarray(flat[::step]).tobytes()) if flat.size else 0
+    return (a.ctypes.data if with_address else 0, a.shape, a.dtype.str, crc)
 
 
 def set_seed(seed):
     global _SEED
     _SEED = int(seed)
+    _EPOCHS["done"] = 0
+    drop_training()
 
 
 def set_device(device):
@@ -91,10 +127,21 @@ def set_device(device):
     _DEVICE = int(device)
 
 
-def set_comm(rank, world, nccl_id):
+def set_comm(rank, world, nccl_id, user_range=None):
     """multi-GPU: one process per GPU; ``nccl_id`` = the 128 bytes of ``nccl_unique_id()`` made on rank 0 and
-    broadcast by the caller.  Each rank then passes ITS shard of the interactions (see ``shard_by_user``)."""
-    _COMM.update(rank=int(rank), world=int(world), nccl_id=None if nccl_id is None else np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy())
+    broadcast by the caller.  Each rank then passes ITS shard of the interactions (see ``shard_by_user``) and owns the
+    users ``user_range = (lo, hi)`` (default: the smallest range that covers the shard's users): only those rows of
+    ``v_u`` are trained and written back on this rank, the item side is identical on every rank after every epoch.
+    The library keeps the communicator of an id for all later calls (``release_comms`` frees it)."""
+    drop_training()
+    _COMM.update(rank=int(rank), world=int(world), nccl_id=None if nccl_id is None else np.frombuffer(bytes(nccl_id), dtype=np.uint8).copy(),
+                 user_range=None if user_range is None else (int(user_range[0]), int(user_range[1])))
+
+
+def release_comms():
+    """destroy the cached communicators no session uses any more (collective over the ranks of each job)"""
+    drop_training()
+    check(_lib.lib().rfm_comm_release_all())
 
 
 def nccl_unique_id():
@@ -198,6 +245,26 @@ def _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep):
     for a, nd, name in ((x_uf, 2, "x_uf"), (x_if, 2, "x_if"), (w_i, 1, "w_i"), (w_if, 1, "w_if"),
                         (v_u, 2, "v_u"), (v_i, 2, "v_i"), (v_uf, 2, "v_uf"), (v_if, 2, "v_if")):
         as_buffer(a, np.float32, nd, name)
+    # The library takes U, I, P, Q, F from the weight arrays and reads x_uf as [U,P], x_if as [I,Q]: every shape has to
+    # agree before a raw pointer crosses the C ABI.  The reference never reads a feature block whose matrix is all zero
+    # (`x_uf_any` / `x_if_any`, _rankfm.pyx:193-194), so `fit(user_features=...)` followed by `fit_partial()` without
+    # features -- x_uf back to zeros [U,1] while v_uf stays [P,F] (rankfm.py:199,236) -- is legal there: an all-zero
+    # matrix of the wrong width is replaced by zeros of the right one, anything else is an error.
+    (U, F), I, P, Q = v_u.shape, v_i.shape[0], v_uf.shape[0], v_if.shape[0]
+    if v_i.shape[1] != F or v_uf.shape[1] != F or v_if.shape[1] != F:
+        raise ValueError("v_u, v_i, v_uf, v_if must have the same number of factors")
+    if w_i.shape[0] != I or w_if.shape[0] != Q:
+        raise ValueError("w_i / w_if do not match v_i [%d] / v_if [%d]" % (I, Q))
+    if x_uf.shape[0] != U or x_if.shape[0] != I:
+        raise ValueError("x_uf / x_if rows do not match v_u [%d] / v_i [%d]" % (U, I))
+    if x_uf.shape[1] != P:
+        if x_uf.any():
+            raise ValueError("x_uf has %d feature columns but v_uf has %d rows" % (x_uf.shape[1], P))
+        x_uf = np.zeros((U, P), dtype=np.float32)
+    if x_if.shape[1] != Q:
+        if x_if.any():
+            raise ValueError("x_if has %d feature columns but v_if has %d rows" % (x_if.shape[1], Q))
+        x_if = np.zeros((I, Q), dtype=np.float32)
     p = Problem()
     p.x_uf, p.x_if = ptr(x_uf), ptr(x_if)
     p.w_i, p.w_if, p.v_u, p.v_i, p.v_uf, p.v_if = ptr(w_i), ptr(w_if), ptr(v_u), ptr(v_i), ptr(v_uf), ptr(v_if)
@@ -212,7 +279,7 @@ def _problem(x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, keep):
 
 def fit_problem(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
                 alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples,
-                mode=None, seed=None, keep=None):
+                mode=None, seed=None, keep=None, user_range=None, epoch_offset=0):
     """build the ``rfm_problem`` for a training call; ``keep`` collects the arrays whose memory it points into"""
     keep = [] if keep is None else keep
     as_buffer(interactions, np.int32, 2, "interactions")
@@ -237,10 +304,19 @@ def fit_problem(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, 
     p.mt_seed = 1492                                                           # _rankfm.pyx:182
     p.seed = _SEED if seed is None else int(seed)
     p.max_rejects = 0
+    p.epoch_offset = int(epoch_offset)
     p.rank, p.world = _COMM["rank"], _COMM["world"]
     if p.world > 1:
         keep.append(_COMM["nccl_id"])
         p.nccl_id = ptr(_COMM["nccl_id"])
+        user_range = user_range or _COMM["user_range"]
+        if user_range is None:                  # the smallest range covering this shard's users; rows of users without
+            users = interactions[:, 0]          # interactions never change, so nothing is lost outside it
+            user_range = (int(users.min()), int(users.max()) + 1) if len(users) else (0, 1)
+    if user_range is not None:
+        p.user_lo, p.user_hi = int(user_range[0]), int(user_range[1])
+        if len(interactions) and (interactions[:, 0].min() < p.user_lo or interactions[:, 0].max() >= p.user_hi):
+            raise ValueError("interactions of users outside this rank's user range [%d, %d)" % (p.user_lo, p.user_hi))
     return p
 
 
@@ -251,13 +327,15 @@ def _stats_list(stats, epochs):
 
 def fit_ex(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
            alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, epochs,
-           mode=None, perms=None, seed=None, order=None, sampler=None, sched=None, max_rejects=0):
+           mode=None, perms=None, seed=None, order=None, sampler=None, sched=None, max_rejects=0, user_range=None, epoch_offset=0,
+           on_epoch=None):
     """``_fit`` with the execution knobs exposed (tests, bench).  ``perms`` int32 [epochs, N] is required when the
     order is HOST; ``order``/``sampler``/``sched`` override what ``mode`` selects.  Returns the per-epoch stats;
     raises like ``_fit``."""
     keep = []
     p = fit_problem(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
-                    alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, mode=mode, seed=seed, keep=keep)
+                    alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, mode=mode, seed=seed, keep=keep,
+                    user_range=user_range, epoch_offset=epoch_offset)
     if order is not None:
         p.order = order
     if sampler is not None:
@@ -270,11 +348,46 @@ def fit_ex(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, 
         assert perms.shape == (epochs, interactions.shape[0]), "[perms] must be int32 [epochs, N]"
     else:
         perms = None
+    if on_epoch is not None:                 # per-epoch reporting needs a session (the one-shot call has no callback argument)
+        sess = Session(p, keep)
+        try:
+            try:
+                return sess.train(epochs, perms, on_epoch=on_epoch)
+            finally:
+                sess.download(w_i, w_if, v_u, v_i, v_uf, v_if)
+        finally:
+            sess.close()
     stats = (EpochStats * epochs)()
     rc = _lib.lib().rfm_fit(C.byref(p), epochs, ptr(perms), C.cast(stats, C.c_void_p))
     out = _stats_list(stats, epochs)
     check(rc)
     return out
+
+
+def _print_epoch(epoch, log_likelihood, penalty):
+    print("\ntraining epoch:", epoch)                                          # _rankfm.pyx:332-336
+    print("log likelihood:", round(float(np.float32(log_likelihood - penalty)), 2))
+
+
+def _training_session(interactions, sample_weight, user_items, x_uf, x_if, weights, hyper, max_samples):
+    """the resident training session for exactly this data / these hyper-parameters, (re)built when anything differs.
+    -> (session, fresh): `fresh` sessions were created from `weights` and need no further upload"""
+    from_csr = hasattr(user_items, "indptr") and hasattr(user_items, "indices")
+    indptr, indices = user_items_to_csr(user_items, weights[2].shape[0])
+    key = (_fingerprint(interactions), _fingerprint(sample_weight), _fingerprint(indptr, from_csr), _fingerprint(indices, from_csr),
+           _fingerprint(x_uf), _fingerprint(x_if), tuple(w.shape for w in weights), tuple(hyper), int(max_samples),
+           _SEED, _DEVICE, _COMM["rank"], _COMM["world"], None if _COMM["nccl_id"] is None else _COMM["nccl_id"].tobytes(), _COMM["user_range"])
+    if _training["key"] == key and _training["sess"] is not None:
+        _training["hits"] += 1
+        return _training["sess"], False
+    drop_training()
+    keep = []
+    user_items = user_items if from_csr else UserItems(indptr, indices)
+    p = fit_problem(interactions, sample_weight, user_items, x_uf, x_if, *weights, *hyper, max_samples, mode="production", keep=keep,
+                    epoch_offset=_EPOCHS["done"])
+    _training.update(key=key, sess=Session(p, keep))
+    _training["builds"] += 1
+    return _training["sess"], True
 
 
 def _fit(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
@@ -283,7 +396,8 @@ def _fit(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_
     arrays are updated in place, nothing is returned, ``AssertionError`` if weights go non-finite."""
     global last_stats
     drop_resident()                                                            # the weights are about to change in place
-    perms = None
+    hyper = (alpha, beta, learning_rate, learning_schedule, learning_exponent)
+    weights = (w_i, w_if, v_u, v_i, v_uf, v_if)
     if _MODE == "replay":
         N = interactions.shape[0]
         shuffle_index = np.arange(N, dtype=np.int32)                           # _rankfm.pyx:197
@@ -291,12 +405,39 @@ def _fit(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_
         for e in range(epochs):
             np.random.shuffle(shuffle_index)                                   # _rankfm.pyx:227 (cumulative)
             perms[e] = shuffle_index
-    last_stats = fit_ex(interactions, sample_weight, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if,
-                        alpha, beta, learning_rate, learning_schedule, learning_exponent, max_samples, epochs, perms=perms)
-    if verbose:
-        for e, s in enumerate(last_stats):                                     # _rankfm.pyx:332-336
-            print("\ntraining epoch:", e)
-            print("log likelihood:", round(float(np.float32(s["log_likelihood"] - s["penalty"])), 2))
+        last_stats = fit_ex(interactions, sample_weight, user_items, x_uf, x_if, *weights, *hyper, max_samples, epochs, perms=perms)
+        if verbose:
+            for e, st in enumerate(last_stats):
+                _print_epoch(e, st["log_likelihood"], st["penalty"])
+        return
+    # production: the log-likelihood of every epoch is printed as the epoch completes (_rankfm.pyx:332-336)
+    on_epoch = (lambda e, st: _print_epoch(e, st["log_likelihood"], st["penalty"])) if verbose else None
+    if not _RESIDENT_TRAIN:
+        try:
+            last_stats = fit_ex(interactions, sample_weight, user_items, x_uf, x_if, *weights, *hyper, max_samples, epochs,
+                                epoch_offset=_EPOCHS["done"], on_epoch=on_epoch)
+        finally:
+            _EPOCHS["done"] += int(epochs)
+        return
+    as_buffer(interactions, np.int32, 2, "interactions")
+    as_buffer(sample_weight, np.float32, 1, "sample_weight")
+    if learning_schedule not in _lib.SCHEDULE:
+        raise ValueError('unknown [learning_schedule]')                       # _rankfm.pyx:225
+    sess, fresh = _training_session(interactions, sample_weight, user_items, x_uf, x_if, weights, hyper, max_samples)
+    try:
+        if not fresh:
+            for a, nd, name in zip(weights, (1, 1, 2, 2, 2, 2), WEIGHT_NAMES):
+                as_buffer(a, np.float32, nd, name)
+            sess.set_weights(*weights)                                         # warm start from the caller's arrays
+        try:
+            last_stats = sess.train(epochs, on_epoch=on_epoch)
+        finally:
+            _EPOCHS["done"] += int(epochs)
+            last_stats = sess.last_stats
+            sess.download(*weights)          # like the reference, weights are written back even when they went non-finite
+    except Exception:
+        drop_training()
+        raise
 
 
 def _predict(pairs, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if):
@@ -358,16 +499,32 @@ class Session:
     def __init__(self, problem, keep):
         self._keep = keep
         self._p = problem
+        self.last_stats = None
         h = C.c_void_p()
         check(_lib.lib().rfm_session_create(C.byref(problem), C.byref(h)))
         self._h = h
 
-    def train(self, epochs, perms=None):
+    def train(self, epochs, perms=None, on_epoch=None):
+        """`on_epoch(epoch, stats_dict)` is called after every epoch (one stream synchronisation each)"""
         stats = (EpochStats * epochs)()
-        rc = _lib.lib().rfm_session_train(self._h, epochs, ptr(perms), C.cast(stats, C.c_void_p))
-        out = _stats_list(stats, epochs)
+        cb = None
+        if on_epoch is not None:
+            cb = _lib.EPOCH_CALLBACK(lambda e, st, _user: on_epoch(int(e), _stats_list([st.contents], 1)[0]))
+            check(_lib.lib().rfm_session_set_epoch_callback(self._h, cb, None))
+        try:
+            rc = _lib.lib().rfm_session_train(self._h, epochs, ptr(perms), C.cast(stats, C.c_void_p))
+        finally:
+            if cb is not None:
+                _lib.lib().rfm_session_set_epoch_callback(self._h, _lib.EPOCH_CALLBACK(), None)
+        self.last_stats = _stats_list(stats, epochs)
         check(rc)
-        return out
+        return self.last_stats
+
+    def exchange_path(self):
+        """multi-GPU: 0 = single GPU, 1 = fused peer-memory kernel, 2 = ncclAllReduce fallback"""
+        path = C.c_int32()
+        check(_lib.lib().rfm_session_exchange_path(self._h, C.byref(path)))
+        return path.value
 
     def set_weights(self, w_i, w_if, v_u, v_i, v_uf, v_if):
         check(_lib.lib().rfm_session_set_weights(self._h, *[ptr(a) for a in (w_i, w_if, v_u, v_i, v_uf, v_if)]))

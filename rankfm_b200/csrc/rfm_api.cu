@@ -15,11 +15,13 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/rankfm_b200.h"
-#include "rfm_kernels.h"
+#include "rfm_host.h"
 #include <cuda_bf16.h>
 
 using namespace rfm;
+using rfmh::fail;
+using rfmh::dev_malloc;
+using rfmh::dev_free;
 
 namespace rfm { bool gemm_encode_available(); }
 static bool encode_ok() { return rfm::gemm_encode_available(); }
@@ -29,7 +31,7 @@ static bool encode_ok() { return rfm::gemm_encode_available(); }
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...)
+int rfmh::fail(int code, const char* fmt, ...)
 {
     char buf[1024];
     va_list ap;
@@ -39,12 +41,6 @@ static int fail(int code, const char* fmt, ...)
     g_err = buf;
     return code;
 }
-
-#define CU(call)                                                                                       \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess) return fail(RFM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
 
 extern "C" const char* rfm_version(void) { return "rankfm_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* rfm_last_error(void) { return g_err.c_str(); }
@@ -92,7 +88,7 @@ void trim_locked(int dev)
 }
 }  // namespace
 
-static cudaError_t dev_malloc(void** out, size_t bytes)
+cudaError_t rfmh::dev_malloc(void** out, size_t bytes)
 {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -115,7 +111,7 @@ static cudaError_t dev_malloc(void** out, size_t bytes)
     return e;
 }
 
-static void dev_free(void* p)
+void rfmh::dev_free(void* p)
 {
     if (!p) return;
     std::unique_lock<std::mutex> lock(g_blocks.mu);
@@ -142,53 +138,10 @@ extern "C" int rfm_trim_device_cache(void)
     return RFM_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// NCCL, loaded lazily so that single-GPU use has no NCCL dependency
-// ---------------------------------------------------------------------------------------------------------------
-struct Id128 { char b[128]; };   // ncclUniqueId is 128 opaque bytes, passed by value
-namespace {
-struct NcclApi {
-    void* h = nullptr;
-    int (*GetUniqueId)(void*) = nullptr;
-    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
-    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
-    int (*CommDestroy)(void*) = nullptr;
-    const char* (*GetErrorString)(int) = nullptr;
-};
-}  // namespace
-static NcclApi g_nccl;
-
-static int nccl_load()
-{
-    if (g_nccl.h) return RFM_OK;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    void* h = nullptr;
-    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
-    if (!h) return fail(RFM_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
-    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
-    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
-    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
-    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
-    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
-        return fail(RFM_ERR_NCCL, "libnccl.so.2 lacks required symbols");
-    g_nccl.h = h;
-    return RFM_OK;
-}
-#define NC(call)                                                                                        \
-    do {                                                                                                \
-        int r_ = (call);                                                                                \
-        if (r_ != 0) return fail(RFM_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
-    } while (0)
-constexpr int kNcclFloat = 7, kNcclSum = 0;   // ncclFloat32, ncclSum (nccl.h enum values, stable across 2.x)
-
 extern "C" int rfm_nccl_unique_id(uint8_t* out128)
 {
     if (!out128) return fail(RFM_ERR_ARG, "out128 is NULL");
-    int rc = nccl_load();
-    if (rc) return rc;
-    NC(g_nccl.GetUniqueId(out128));
-    return RFM_OK;
+    return rfmh::nccl_unique_id(out128);
 }
 
 extern "C" int rfm_host_register(void* ptr, uint64_t bytes)
@@ -247,9 +200,15 @@ struct rfm_session {
     int epochs_done = 0;
     int grid = 148;
     int64_t launches = 0;
+    // real allocations behind the tables.  T.UT, d_indptr, d_indices and d_bitmap are VIRTUAL bases when the session holds
+    // only the users [T.u0, T.u0+T.Un) of a multi-GPU job: indexing them with a global user id lands in
+    // the allocation; T.IT / T.GP / d_item_touch sit in the communicator's peer window when `p2p`
+    float* ut_alloc = nullptr; int64_t* indptr_alloc = nullptr; int32_t* indices_alloc = nullptr; uint32_t* bitmap_alloc = nullptr;
     // multi-GPU
-    void* comm = nullptr;
-    float *d_it_snap = nullptr, *d_gp_snap = nullptr, *d_ut_init = nullptr;
+    rfmh::Comm* comm = nullptr;
+    bool p2p = false;
+    float *d_it_snap = nullptr, *d_gp_snap = nullptr;
+    double* d_red = nullptr; int red_cap = 0;       // end-of-training reduction of the epoch records over the ranks
     float* d_gp_acc = nullptr;
     float *d_xuf = nullptr, *d_xif = nullptr;   // device copies of x_uf [U,P] / x_if [I,Q] (only when that block is active)
     int32_t* d_item_touch = nullptr;    // multi-GPU: how often each item occurs as a positive in this rank's shard
@@ -265,6 +224,7 @@ struct rfm_session {
     std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
     float* d_flush = nullptr; size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;
+    rfm_epoch_callback epoch_cb = nullptr; void* epoch_cb_user = nullptr;
 };
 
 static size_t round4(size_t x) { return (x + 3) & ~(size_t)3; }
@@ -302,14 +262,14 @@ static int upload_weights(rfm_session* s, const float* w_i, const float* w_if, c
     const Tables& T = s->T;
     DevBuf<float> st_vu, st_vi, st_wi, st_g;
     int rc;
-    if ((rc = st_vu.alloc((size_t)T.U * T.F))) return rc;
+    if ((rc = st_vu.alloc((size_t)T.Un * T.F))) return rc;
     if ((rc = st_vi.alloc((size_t)T.I * T.F))) return rc;
     if ((rc = st_wi.alloc((size_t)T.I))) return rc;
-    CU(cudaMemcpyAsync(st_vu, v_u, (size_t)T.U * T.F * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(st_vu, v_u + (size_t)T.u0 * T.F, (size_t)T.Un * T.F * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(st_vi, v_i, (size_t)T.I * T.F * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(st_wi, w_i, (size_t)T.I * 4, cudaMemcpyHostToDevice, s->st));
     // the (read-only) feature matrices are uploaded once per session and kept, so later weight uploads need no host copy
-    if (T.Pp && !s->d_xuf) { if ((rc = dev_alloc(&s->d_xuf, (size_t)T.U * T.P))) return rc; CU(cudaMemcpyAsync(s->d_xuf, x_uf, (size_t)T.U * T.P * 4, cudaMemcpyHostToDevice, s->st)); }
+    if (T.Pp && !s->d_xuf) { if ((rc = dev_alloc(&s->d_xuf, (size_t)T.Un * T.P))) return rc; CU(cudaMemcpyAsync(s->d_xuf, x_uf + (size_t)T.u0 * T.P, (size_t)T.Un * T.P * 4, cudaMemcpyHostToDevice, s->st)); }
     if (T.Qp && !s->d_xif) { if ((rc = dev_alloc(&s->d_xif, (size_t)T.I * T.Q))) return rc; CU(cudaMemcpyAsync(s->d_xif, x_if, (size_t)T.I * T.Q * 4, cudaMemcpyHostToDevice, s->st)); }
     CU(launch_pack_users(T, st_vu, s->d_xuf, s->st));
     CU(launch_pack_items(T, st_vi, st_wi, s->d_xif, s->st));
@@ -326,16 +286,37 @@ static int upload_weights(rfm_session* s, const float* w_i, const float* w_if, c
     return RFM_OK;
 }
 
+// 32-bit pivot arithmetic of group_member (rfm_common.cuh): G * degree < 2^32 with G <= 32
+constexpr int64_t kMaxUserDegree = ((int64_t)1 << 32) / 32;
+
+// (re)seed the device MT19937 state on the host exactly like init_genrand (mt19937ar.c:60-73); pos = N -> first draw twists
+static int seed_mt(rfm_session* s)
+{
+    MtState h;
+    uint32_t prev = s->p.mt_seed;
+    h.s[0] = prev;
+    for (int k = 1; k < kMtN; ++k) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)k; h.s[k] = prev; }
+    h.pos = kMtN;
+    if (!s->d_mt) { int rc = dev_alloc(&s->d_mt, 1); if (rc) return rc; }
+    CU(cudaMemcpy(s->d_mt, &h, sizeof h, cudaMemcpyHostToDevice));
+    return RFM_OK;
+}
+
 extern "C" int rfm_session_destroy(rfm_session* s)
 {
     if (!s) return RFM_OK;
     cudaSetDevice(s->device);
-    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    if (s->st) cudaStreamSynchronize(s->st);
+    if (s->comm) {                     // the communicator (and its peer window) stays cached in the library for the next session
+        rfmh::comm_window_detach(s->comm, s);
+        rfmh::comm_release(s->comm);
+    }
     for (auto e : s->ev) cudaEventDestroy(e);
-    dev_free(s->T.UT); dev_free(s->T.IT); dev_free(s->T.GP);
-    dev_free(s->d_inter); dev_free(s->d_sw); dev_free(s->d_indptr); dev_free(s->d_indices);
-    dev_free(s->d_bitmap); dev_free(s->d_perm); dev_free(s->d_mult); dev_free(s->d_mt); dev_free(s->d_acc);
-    dev_free(s->d_it_snap); dev_free(s->d_gp_snap); dev_free(s->d_ut_init); dev_free(s->d_flush); dev_free(s->d_gp_acc); dev_free(s->d_item_touch); dev_free(s->d_xuf); dev_free(s->d_xif);
+    dev_free(s->ut_alloc);
+    if (!s->p2p) { dev_free(s->T.IT); dev_free(s->T.GP); dev_free(s->d_item_touch); }
+    dev_free(s->d_inter); dev_free(s->d_sw); dev_free(s->indptr_alloc); dev_free(s->indices_alloc);
+    dev_free(s->bitmap_alloc); dev_free(s->d_perm); dev_free(s->d_mult); dev_free(s->d_mt); dev_free(s->d_acc);
+    dev_free(s->d_it_snap); dev_free(s->d_gp_snap); dev_free(s->d_red); dev_free(s->d_flush); dev_free(s->d_gp_acc); dev_free(s->d_xuf); dev_free(s->d_xif);
     dev_free(s->d_snap_ut); dev_free(s->d_snap_it); dev_free(s->d_snap_gp); dev_free(s->d_trace);
     dev_free(s->d_gemm_B); dev_free(s->d_gemm_bias); dev_free(s->d_gemm_order);
     for (void* q : s->scratch) dev_free(q);
@@ -358,6 +339,10 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
     if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return fail(RFM_ERR_ARG, "bad rank/world %d/%d", p->rank, p->world);
     if (p->sampler == RFM_SAMPLER_MT && p->sched != RFM_SCHED_SERIAL) return fail(RFM_ERR_ARG, "the MT19937 sampler needs the serial schedule");
     if (p->max_samples < 1) return fail(RFM_ERR_ARG, "max_samples must be >= 1");
+    if (p->epoch_offset < 0) return fail(RFM_ERR_ARG, "epoch_offset < 0");
+    const bool ranged = p->user_lo != 0 || p->user_hi != 0;
+    if (ranged && (p->user_lo < 0 || p->user_hi <= p->user_lo || p->user_hi > p->U))
+        return fail(RFM_ERR_ARG, "bad user range [%d, %d) for %d users", p->user_lo, p->user_hi, p->U);
     const int ndev = rfm_device_count();
     if (ndev == 0) return fail(RFM_ERR_NO_DEVICE, "no CUDA device: rankfm_b200 has no CPU fallback");
     if (p->device < 0 || p->device >= ndev) return fail(RFM_ERR_ARG, "device %d out of range (%d devices)", p->device, ndev);
@@ -365,6 +350,7 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
     rfm_session* s = new rfm_session();
     s->p = *p;
     s->device = p->device;
+    s->epochs_done = p->epoch_offset;
     int rc = RFM_OK;
     auto bail = [&](int code) { rfm_session_destroy(s); return code; };
 #define TRY(x) do { rc = (x); if (rc) return bail(rc); } while (0)
@@ -384,7 +370,11 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
 
     Tables& T = s->T;
     T.U = p->U; T.I = p->I; T.F = p->F; T.P = p->P; T.Q = p->Q;
-    T.x_uf_any = any_nonzero(p->x_uf, (size_t)p->U * p->P) ? 1 : 0;     // _rankfm.pyx:193-194
+    T.u0 = ranged ? p->user_lo : 0;
+    T.Un = ranged ? p->user_hi - p->user_lo : p->U;
+    // the flags decide the table layout and which kernel variant runs: every rank of a multi-GPU job must reach the same
+    // answer, so they are computed over ALL users / items like the reference does (_rankfm.pyx:193-194)
+    T.x_uf_any = any_nonzero(p->x_uf, (size_t)p->U * p->P) ? 1 : 0;
     T.x_if_any = any_nonzero(p->x_if, (size_t)p->I * p->Q) ? 1 : 0;
     T.Fp = (int)round4(p->F); T.NQ = T.Fp / 4;
     T.Pp = T.x_uf_any ? (int)round4(p->P) : 0;
@@ -401,22 +391,35 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
         if (std::max(T.Pp, T.Qp) > 4 * G || qpl > 4)
             return bail(fail(RFM_ERR_UNSUPPORTED, "unsupported shape: factors=%d (max 512), active user/item features %d/%d (max 128)", p->F, T.Pp ? p->P : 0, T.Qp ? p->Q : 0));
     }
-    TRY(dev_alloc(&T.UT, (size_t)T.U * T.ldu));
-    TRY(dev_alloc(&T.IT, (size_t)T.I * T.ldi));
-    TRY(dev_alloc(&T.GP, s->gp_floats));
+    if (p->world > 1) {
+        // communicator of this job: created by the first session, kept by the library for the following ones
+        TRY(rfmh::comm_acquire(p->nccl_id, p->rank, p->world, p->device, &s->comm));
+        const rfmh::ExchangeShape shape{T.I, T.ldi, T.NQ, T.Fp, s->gp_floats};
+        TRY(rfmh::comm_window_attach(s->comm, shape, s->st, s, &T.IT, &T.GP, &s->d_item_touch, &s->p2p));
+    }
+    TRY(dev_alloc(&s->ut_alloc, (size_t)T.Un * T.ldu));
+    T.UT = s->ut_alloc - (ptrdiff_t)T.u0 * T.ldu;                   // virtual base: T.UT + u*ldu is the row of GLOBAL user u
+    if (!s->p2p) {
+        TRY(dev_alloc(&T.IT, (size_t)T.I * T.ldi));
+        TRY(dev_alloc(&T.GP, s->gp_floats));
+    }
     TRY(upload_weights(s, p->w_i, p->w_if, p->v_u, p->v_i, p->v_uf, p->v_if, p->x_uf, p->x_if));
 
     s->N = p->n_interactions;
     if (s->N > 0) {
-        s->nnz = p->csr_indptr[p->U];
+        // user_items of the owned users only: indptr[u0 .. u0+Un] and the slice of indices they point into
+        const int64_t nz0 = p->csr_indptr[T.u0], nz1 = p->csr_indptr[T.u0 + T.Un];
+        s->nnz = nz1 - nz0;
         TRY(dev_alloc(&s->d_inter, (size_t)s->N));
         TRY(dev_alloc(&s->d_sw, (size_t)s->N));
-        TRY(dev_alloc(&s->d_indptr, (size_t)p->U + 1));
-        TRY(dev_alloc(&s->d_indices, (size_t)s->nnz));
+        TRY(dev_alloc(&s->indptr_alloc, (size_t)T.Un + 1));
+        TRY(dev_alloc(&s->indices_alloc, (size_t)s->nnz));
+        s->d_indptr = s->indptr_alloc - T.u0;
+        s->d_indices = s->indices_alloc - nz0;
         CUB(cudaMemcpyAsync(s->d_inter, p->interactions, (size_t)s->N * 8, cudaMemcpyHostToDevice, s->st));
         CUB(cudaMemcpyAsync(s->d_sw, p->sample_weight, (size_t)s->N * 4, cudaMemcpyHostToDevice, s->st));
-        CUB(cudaMemcpyAsync(s->d_indptr, p->csr_indptr, ((size_t)p->U + 1) * 8, cudaMemcpyHostToDevice, s->st));
-        CUB(cudaMemcpyAsync(s->d_indices, p->csr_indices, (size_t)s->nnz * 4, cudaMemcpyHostToDevice, s->st));
+        CUB(cudaMemcpyAsync(s->indptr_alloc, p->csr_indptr + T.u0, ((size_t)T.Un + 1) * 8, cudaMemcpyHostToDevice, s->st));
+        CUB(cudaMemcpyAsync(s->indices_alloc, p->csr_indices + nz0, (size_t)s->nnz * 4, cudaMemcpyHostToDevice, s->st));
         s->h_indptr.assign(p->csr_indptr, p->csr_indptr + p->U + 1);
         // WARP multiplier by number of draws: log((I-1)//sampled)/log(I)  (_rankfm.pyx:269, integer quotient)
         std::vector<float> mult((size_t)p->max_samples + 1, 0.f);
@@ -424,32 +427,30 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
             mult[k] = (float)(std::log((double)((long)(p->I - 1) / (long)k)) / std::log((double)p->I));
         TRY(dev_alloc(&s->d_mult, mult.size()));
         CUB(cudaMemcpyAsync(s->d_mult, mult.data(), mult.size() * 4, cudaMemcpyHostToDevice, s->st));
-        if (p->sampler == RFM_SAMPLER_MT) {
-            // seed on the host exactly like init_genrand (mt19937ar.c:60-73), pos = N -> first draw twists
-            MtState h;
-            uint32_t prev = p->mt_seed;
-            h.s[0] = prev;
-            for (int k = 1; k < kMtN; ++k) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)k; h.s[k] = prev; }
-            h.pos = kMtN;
-            TRY(dev_alloc(&s->d_mt, 1));
-            CUB(cudaMemcpyAsync(s->d_mt, &h, sizeof h, cudaMemcpyHostToDevice, s->st));
-        }
+        if (p->sampler == RFM_SAMPLER_MT) TRY(seed_mt(s));
         if (p->order == RFM_ORDER_HOST) TRY(dev_alloc(&s->d_perm, (size_t)s->N));
-        if (s->nnz >= ((int64_t)1 << 31) / 32) return bail(fail(RFM_ERR_UNSUPPORTED, "user_items larger than 2^26 entries per user are not supported"));
         {
-            // membership bitmap when U x I bits fit the budget: default min(8 GiB, a quarter of the free HBM);
+            // the (G+1)-ary membership search does 32-bit pivot arithmetic on G * (a user's degree), G <= 32
+            int64_t max_deg = 0;
+            for (int u = T.u0; u < T.u0 + T.Un; ++u) max_deg = std::max(max_deg, p->csr_indptr[u + 1] - p->csr_indptr[u]);
+            if (max_deg >= kMaxUserDegree)
+                return bail(fail(RFM_ERR_UNSUPPORTED, "a user with %lld observed items: more than %lld per user are not supported", (long long)max_deg, (long long)kMaxUserDegree - 1));
+        }
+        {
+            // membership bitmap when (owned users) x I bits fit the budget: default min(8 GiB, a quarter of the free HBM);
             // RANKFM_B200_BITMAP_MB overrides, 0 disables (the kernels then search the CSR)
             const char* env = getenv("RANKFM_B200_BITMAP_MB");
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             const double budget_mb = env ? atof(env) : std::min(8192.0, (double)free_b / (4.0 * 1024.0 * 1024.0));
             const int words = (p->I + 31) / 32;
-            const double need_mb = (double)p->U * words * 4.0 / (1024.0 * 1024.0);
+            const double need_mb = (double)T.Un * words * 4.0 / (1024.0 * 1024.0);
             if (need_mb <= budget_mb) {
                 s->bitmap_words = words;
-                TRY(dev_alloc(&s->d_bitmap, (size_t)p->U * words));
-                CUB(cudaMemsetAsync(s->d_bitmap, 0, (size_t)p->U * words * 4, s->st));
-                CUB(launch_build_bitmap(s->d_indptr, s->d_indices, p->U, s->d_bitmap, words, s->st));
+                TRY(dev_alloc(&s->bitmap_alloc, (size_t)T.Un * words));
+                s->d_bitmap = s->bitmap_alloc - (ptrdiff_t)T.u0 * words;
+                CUB(cudaMemsetAsync(s->bitmap_alloc, 0, (size_t)T.Un * words * 4, s->st));
+                CUB(launch_build_bitmap(s->indptr_alloc, s->d_indices, T.Un, s->bitmap_alloc, words, s->st));
                 s->launches += 1;
             }
         }
@@ -470,20 +471,12 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
         if (const char* e = getenv("RANKFM_B200_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // experiments
         s->grid = s->n_sm * per_sm;
     }
-    if (p->world > 1) {
-        TRY(nccl_load());
-        if (!p->nccl_id) return bail(fail(RFM_ERR_ARG, "world>1 needs nccl_id"));
-        Id128 id;
-        memcpy(id.b, p->nccl_id, 128);
-        int r = g_nccl.CommInitRank(&s->comm, p->world, id, p->rank);
-        if (r != 0) return bail(fail(RFM_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    if (s->comm) {
         TRY(dev_alloc(&s->d_it_snap, (size_t)T.I * T.ldi));
         TRY(dev_alloc(&s->d_gp_snap, s->gp_floats));
-        TRY(dev_alloc(&s->d_ut_init, (size_t)T.U * T.ldu));
-        TRY(dev_alloc(&s->d_item_touch, (size_t)T.I));
+        if (!s->p2p) TRY(dev_alloc(&s->d_item_touch, (size_t)T.I));
         CUB(cudaMemsetAsync(s->d_item_touch, 0, (size_t)T.I * 4, s->st));
         if (s->N > 0) { item_histogram_kernel<<<s->n_sm * 4, 256, 0, s->st>>>(s->d_inter, s->N, s->d_item_touch); s->launches += 1; }
-        CUB(cudaMemcpyAsync(s->d_ut_init, T.UT, (size_t)T.U * T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
         CUB(cudaStreamSynchronize(s->st));
     }
 #undef TRY
@@ -500,16 +493,9 @@ extern "C" int rfm_session_set_weights(rfm_session* s, const float* w_i, const f
     int rc = upload_weights(s, w_i, w_if, v_u, v_i, v_uf, v_if, nullptr, nullptr);   // features stay as uploaded at creation
     if (rc) return rc;
     s->gemm_valid = false;
-    if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->T.UT, (size_t)s->T.U * s->T.ldu * 4, cudaMemcpyDeviceToDevice, s->st));
-    s->epochs_done = 0;
-    if (s->d_mt) {
-        MtState h;
-        uint32_t prev = s->p.mt_seed;
-        h.s[0] = prev;
-        for (int k = 1; k < kMtN; ++k) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)k; h.s[k] = prev; }
-        h.pos = kMtN;
-        CU(cudaMemcpyAsync(s->d_mt, &h, sizeof h, cudaMemcpyHostToDevice, s->st));
-    }
+    // the Philox / Feistel keys keep counting over the life of the session (`epochs_done`): new weights are a warm start
+    // (`fit_partial`), not a replay; the MT19937 stream restarts like the reference re-seeds it in every `_fit` (:182)
+    if (s->d_mt) { rc = seed_mt(s); if (rc) return rc; }
     CU(cudaStreamSynchronize(s->st));
     return RFM_OK;
 }
@@ -518,14 +504,14 @@ extern "C" int rfm_session_snapshot(rfm_session* s)
 {
     if (!s) return fail(RFM_ERR_ARG, "NULL session");
     CU(cudaSetDevice(s->device));
-    const size_t nu = (size_t)s->T.U * s->T.ldu, ni = (size_t)s->T.I * s->T.ldi;
+    const size_t nu = (size_t)s->T.Un * s->T.ldu, ni = (size_t)s->T.I * s->T.ldi;
     int rc;
     if (!s->d_snap_ut) {
         if ((rc = dev_alloc(&s->d_snap_ut, nu))) return rc;
         if ((rc = dev_alloc(&s->d_snap_it, ni))) return rc;
         if ((rc = dev_alloc(&s->d_snap_gp, s->gp_floats))) return rc;
     }
-    CU(cudaMemcpyAsync(s->d_snap_ut, s->T.UT, nu * 4, cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_snap_ut, s->ut_alloc, nu * 4, cudaMemcpyDeviceToDevice, s->st));
     CU(cudaMemcpyAsync(s->d_snap_it, s->T.IT, ni * 4, cudaMemcpyDeviceToDevice, s->st));
     CU(cudaMemcpyAsync(s->d_snap_gp, s->T.GP, s->gp_floats * 4, cudaMemcpyDeviceToDevice, s->st));
     s->snap_epochs = s->epochs_done;
@@ -537,11 +523,10 @@ extern "C" int rfm_session_restore(rfm_session* s)
 {
     if (!s || !s->d_snap_ut) return fail(RFM_ERR_ARG, "no snapshot to restore");
     CU(cudaSetDevice(s->device));
-    const size_t nu = (size_t)s->T.U * s->T.ldu, ni = (size_t)s->T.I * s->T.ldi;
-    CU(cudaMemcpyAsync(s->T.UT, s->d_snap_ut, nu * 4, cudaMemcpyDeviceToDevice, s->st));
+    const size_t nu = (size_t)s->T.Un * s->T.ldu, ni = (size_t)s->T.I * s->T.ldi;
+    CU(cudaMemcpyAsync(s->ut_alloc, s->d_snap_ut, nu * 4, cudaMemcpyDeviceToDevice, s->st));
     CU(cudaMemcpyAsync(s->T.IT, s->d_snap_it, ni * 4, cudaMemcpyDeviceToDevice, s->st));
     CU(cudaMemcpyAsync(s->T.GP, s->d_snap_gp, s->gp_floats * 4, cudaMemcpyDeviceToDevice, s->st));
-    if (s->comm) CU(cudaMemcpyAsync(s->d_ut_init, s->d_snap_ut, nu * 4, cudaMemcpyDeviceToDevice, s->st));
     s->epochs_done = s->snap_epochs;
     s->gemm_valid = false;
     return RFM_OK;
@@ -574,7 +559,7 @@ extern "C" int rfm_session_download(rfm_session* s, float* w_i, float* w_if, flo
     const Tables& T = s->T;
     DevBuf<float> st_vu, st_vi, st_wi, st_g;
     int rc;
-    if ((rc = st_vu.alloc((size_t)T.U * T.F))) return rc;
+    if ((rc = st_vu.alloc((size_t)T.Un * T.F))) return rc;
     if ((rc = st_vi.alloc((size_t)T.I * T.F))) return rc;
     if ((rc = st_wi.alloc((size_t)T.I))) return rc;
     const size_t n_wif = (size_t)T.Q, n_vuf = (size_t)T.P * T.F, n_vif = (size_t)T.Q * T.F;
@@ -583,7 +568,8 @@ extern "C" int rfm_session_download(rfm_session* s, float* w_i, float* w_if, flo
     CU(launch_unpack_items(T, st_vi, st_wi, s->st));
     CU(launch_unpack_globals(T, st_g, st_g + n_wif, st_g + n_wif + n_vuf, s->st));
     s->launches += 3;
-    CU(cudaMemcpyAsync(v_u, st_vu, (size_t)T.U * T.F * 4, cudaMemcpyDeviceToHost, s->st));
+    // only the rows this session owns are written: with a user-partitioned job the other rows belong to other ranks
+    CU(cudaMemcpyAsync(v_u + (size_t)T.u0 * T.F, st_vu, (size_t)T.Un * T.F * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(v_i, st_vi, (size_t)T.I * T.F * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(w_i, st_wi, (size_t)T.I * 4, cudaMemcpyDeviceToHost, s->st));
     if (T.x_if_any) CU(cudaMemcpyAsync(w_if, st_g, n_wif * 4, cudaMemcpyDeviceToHost, s->st));
@@ -612,7 +598,8 @@ static int exchange_deltas(rfm_session* s, float* cur, float* snap, size_t n, fl
 {
     const int grid = s->n_sm * 4;
     delta_kernel<<<grid, 256, 0, s->st>>>(cur, snap, n, scale);
-    NC(g_nccl.AllReduce(cur, cur, n, kNcclFloat, kNcclSum, s->comm, s->st));
+    int rc = rfmh::comm_allreduce_f32(s->comm, cur, n, s->st);
+    if (rc) return rc;
     apply_kernel<<<grid, 256, 0, s->st>>>(cur, snap, n);
     s->launches += 2;
     CU(cudaGetLastError());
@@ -645,14 +632,15 @@ __global__ void item_delta_kernel(float* __restrict__ cur, const float* __restri
     }
 }
 
-static int exchange_item_deltas(rfm_session* s, const EpochAcc* acc, float eta)
+// NCCL fallback of the per-epoch exchange (the default is the fused peer-memory kernel, rfm_comm.cu)
+static int exchange_item_deltas_nccl(rfm_session* s, const EpochAcc* acc, float lam_factor, float lam_bias)
 {
     const Tables& T = s->T;
     const int grid = s->n_sm * 4;
     const size_t n = (size_t)T.I * T.ldi;
-    const float lam_factor = eta * (2.0f * s->p.alpha + 0.01f), lam_bias = eta * (2.0f * s->p.alpha + 0.15f);
     item_delta_kernel<<<grid, 256, 0, s->st>>>(T.IT, s->d_it_snap, T.I, T.ldi, T.Fp, s->d_item_touch, acc, lam_factor, lam_bias, (float)s->p.world);
-    NC(g_nccl.AllReduce(T.IT, T.IT, n, kNcclFloat, kNcclSum, s->comm, s->st));
+    int rc = rfmh::comm_allreduce_f32(s->comm, T.IT, n, s->st);
+    if (rc) return rc;
     apply_kernel<<<grid, 256, 0, s->st>>>(T.IT, s->d_it_snap, n);
     s->launches += 2;
     CU(cudaGetLastError());
@@ -662,12 +650,83 @@ static int exchange_item_deltas(rfm_session* s, const EpochAcc* acc, float eta)
 // Folding C independent chains of a parameter with per-step decay (1-lambda), each run for n steps from the same start:
 // theta = start + gain * sum_c (theta_c - start).  gain = (1 - d^C) / (C (1 - d)), d = (1-lambda)^n, is exact for the
 // decay part: 1 (sum of deltas) when the chains barely move, 1/C (average) when each chain has forgotten its start.
+// logistic curvature per touch assumed by the per-row fold gain of the item table (DESIGN.md "Per-row fold gain")
+constexpr float kCurvatureFactor = 0.01f, kCurvatureBias = 0.15f;
+
 static float fold_gain(double lambda, double n, double C)
 {
     if (C <= 1.0) return 1.0f;
     const double d = std::pow(std::max(0.0, 1.0 - lambda), n);
     if (1.0 - d < 1e-12) return 1.0f;
     return (float)((1.0 - std::pow(d, C)) / (C * (1.0 - d)));
+}
+
+// Read back the records of epochs [e0, e1) of the current rfm_session_train call, fold them over the ranks of a multi-GPU
+// job, fill `stats`, run the epoch callback and turn non-finite weights into RFM_ERR_NONFINITE (`assert_finite`,
+// _rankfm.pyx:95-103,329) -- `status` keeps the first failure.
+static int collect_epochs(rfm_session* s, int e0, int e1, const std::vector<float>& etas, rfm_epoch_stats* stats, int& status)
+{
+    if (e1 <= e0) return status;
+    const rfm_problem& p = s->p;
+    const int n = e1 - e0;
+    std::vector<EpochAcc> acc((size_t)n);
+    CU(cudaMemcpyAsync(acc.data(), s->d_acc + e0, (size_t)n * sizeof(EpochAcc), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    if (s->comm) {
+        // user rows are owned by exactly one rank and stay there (no collective on v_u).  The epoch records
+        // are per shard: sum log-likelihood / draws / the v_u part of the penalty over the ranks (one tiny allreduce)
+        int rc = rfmh::comm_check(s->comm, s->st);
+        if (rc) return rc;
+        constexpr int kRed = 5;
+        if (s->red_cap < n) {
+            dev_free(s->d_red); s->d_red = nullptr;
+            if ((rc = dev_alloc(&s->d_red, (size_t)n * kRed))) return rc;
+            s->red_cap = n;
+        }
+        std::vector<double> red((size_t)n * kRed);
+        for (int e = 0; e < n; ++e) {
+            const EpochAcc& a = acc[(size_t)e];
+            double* r = red.data() + (size_t)e * kRed;
+            r[0] = a.ll; r[1] = (double)a.draws; r[2] = a.bad ? 1.0 : 0.0; r[3] = a.wstats[2]; r[4] = a.wstats[6 + 2];
+        }
+        CU(cudaMemcpyAsync(s->d_red, red.data(), red.size() * 8, cudaMemcpyHostToDevice, s->st));
+        if ((rc = rfmh::comm_allreduce_f64(s->comm, s->d_red, red.size(), s->st))) return rc;
+        CU(cudaMemcpyAsync(red.data(), s->d_red, red.size() * 8, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        for (int e = 0; e < n; ++e) {
+            EpochAcc& a = acc[(size_t)e];
+            const double* r = red.data() + (size_t)e * kRed;
+            a.ll = r[0]; a.draws = (long long)(r[1] + 0.5); a.bad = r[2] > 0.5 ? 1 : 0; a.wstats[2] = r[3]; a.wstats[6 + 2] = r[4];
+        }
+    }
+    for (int e = e0; e < e1; ++e) {
+        const EpochAcc& a = acc[(size_t)(e - e0)];
+        rfm_epoch_stats st{};
+        st.log_likelihood = a.ll;
+        st.draws = a.draws;
+        st.eta = etas[(size_t)e];
+        st.penalty = (double)p.alpha * (a.wstats[6 + 0] + a.wstats[6 + 2] + a.wstats[6 + 3]) + (double)p.beta * (a.wstats[6 + 1] + a.wstats[6 + 4] + a.wstats[6 + 5]);
+        for (int k = 0; k < 6; ++k) st.finite[k] = std::isfinite(a.wstats[k]) ? 1 : 0;
+        cudaEventElapsedTime(&st.kernel_ms, s->ev[4 * e + 0], s->ev[4 * e + 1]);
+        cudaEventElapsedTime(&st.sync_ms, s->ev[4 * e + 2], s->ev[4 * e + 3]);
+        if (stats) stats[e] = st;
+        if (s->epoch_cb) s->epoch_cb(e, &st, s->epoch_cb_user);
+        if (status == RFM_OK) {
+            static const char* names[6] = {"item weights [w_i]", "item feature weights [w_if]", "user factors [v_u]", "item factors [v_i]",
+                                           "user-feature factors [v_uf]", "item-feature factors [v_if]"};
+            for (int k = 0; k < 6; ++k)
+                if (!st.finite[k]) { status = fail(RFM_ERR_NONFINITE, "%s are not finite - try decreasing feature/sample_weight magnitudes", names[k]); break; }
+            if (status == RFM_OK && a.bad) status = fail(RFM_ERR_NONFINITE, "pairwise utilities are not finite - try decreasing feature/sample_weight magnitudes");
+        }
+    }
+    return status;
+}
+
+extern "C" int rfm_session_set_epoch_callback(rfm_session* s, rfm_epoch_callback cb, void* user)
+{
+    if (!s) return fail(RFM_ERR_ARG, "NULL session");
+    s->epoch_cb = cb; s->epoch_cb_user = user;
+    return RFM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -710,6 +769,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     tp.mt = p.sampler == RFM_SAMPLER_MT ? s->d_mt : nullptr;
     tp.trace = s->d_trace;
     std::vector<float> etas((size_t)epochs);
+    int status = RFM_OK, cb_done = 0;
     const char* spec_s = getenv("RANKFM_B200_SPEC");          // 0 (default) = adaptive, else force 1 / 2 / 4
     const int spec_env = spec_s ? atoi(spec_s) : 0;
     // Hogwild staleness cap: never keep more than 1/8 of an epoch in flight, so that on small inputs the schedule
@@ -731,7 +791,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
         if (p.schedule == RFM_SCHEDULE_INVSCALING) eta = (float)(((double)p.learning_rate) / std::pow((double)(e + 1), (double)p.learning_exponent));
         etas[e] = eta;
         tp.eta = eta;
-        tp.epoch_key = (uint32_t)(s->epochs_done + e);
+        tp.epoch_key = (uint32_t)(s->epochs_done + e);                 // epochs_done starts at the problem's epoch_offset
         tp.acc = s->d_acc + e;
         tp.prev_acc = e > 0 ? s->d_acc + (e - 1) : nullptr;
         tp.spec = tp.serial ? 4 : spec_env;
@@ -760,51 +820,32 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
         s->launches += 1;
         CU(cudaEventRecord(s->ev[4 * e + 2], s->st));
         if (s->comm) {
-            int rc = exchange_item_deltas(s, s->d_acc + e, eta);
-            if (rc) return rc;
-            if (s->T.x_uf_any || s->T.x_if_any) {
-                // every rank ran its own feature-parameter chains: fold the ranks with the same rule
-                const float rank_gain = feat_parallel ? fold_gain((double)tp.reg_b * eta, (double)s->N, (double)p.world) : 1.0f;
-                rc = exchange_deltas(s, s->T.GP, s->d_gp_snap, s->gp_floats, rank_gain);
-                if (rc) return rc;
+            // fold the ranks' replicas of the item table (and of the feature parameters: every rank ran its own chains, same rule)
+            const bool has_gp = s->T.x_uf_any || s->T.x_if_any;
+            const float rank_gain = feat_parallel ? fold_gain((double)tp.reg_b * eta, (double)s->N, (double)p.world) : 1.0f;
+            const float lam_factor = eta * (2.0f * p.alpha + kCurvatureFactor), lam_bias = eta * (2.0f * p.alpha + kCurvatureBias);
+            int rc;
+            if (s->p2p) {
+                rc = rfmh::comm_exchange_p2p(s->comm, s->st, s->d_it_snap, has_gp ? s->d_gp_snap : nullptr, s->d_acc + e, lam_factor, lam_bias, rank_gain);
+                s->launches += 1;
+            } else {
+                rc = exchange_item_deltas_nccl(s, s->d_acc + e, lam_factor, lam_bias);
+                if (!rc && has_gp) rc = exchange_deltas(s, s->T.GP, s->d_gp_snap, s->gp_floats, rank_gain);
             }
+            if (rc) return rc;
         }
         CU(cudaEventRecord(s->ev[4 * e + 3], s->st));
         CU(launch_weight_stats(s->T, (s->d_acc + e)->wstats, s->n_sm * 2, s->st));
         s->launches += 1;
+        if (s->epoch_cb) {                      // verbose callers see every epoch as it completes, like the reference's prints (:332-336)
+            int rc = collect_epochs(s, e, e + 1, etas, stats, status);
+            if (rc != RFM_OK && rc != RFM_ERR_NONFINITE) return rc;
+            cb_done = e + 1;
+        }
     }
     s->epochs_done += epochs;
     s->gemm_valid = false;
-    if (s->comm) {
-        // user rows are owned by exactly one rank: the sum over ranks of (UT - UT_at_start) restores the full table
-        const size_t n = (size_t)s->T.U * s->T.ldu;
-        int rc = exchange_deltas(s, s->T.UT, s->d_ut_init, n);
-        if (rc) return rc;
-    }
-    std::vector<EpochAcc> acc((size_t)epochs);
-    CU(cudaMemcpyAsync(acc.data(), s->d_acc, (size_t)epochs * sizeof(EpochAcc), cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
-    int status = RFM_OK;
-    for (int e = 0; e < epochs; ++e) {
-        const EpochAcc& a = acc[e];
-        rfm_epoch_stats st{};
-        st.log_likelihood = a.ll;
-        st.draws = a.draws;
-        st.eta = etas[e];
-        st.penalty = (double)p.alpha * (a.wstats[6 + 0] + a.wstats[6 + 2] + a.wstats[6 + 3]) + (double)p.beta * (a.wstats[6 + 1] + a.wstats[6 + 4] + a.wstats[6 + 5]);
-        for (int k = 0; k < 6; ++k) st.finite[k] = std::isfinite(a.wstats[k]) ? 1 : 0;
-        cudaEventElapsedTime(&st.kernel_ms, s->ev[4 * e + 0], s->ev[4 * e + 1]);
-        cudaEventElapsedTime(&st.sync_ms, s->ev[4 * e + 2], s->ev[4 * e + 3]);
-        if (stats) stats[e] = st;
-        if (status == RFM_OK) {
-            static const char* names[6] = {"item weights [w_i]", "item feature weights [w_if]", "user factors [v_u]", "item factors [v_i]",
-                                           "user-feature factors [v_uf]", "item-feature factors [v_if]"};
-            for (int k = 0; k < 6; ++k)
-                if (!st.finite[k]) { status = fail(RFM_ERR_NONFINITE, "%s are not finite - try decreasing feature/sample_weight magnitudes", names[k]); break; }
-            if (status == RFM_OK && a.bad) status = fail(RFM_ERR_NONFINITE, "pairwise utilities are not finite - try decreasing feature/sample_weight magnitudes");
-        }
-    }
-    return status;
+    return collect_epochs(s, cb_done, epochs, etas, stats, status);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1126,7 +1167,7 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     CU(cudaSetDevice(s->device));
     std::vector<int32_t> hu;
     users_to_int(users, n_users, hu);
-    for (auto u : hu) if (u >= s->T.U) return fail(RFM_ERR_ARG, "user index %d out of range", u);
+    for (auto u : hu) if (u >= 0 && (u < s->T.u0 || u >= s->T.u0 + s->T.Un)) return fail(RFM_ERR_ARG, "user index %d out of range [%d, %d)", u, s->T.u0, s->T.u0 + s->T.Un);
     std::vector<int64_t> order;
     const int64_t n_tc = recommend_plan(s, hu, n_items, filter_previous, order);
     std::vector<int32_t> hp((size_t)n_users);
@@ -1250,6 +1291,13 @@ extern "C" int rfm_session_flush_l2(rfm_session* s)
     return RFM_OK;
 }
 
+extern "C" int rfm_session_exchange_path(rfm_session* s, int32_t* path)
+{
+    if (!s || !path) return fail(RFM_ERR_ARG, "NULL argument");
+    *path = !s->comm ? 0 : (s->p2p ? 1 : 2);
+    return RFM_OK;
+}
+
 extern "C" int rfm_session_launch_count(rfm_session* s, int64_t* launches)
 {
     if (!s || !launches) return fail(RFM_ERR_ARG, "NULL argument");
@@ -1306,8 +1354,10 @@ static int attach_csr(rfm_session* s, const rfm_problem* p)
     if (!p->csr_indptr || !p->csr_indices) return fail(RFM_ERR_ARG, "filter_previous needs csr_indptr / csr_indices");
     const int64_t nnz = p->csr_indptr[p->U];
     int rc;
-    if ((rc = dev_alloc(&s->d_indptr, (size_t)p->U + 1))) return rc;
-    if ((rc = dev_alloc(&s->d_indices, (size_t)nnz))) return rc;
+    if (s->T.Un != s->T.U) return fail(RFM_ERR_UNSUPPORTED, "scoring with filter_previous needs a session that holds all users");
+    if ((rc = dev_alloc(&s->indptr_alloc, (size_t)p->U + 1))) return rc;
+    if ((rc = dev_alloc(&s->indices_alloc, (size_t)nnz))) return rc;
+    s->d_indptr = s->indptr_alloc; s->d_indices = s->indices_alloc;
     CU(cudaMemcpyAsync(s->d_indptr, p->csr_indptr, ((size_t)p->U + 1) * 8, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(s->d_indices, p->csr_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, s->st));
     s->h_indptr.assign(p->csr_indptr, p->csr_indptr + p->U + 1);
@@ -1319,7 +1369,8 @@ extern "C" int rfm_session_attach_csr(rfm_session* s, const int64_t* indptr, con
 {
     if (!s || !indptr || !indices) return fail(RFM_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
-    dev_free(s->d_indptr); dev_free(s->d_indices);
+    dev_free(s->indptr_alloc); dev_free(s->indices_alloc);
+    s->indptr_alloc = nullptr; s->indices_alloc = nullptr;
     s->d_indptr = nullptr; s->d_indices = nullptr;
     rfm_problem q = s->p;
     q.csr_indptr = indptr; q.csr_indices = indices;
@@ -1345,6 +1396,7 @@ extern "C" int rfm_session_similar(rfm_session* s, int32_t which, int32_t index,
     if (which != 0 && which != 1) return fail(RFM_ERR_ARG, "which must be 0 (items) or 1 (users)");
     const int rows = which == 0 ? s->T.I : s->T.U;
     if (index < 0 || index >= rows) return fail(RFM_ERR_ARG, "index out of range");
+    if (which == 1 && s->T.Un != s->T.U) return fail(RFM_ERR_UNSUPPORTED, "similar_users needs a session that holds all users");
     if (n < 1 || n > 16384) return fail(RFM_ERR_ARG, "n out of range");
     CU(cudaSetDevice(s->device));
     DevBuf<float> qc, S, d_rec; DevBuf<int32_t> d_one, d_ex;

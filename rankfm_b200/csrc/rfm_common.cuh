@@ -19,6 +19,8 @@ namespace rfm {
 struct Tables {
     float *UT, *IT, *GP;
     int32_t U, I, F, Fp, NQ;     // NQ = Fp/4 factor quads
+    int32_t u0, Un;              // the user table holds the rows of users [u0, u0+Un) only (multi-GPU: this rank's users); UT is the
+                                 // VIRTUAL base of the full table, so UT + u*ldu is the row of global user u for every owned u
     int32_t P, Pp, Q, Qp;        // Pp/Qp = 0 when that feature block is inactive
     int32_t ldu, ldi;            // row strides in floats
     int32_t x_uf_any, x_if_any;

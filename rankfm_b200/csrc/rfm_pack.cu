@@ -4,16 +4,18 @@
 
 namespace rfm {
 
+// v_u / x_uf here are the staged rows of the OWNED users [T.u0, T.u0+T.Un) (row 0 = user T.u0)
 __global__ void pack_users_kernel(const Tables T, const float* __restrict__ v_u, const float* __restrict__ x_uf)
 {
-    const long long n = (long long)T.U * T.ldu;
+    const long long n = (long long)T.Un * T.ldu;
+    float* base = T.UT + (long long)T.u0 * T.ldu;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const long long u = e / T.ldu;
         const int c = (int)(e % T.ldu);
         float v = 0.f;
         if (c < T.F) v = v_u[u * T.F + c];
         else if (c >= T.Fp && c - T.Fp < T.P && T.Pp > 0) v = x_uf[u * T.P + (c - T.Fp)];
-        T.UT[e] = v;
+        base[e] = v;
     }
 }
 
@@ -33,9 +35,10 @@ __global__ void pack_items_kernel(const Tables T, const float* __restrict__ v_i,
 
 __global__ void unpack_users_kernel(const Tables T, float* __restrict__ v_u)
 {
-    const long long n = (long long)T.U * T.F;
+    const long long n = (long long)T.Un * T.F;
+    const float* base = T.UT + (long long)T.u0 * T.ldu;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
-        v_u[e] = T.UT[(e / T.F) * T.ldu + (e % T.F)];
+        v_u[e] = base[(e / T.F) * T.ldu + (e % T.F)];
 }
 
 __global__ void unpack_items_kernel(const Tables T, float* __restrict__ v_i, float* __restrict__ w_i)
@@ -71,7 +74,7 @@ static inline int grid_for(long long n) { return (int)(n / 256 + 1 > 148 * 8 ? 1
 
 cudaError_t launch_pack_users(const Tables& T, const float* v_u, const float* x_uf, cudaStream_t st)
 {
-    pack_users_kernel<<<grid_for((long long)T.U * T.ldu), 256, 0, st>>>(T, v_u, x_uf);
+    pack_users_kernel<<<grid_for((long long)T.Un * T.ldu), 256, 0, st>>>(T, v_u, x_uf);
     return cudaGetLastError();
 }
 cudaError_t launch_pack_items(const Tables& T, const float* v_i, const float* w_i, const float* x_if, cudaStream_t st)
@@ -81,7 +84,7 @@ cudaError_t launch_pack_items(const Tables& T, const float* v_i, const float* w_
 }
 cudaError_t launch_unpack_users(const Tables& T, float* v_u, cudaStream_t st)
 {
-    unpack_users_kernel<<<grid_for((long long)T.U * T.F), 256, 0, st>>>(T, v_u);
+    unpack_users_kernel<<<grid_for((long long)T.Un * T.F), 256, 0, st>>>(T, v_u);
     return cudaGetLastError();
 }
 cudaError_t launch_unpack_items(const Tables& T, float* v_i, float* w_i, cudaStream_t st)

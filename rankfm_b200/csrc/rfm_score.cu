@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) predict_kernel(const Tables T, const floa
         const bool inb = r < n;
         float2 pr = make_float2(0.f, 0.f);
         if (inb) pr = __ldg(pairs + r);
-        const bool known = inb && !isnan(pr.x) && !isnan(pr.y);            // NaN index = cold-start id (:383-384)
+        // NaN index = cold-start id (:383-384); users whose rows this session does not hold (multi-GPU shard) score NaN too
+        const bool known = inb && !isnan(pr.x) && !isnan(pr.y) && (int)pr.x >= T.u0 && (int)pr.x < T.u0 + T.Un;
         const int u = known ? (int)pr.x : 0, i = known ? (int)pr.y : 0;
         UserCtx<QPL> uc;
         ItemRow<QPL> it;

@@ -518,10 +518,12 @@ cudaError_t launch_gp_apply(float* gp, float* acc, int n, cudaStream_t st)
 // ---------------------------------------------------------------------------------------------------------------
 // per-user membership bitmap (small catalogues): replaces the search of user_items by one bit test per draw
 // ---------------------------------------------------------------------------------------------------------------
+// indptr [U+1] holds offsets into `indices` that need not start at 0 (a rank's slice of a global CSR); row u of the bitmap
+// belongs to the u-th user of that slice
 __global__ void build_bitmap_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int U, uint32_t* __restrict__ bitmap, int words)
 {
-    const long long nnz = indptr[U];
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+    const long long first = indptr[0], nnz = indptr[U];
+    for (long long e = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = U;                                   // owner of CSR slot e: last u with indptr[u] <= e
         while (hi - lo > 1) { const int md = (lo + hi) >> 1; if (indptr[md] <= e) lo = md; else hi = md; }
         const int it = indices[e];
@@ -543,9 +545,9 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const Tables T, doubl
 {
     double s[6] = {0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-    const long long uq = (long long)T.U * T.NQ, iq = (long long)T.I * T.NQ;
+    const long long uq = (long long)T.Un * T.NQ, iq = (long long)T.I * T.NQ;      // owned user rows only
     for (long long e = tid; e < uq; e += nth) {
-        const float4 v = ld_cg4(T.UT + (e / T.NQ) * T.ldu + 4 * (e % T.NQ));
+        const float4 v = ld_cg4(T.UT + (T.u0 + e / T.NQ) * T.ldu + 4 * (e % T.NQ));
         s[2] += (double)v.x + v.y + v.z + v.w; s2[2] += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
     }
     for (long long e = tid; e < iq; e += nth) {
