@@ -121,6 +121,24 @@ int rfm_host_unregister(void *ptr);
 int rfm_debug_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4);
 int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_t r0, int64_t count, int64_t *out);
 
+/* ---- data preparation on the device: what `RankFM._init_all` / `_init_interactions` do with pandas on
+ * the host (`rankfm.py:114-177`) and `_fit` with a Python loop (`_rankfm.pyx:201-212`), as device radix sorts ---- */
+
+/* sorted unique ids and the index of every id in that list: `np.unique` + the `user_to_index` / `item_to_index` Series maps
+ * (`rankfm.py:114-128,150-155`) for integer ids.  unique_out must have room for n values. */
+int rfm_prep_index_ids(const int64_t *ids, int64_t n, int32_t device, int64_t *unique_out, int64_t *n_unique_out, int32_t *index_out);
+/* `user_items` (`rankfm.py:165-174`: {user_idx: sorted item_idx array}, duplicates kept) as CSR: indptr_out [U+1],
+ * indices_out [n], each user's items ascending */
+int rfm_prep_user_items(const int32_t *interactions /* [n,2] */, int64_t n, int32_t U, int32_t I, int32_t device,
+                        int64_t *indptr_out, int32_t *indices_out);
+/* bench tooling: synthetic interactions of the BASELINE.json shapes: user ~ Zipf(a_u) over U ranks, item ~
+ * Zipf(a_i) over I ranks, de-duplicated, trimmed to N pairs in random order, ids randomly permuted (perm_seed: ranks of a
+ * multi-GPU job share the item popularity ranking) and, if `reindex`, re-indexed to the observed uniques like
+ * `rankfm.py:115-116`.  out int32 [N,2] (user index + user_offset, item index); n_out <= N pairs were written;
+ * users_out / items_out = number of distinct users / items observed. */
+int rfm_synth_zipf(int32_t U, int32_t I, int64_t N, double a_u, double a_i, uint64_t seed, uint64_t perm_seed, int32_t reindex,
+                   int32_t user_offset, int32_t device, int32_t *out, int64_t *n_out, int32_t *users_out, int32_t *items_out);
+
 /* ---- one-shot calls on host buffers: the drop-in boundary ---- */
 
 /* replaces `_fit` (`_rankfm.pyx:122-342`): trains `epochs` epochs, updates the six weight arrays in place.

@@ -216,8 +216,18 @@ class UserItems(dict):
         return (UserItems, (self.indptr, self.indices))
 
     @classmethod
-    def from_interactions(cls, interactions, n_users):
-        """CSR of the items of each user, sorted ascending, duplicates kept (like ``rankfm.py:174``)"""
+    def from_interactions(cls, interactions, n_users, n_items=None):
+        """CSR of the items of each user, sorted ascending, duplicates kept (like ``rankfm.py:174``).  One radix sort on the
+        GPU (``rfm_prep_user_items``) when a device is present and the input is large enough to pay for the copies, else
+        one NumPy key sort -- same result either way (``tests/test_gpu_parity.py::test_device_prep_matches_host_prep``)."""
+        inter = np.asarray(interactions)
+        if len(inter) >= _PREP_DEVICE_MIN and device_count() > 0:
+            n_items = int(inter[:, 1].max()) + 1 if n_items is None else int(n_items)
+            return cls(*prep_user_items(inter, n_users, n_items))
+        return cls.from_interactions_host(inter, n_users)
+
+    @classmethod
+    def from_interactions_host(cls, interactions, n_users):
         inter = np.asarray(interactions)
         n_items = int(inter[:, 1].max()) + 1 if len(inter) else 1
         keys = inter[:, 0].astype(np.int64) * n_items + inter[:, 1]        # one key sort instead of a 2-key lexsort
@@ -226,6 +236,29 @@ class UserItems(dict):
         indptr = np.zeros(n_users + 1, dtype=np.int64)
         np.cumsum(counts, out=indptr[1:])
         return cls(indptr, (keys % n_items).astype(np.int32))
+
+
+_PREP_DEVICE_MIN = int(os.environ.get("RANKFM_B200_PREP_DEVICE_MIN", 200_000))   # below this the host sort is faster than the PCIe round trip
+
+
+def prep_user_items(interactions, n_users, n_items):
+    """``user_items`` as CSR (indptr int64 [U+1], indices int32 [N]) by a device radix sort (``rankfm.py:165-174``)"""
+    inter = np.ascontiguousarray(interactions, dtype=np.int32)
+    indptr = np.empty(n_users + 1, dtype=np.int64)
+    indices = np.empty(len(inter), dtype=np.int32)
+    check(_lib.lib().rfm_prep_user_items(ptr(inter), len(inter), int(n_users), int(n_items), _DEVICE, ptr(indptr), ptr(indices)))
+    return indptr, indices
+
+
+def prep_index_ids(ids):
+    """(sorted unique ids, int32 index of every id in them) for integer ids, on the device: ``np.unique`` + the Series maps of
+    ``rankfm.py:114-128,150-155``"""
+    ids64 = np.ascontiguousarray(ids, dtype=np.int64)
+    uniq = np.empty(len(ids64), dtype=np.int64)
+    index = np.empty(len(ids64), dtype=np.int32)
+    n = C.c_int64()
+    check(_lib.lib().rfm_prep_index_ids(ptr(ids64), len(ids64), _DEVICE, ptr(uniq), C.byref(n), ptr(index)))
+    return uniq[:n.value].copy(), index
 
 
 def user_items_to_csr(user_items, n_users):
@@ -491,6 +524,20 @@ def shard_by_user(interactions, sample_weight, n_users, rank, world):
     lo, hi = bounds[rank], bounds[rank + 1]
     sel = (interactions[:, 0] >= lo) & (interactions[:, 0] < hi)
     return np.ascontiguousarray(interactions[sel]), np.ascontiguousarray(sample_weight[sel]), (int(lo), int(hi))
+
+
+def allgather_user_rows(v_u, user_range):
+    """multi-process jobs (torch.distributed initialised by the caller, any backend): after a sharded ``_fit`` every
+    rank holds the trained rows of ITS users only; this assembles the full user table in every rank's ``v_u`` in place.
+    Control plane, outside the hot path: one broadcast per rank of the row range it owns."""
+    import torch
+    import torch.distributed as dist
+    ranges = [None] * dist.get_world_size()
+    dist.all_gather_object(ranges, (int(user_range[0]), int(user_range[1])))
+    for src, (lo, hi) in enumerate(ranges):
+        if hi > lo:
+            dist.broadcast(torch.from_numpy(v_u[lo:hi]), src=src)
+    return v_u
 
 
 class Session:

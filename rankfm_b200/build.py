@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librankfm_b200.so")
-SOURCES = ["rfm_api.cu", "rfm_comm.cu", "rfm_train.cu", "rfm_score.cu", "rfm_pack.cu", "rfm_gemm.cu"]
+SOURCES = ["rfm_api.cu", "rfm_comm.cu", "rfm_train.cu", "rfm_score.cu", "rfm_pack.cu", "rfm_gemm.cu", "rfm_prep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-diag-suppress", "63"]
 

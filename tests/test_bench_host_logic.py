@@ -24,6 +24,7 @@ class _FakeSession:
     def timer_stop(self): return 12.5
     def launch_count(self): return self.launches
     def close(self): pass
+    def exchange_path(self): return 0
 
     def train(self, epochs):
         self.launches += 2 * epochs
@@ -42,10 +43,12 @@ def test_run_ours_assembles_the_line(monkeypatch, capsys):
     monkeypatch.setattr(_rankfm, "pin", lambda *a: None)
     monkeypatch.setattr(_rankfm, "unpin", lambda *a: None)
     monkeypatch.setattr(_rankfm, "_fit", oracle._fit)
+    monkeypatch.setattr(_rankfm, "set_resident_training", lambda flag: None)
+    monkeypatch.setattr(_rankfm, "drop_training", lambda: None)
     monkeypatch.setattr(bench, "ClockSampler", lambda index: type("C", (), {"stop": lambda self: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 1}})())
     monkeypatch.setenv("BENCH_CPU_BASELINE_S", "2")
     monkeypatch.setitem(bench.CONFIGS, "cfg1", dict(bench.CONFIGS["cfg1"], N=20_000, epochs=2))
-    args = argparse.Namespace(gpus=1, steps=3, warmup=3, impl="ours", workload="cfg1", no_cpu_baseline=False, no_recommend=True, no_large=True)
+    args = argparse.Namespace(gpus=1, steps=3, warmup=3, impl="ours", workload="cfg1", no_cpu_baseline=False, no_recommend=True, sub="all")
     bench.run_ours(args)
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -58,8 +61,9 @@ def test_run_ours_assembles_the_line(monkeypatch, capsys):
     assert r["bound"] == "hbm" and np.isclose(r["achieved"], N * bytes_per_positive / 0.5e-3 / 1e9) and np.isclose(r["frac"], r["achieved"] / r["peak"])
     assert np.isclose(r["mean_draws_per_positive"], 1.5) and d["gpu_launches"] == 12
     e = d["e2e"]
-    assert e["unit"] == "interactions/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and len(e["ms_each"]) >= 15
+    assert e["unit"] == "interactions/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and len(e["ms_each"]) >= 3
     assert np.isclose(e["value"], N * 2 / (e["ms_per_step"] * 1e-3))
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] == 1 and c["value"] > 0
-    assert d["recommend"] is None and d["roofline_dram_resident"] is None and d["clocks"]["reasons"] == []
+    assert d["e2e_resident"]["h2d_bytes_per_step"] < e["h2d_bytes_per_step"]
+    assert "recommend" not in d and "workloads" not in d and d["clocks"]["reasons"] == []
