@@ -105,3 +105,37 @@ def topk_overlap(rec_a, rec_b):
         tot += len(sa & sb) / max(len(sb), 1)
         n += 1
     return tot / max(n, 1)
+
+
+def golden_module():
+    """tests/golden/make_golden.py as a module (its problem generators are shared with the tests so that large cases only
+    store OUTPUTS: the inputs are regenerated from the seed with NumPy's stream-stable legacy generator)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cfg1_case():
+    """BASELINE.json configs[0] at its named size + the reference's outputs for it -> (problem dict, golden dict)"""
+    p = golden_module().cfg1_problem()
+    z = np.load(os.path.join(GOLDEN, "cfg1_bpr.npz"))
+    g = {k: z[k] for k in z.files}
+    assert int(g["n_interactions"]) == len(p["X"]) and int(g["checksum"]) == int(p["X"].astype(np.int64).sum()), \
+        "the regenerated cfg1 inputs differ from the ones the golden was minted on (NumPy legacy stream changed?)"
+    return p, g
+
+
+def assert_topn_exact_up_to_rounding(got, scores64, n, tol):
+    """`got` is THE top-n of `scores64` (float64 ground truth), except that candidates whose scores differ by less than the
+    float32 rounding bound `tol` may swap places or swap across the cut: (1) n distinct entries, (2) everything clearly
+    above the n-th best score is present, (3) nothing clearly below it is, (4) the order is descending up to tol"""
+    got = np.asarray(got)
+    assert len(got) == n and len(set(got.tolist())) == n, got
+    kth = np.sort(scores64)[::-1][n - 1]
+    s = scores64[got]
+    must = set(np.flatnonzero(scores64 > kth + tol).tolist())
+    assert must <= set(got.tolist()), (sorted(must - set(got.tolist())), kth)
+    assert (s >= kth - tol).all(), (s, kth)
+    assert (s[:-1] >= s[1:] - tol).all(), s

@@ -100,3 +100,33 @@ def test_shard_by_user_partitions_everything():
         assert 150 < len(xs) < 350
         seen += len(xs)
     assert seen == 1000
+
+
+def test_problem_validates_shapes_before_any_pointer_crosses_the_abi():
+    """x_uf / x_if are read as [U,P] / [I,Q] with P, Q taken from v_uf / v_if -- mismatching widths must never
+    reach the library.  All-zero matrices of another width are what `fit(features)` then `fit_partial()` without features
+    produces (rankfm.py:199,236; the reference never reads them: `x_uf_any`, _rankfm.pyx:193): they are replaced by zeros
+    of the right width; anything else is an error."""
+    import numpy as np
+    import pytest
+    from rankfm_b200 import _rankfm
+    U, I, F, P, Q = 5, 4, 3, 2, 3
+    f32 = np.float32
+    w = dict(w_i=np.zeros(I, f32), w_if=np.zeros(Q, f32), v_u=np.zeros((U, F), f32), v_i=np.zeros((I, F), f32), v_uf=np.zeros((P, F), f32), v_if=np.zeros((Q, F), f32))
+    order = ('w_i', 'w_if', 'v_u', 'v_i', 'v_uf', 'v_if')
+    keep = []
+    p = _rankfm._problem(np.zeros((U, 1), f32), np.zeros((I, 1), f32), *[w[k] for k in order], keep)
+    assert (p.U, p.I, p.P, p.Q, p.F) == (U, I, P, Q, F)
+    assert keep[0].shape == (U, P) and keep[1].shape == (I, Q) and not keep[0].any() and not keep[1].any()
+    with pytest.raises(ValueError):
+        _rankfm._problem(np.ones((U, 1), f32), np.zeros((I, Q), f32), *[w[k] for k in order], [])
+    with pytest.raises(ValueError):
+        _rankfm._problem(np.zeros((U, P), f32), np.ones((I, Q + 1), f32), *[w[k] for k in order], [])
+    with pytest.raises(ValueError):
+        _rankfm._problem(np.zeros((U + 1, P), f32), np.zeros((I, Q), f32), *[w[k] for k in order], [])
+    bad = dict(w, w_i=np.zeros(I + 1, f32))
+    with pytest.raises(ValueError):
+        _rankfm._problem(np.zeros((U, P), f32), np.zeros((I, Q), f32), *[bad[k] for k in order], [])
+    bad = dict(w, v_if=np.zeros((Q, F + 1), f32))
+    with pytest.raises(ValueError):
+        _rankfm._problem(np.zeros((U, P), f32), np.zeros((I, Q), f32), *[bad[k] for k in order], [])

@@ -189,3 +189,39 @@ def test_evaluation_metrics(backend):
     assert both["precision"] == pytest.approx(precision(model, test, k, True))
     div = diversity(model, test, k, True)
     assert list(div.columns) == ['item_id', 'cnt_users', 'pct_users'] and div['cnt_users'].sum() == 3 * k and len(div) == 6
+
+
+def _reference_trained_model(g):
+    """our class carrying the model the REFERENCE trained (tests/golden/make_golden.py::eval_case): same id maps (sorted
+    unique ids of the training interactions), the reference's weights"""
+    model = RankFM(factors=8, loss='warp', max_samples=5, learning_schedule='invscaling')
+    model._init_all(g['train'])
+    for k in ('w_i', 'w_if', 'v_u', 'v_i', 'v_uf', 'v_if'):
+        assert getattr(model, k).shape == g[k + '_ref'].shape, k
+        setattr(model, k, np.ascontiguousarray(g[k + '_ref']))
+    model.is_fit = True
+    return model
+
+
+def test_evaluation_matches_the_reference_evaluation_module(backend):
+    """the five ranking metrics + diversity against values computed by the REFERENCE's `rankfm/evaluation.py:9-175` through
+    the reference's own class on a 1,500-user model (golden eval_ref.npz): same model, same test set, same numbers"""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_ref.npz")))
+    model = _reference_trained_model(g)
+    test = g['test']
+    fns = dict(hit_rate=hit_rate, reciprocal_rank=reciprocal_rank, dcg=discounted_cumulative_gain, precision=precision, recall=recall)
+    for k in (5, 10):
+        for filt in (False, True):
+            tag = "_k%d_%s" % (k, "filt" if filt else "all")
+            for name, fn in fns.items():
+                assert fn(model, test, k=k, filter_previous=filt) == pytest.approx(float(g[name + tag]), rel=1e-12, abs=1e-15), name + tag
+            both = all_metrics(model, test, k=k, filter_previous=filt)
+            assert both["hit_rate"] == pytest.approx(float(g["hit_rate" + tag]), rel=1e-12)
+            assert both["discounted_cumulative_gain"] == pytest.approx(float(g["dcg" + tag]), rel=1e-12)
+            assert both["recall"] == pytest.approx(float(g["recall" + tag]), rel=1e-12)
+    div = diversity(model, test, k=10, filter_previous=True)
+    ours = dict(zip(div['item_id'].values.tolist(), div['cnt_users'].values.tolist()))
+    ref = dict(zip(g['diversity_item_id'].tolist(), g['diversity_cnt_users'].tolist()))
+    assert ours == ref                                                       # the order among equal counts is unspecified (unstable sort)
+    assert np.array_equal(div['cnt_users'].values, g['diversity_cnt_users']) and np.allclose(div['pct_users'].values, g['diversity_pct_users'], rtol=1e-12)

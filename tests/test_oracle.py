@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from helpers import KERNEL_CASES, WEIGHTS, golden_fit_args, load_golden
+from helpers import CSRItems, KERNEL_CASES, WEIGHTS, golden_fit_args, load_golden
 from oracle import oracle
 
 # init_genrand(1492); genrand_int32() x6 -- verified against the reference's mt19937ar.c
@@ -87,3 +87,20 @@ def test_philox_sampler_is_deterministic_and_order_free():
         by_row_1 = np.empty(N, np.int64); by_row_1[oracle.feistel_perm(N, 77, e)] = out1['neg'][e]
         by_row_3 = np.empty(N, np.int64); by_row_3[g['perms'][e]] = out3['neg'][e]
         assert np.array_equal(by_row_1, by_row_3)
+
+
+def test_oracle_replay_at_cfg1_named_size_matches_reference_golden():
+    """BASELINE.json configs[0] (10k x 5k, 100k interactions, factors=16, bpr, 5 epochs) at its NAMED size: the oracle's
+    sequential replay of the reference's row order + MT19937 stream against weights / predict() / recommend() minted from
+    the unmodified reference (tests/golden/make_golden.py::cfg1_case)"""
+    from helpers import cfg1_case, rel_err, topk_overlap
+    p, g = cfg1_case()
+    w = {k: v.copy() for k, v in p['w'].items()}
+    ui = CSRItems(p['indptr'], p['indices'])
+    oracle.fit_ex(p['X'], p['sw'], ui, p['x_uf'], p['x_if'], *[w[k] for k in WEIGHTS], *p['hyper'], 1, p['epochs'], perms=p['perms'])
+    for k in ('w_i', 'v_u', 'v_i'):
+        assert rel_err(w[k], g[k + '_ref']) < 1e-4, k          # fast-math vs strict IEEE over 437k sequential steps
+    scores = oracle._predict(p['pairs'], p['x_uf'], p['x_if'], *[w[k] for k in WEIGHTS])
+    assert rel_err(scores, g['scores']) < 1e-4
+    rec = oracle._recommend(p['users'], ui, 10, True, p['x_uf'], p['x_if'], *[w[k] for k in WEIGHTS])
+    assert topk_overlap(rec, g['rec_filtered']) >= 0.99
