@@ -120,6 +120,11 @@ int rfm_host_unregister(void *ptr);
  * contract shared with the oracle: Philox4x32-10 block and the per-epoch Feistel permutation of [0,n) */
 int rfm_debug_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4);
 int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_t r0, int64_t count, int64_t *out);
+/* device self-test of the production kernel's side-feature code specialised for <= 8 + 8 feature columns (csrc/rfm_feat8.cuh)
+ * against the generic code, on pseudo-random rows: out5 = max |difference| of the hoisted user vectors a[], b[]
+ * (`_rankfm.pyx:67-87`), of the feature parameters after one gradient step (`:283-326`), of the row deltas, and the largest
+ * parameter movement of that step (so a caller can see the step was not a no-op).  P or Q = 0: that block is inactive. */
+int rfm_debug_feat8(int32_t F, int32_t P, int32_t Q, uint32_t seed, float *out5);
 
 /* ---- data preparation on the device: what `RankFM._init_all` / `_init_interactions` do with pandas on
  * the host (`rankfm.py:114-177`) and `_fit` with a Python loop (`_rankfm.pyx:201-212`), as device radix sorts ---- */

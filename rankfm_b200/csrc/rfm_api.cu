@@ -170,6 +170,26 @@ extern "C" int rfm_debug_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t 
     return RFM_OK;
 }
 
+extern "C" int rfm_debug_feat8(int32_t F, int32_t P, int32_t Q, uint32_t seed, float* out5)
+{
+    if (!out5 || F < 1 || P < 0 || Q < 0 || (P == 0 && Q == 0)) return fail(RFM_ERR_ARG, "bad argument");
+    if (rfm_device_count() == 0) return fail(RFM_ERR_NO_DEVICE, "no CUDA device: rankfm_b200 has no CPU fallback");
+    Tables T{};
+    T.U = 1; T.I = 2; T.Un = 1; T.F = F; T.P = std::max(P, 1); T.Q = std::max(Q, 1);
+    T.x_uf_any = P > 0; T.x_if_any = Q > 0;
+    T.Fp = (F + 3) & ~3; T.NQ = T.Fp / 4;
+    T.Pp = P > 0 ? (P + 3) & ~3 : 0; T.Qp = Q > 0 ? (Q + 3) & ~3 : 0;
+    T.ldu = T.Fp + T.Pp; T.ldi = T.Fp + 4 + T.Qp;
+    T.gp_vuf = (T.Q + 3) & ~3; T.gp_vif = T.gp_vuf + T.P * T.Fp;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, 5 * sizeof(float)));
+    cudaError_t e = launch_feat8_selftest(T, seed, 0.05f, 0.2f, d, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out5, d, 5 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorInvalidValue ? RFM_ERR_UNSUPPORTED : RFM_ERR_CUDA, "feat8 self-test: %s", cudaGetErrorString(e)); }
+    return RFM_OK;
+}
+
 extern "C" int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_t r0, int64_t count, int64_t* out)
 {
     if (!out || n < 1 || r0 < 0 || r0 + count > n) return fail(RFM_ERR_ARG, "bad feistel range");

@@ -50,6 +50,9 @@ cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, i
 cudaError_t launch_gp_apply(float* gp, float* acc, int n, cudaStream_t st);
 size_t sgd_pipe_smem_bytes(const Tables& T);
 int sgd_pipe_chains_per_warp(const Tables& T);
+// self-test of the P, Q <= 8 specialisation of the side-feature math (rfm_feat8.cuh) against the generic code: out5 =
+// max |difference| of a[], b[], the chain copy after one step, the row deltas; and the largest chain movement (non-zero)
+cudaError_t launch_feat8_selftest(const Tables& T, uint32_t seed, float eta, float reg_b, float* out5, cudaStream_t st);
 cudaError_t launch_weight_stats(const Tables& T, double* out12, int grid, cudaStream_t st);
 
 // scoring (rfm_score.cu)

@@ -6,6 +6,7 @@
 #pragma once
 #include "rfm_kernels.h"
 #include "rfm_pair.cuh"
+#include "rfm_feat8.cuh"
 #include "rfm_rng.cuh"
 
 namespace rfm {
@@ -169,11 +170,14 @@ __device__ __forceinline__ void gp_add4(float* q, const float4& w, const float4&
     atomicAdd(q + 0, d.x); atomicAdd(q + 1, d.y); atomicAdd(q + 2, d.z); atomicAdd(q + 3, d.w);
 }
 
-template <int G, int QPL, bool FEAT, bool EXACT, bool GPS, typename Sink>
+// F8 (production kernel, P and Q <= 8, G >= 8, private chain copy): the feature loops run on the compile-time unrolled
+// code of rfm_feat8.cuh with the feature values in `f8` (f8->xu filled by the caller; f8->dx is filled here)
+template <int G, int QPL, bool FEAT, bool EXACT, bool GPS, typename Sink, bool F8 = false>
 __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, const UserCtx<QPL>& uc, const ItemRow<QPL>& pos, const ItemRow<QPL>& neg,
                                              int min_j, float sw, int sampled, float min_pu, bool valid, long long r,
-                                             int sub, StepAcc& acc, const Sink& sink)
+                                             int sub, StepAcc& acc, const Sink& sink, Feat8* f8 = nullptr)
 {
+    static_assert(!F8 || (FEAT && !EXACT && GPS), "the feat8 path belongs to the production kernel");
     const Tables& T = p.T;
     const bool upd = valid && min_j >= 0;
     if (valid && min_j < 0) acc.bad = 1;
@@ -208,7 +212,10 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
         dvu[k].x = pos.v[k].x - neg.v[k].x; dvu[k].y = pos.v[k].y - neg.v[k].y;
         dvu[k].z = pos.v[k].z - neg.v[k].z; dvu[k].w = pos.v[k].w - neg.v[k].w;
     }
-    if (FEAT && T.x_if_any) {
+    if constexpr (F8) {
+        feat8_item_diff<G>(dx, *f8);
+        feat8_dvu<G, QPL>(T, gp, upd, sub, *f8, dvu);
+    } else if (FEAT && T.x_if_any) {
         for (int q = 0; q < T.Q; ++q) {
             const float dxq = __shfl_sync(0xffffffffu, get4(dx, q & 3), q >> 2, G);
 #pragma unroll
@@ -251,7 +258,9 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
             }
         }
     }
-    if (FEAT) {
+    if constexpr (F8) {
+        feat8_update_chains<G, QPL>(T, gp, upd, sub, *f8, dx, ec, eta * rb, vu_new, dij_new);
+    } else if (FEAT) {
         const float rb_or_ra = rb;
         if (T.x_if_any) {
             if (upd && 4 * sub < T.Qp) {                                   // w_if, every q (:283-286)

@@ -186,7 +186,8 @@ constexpr int kPipeBarBytes = 128;      // up to 16 mbarriers per warp, keeps th
 template <int QPL, bool FEAT, bool WARP>
 constexpr int pipe_min_blocks() { return QPL > 2 ? 1 : ((FEAT || WARP || QPL == 2) ? 2 : 3); }
 
-template <int G, int QPL, bool FEAT, bool WARP, bool TRED>
+// F8: side-feature math specialised for P, Q <= 8 (rfm_feat8.cuh); needs G >= 8 and a chain copy per lane group
+template <int G, int QPL, bool FEAT, bool WARP, bool TRED, bool F8 = false>
 __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP>()) sgd_pipe_kernel(const TrainParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -286,7 +287,13 @@ __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP
                 for (int q = 0; q < QPL; ++q) { uc.vu[q] = zero4(); pos.v[q] = zero4(); neg.v[q] = zero4(); }
                 uc.xu = zero4(); pos.x = zero4(); neg.x = zero4(); pos.w = 0.f; neg.w = 0.f;
             }
-            user_precompute<G, QPL, FEAT, true>(T, gp, valid, sub, uc);
+            Feat8 f8;
+            if constexpr (F8) {
+                feat8_user(T, base, valid, f8);
+                user_precompute8<G, QPL>(T, gp, valid, sub, f8, uc);
+            } else {
+                user_precompute<G, QPL, FEAT, true>(T, gp, valid, sub, uc);
+            }
             float ut_ui = 0.f, pu1;
             if (!WARP) {                       // BPR: only the difference is needed -> one group reduction instead of two
                 float part = 0.f;
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP
                     if (4 * sub < T.Pp) slot[T.NQ + sub] = zero4();
                     if (4 * sub < T.Qp) { slot[nu4 + T.NQ + 1 + sub] = zero4(); slot[nu4 + ni4 + T.NQ + 1 + sub] = zero4(); }
                 }
-                apply_update<G, QPL, FEAT, false, true>(p, gp, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
+                apply_update<G, QPL, FEAT, false, true, SmemSink, F8>(p, gp, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink, &f8);
                 fence_async_smem();
                 __syncwarp();
                 const bool upd = valid && min_j >= 0;
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP
                 if (step >= 1 && step - 1 + D < STEPS) { if (sub < 3) bulk_wait_read1(); __syncwarp(); issue(cur, step - 1 + D); }
             } else {
                 const RedSink sink{T.UT + (size_t)u * T.ldu, T.IT + (size_t)i * T.ldi, T.IT + (size_t)jj * T.ldi, T.Fp};
-                apply_update<G, QPL, FEAT, false, true>(p, gp, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink);
+                apply_update<G, QPL, FEAT, false, true, RedSink, F8>(p, gp, uc, pos, neg, min_j, sw, sampled, min_pu, valid, b * 32 + k, sub, acc, sink, &f8);
             }
         }
         if (TRED) { if (sub < 3) bulk_wait_read0(); __syncwarp(); }   // the next batch refills every stage
@@ -425,9 +432,23 @@ static bool use_tred()
     return cached == 1;
 }
 
-template <int G, int QPL, typename F>
-static void with_pipe_kernel(bool feat, bool warp, bool tred, F&& f)
+// the feat8 specialisation applies to: at most 8 + 8 active feature columns, lane groups of >= 8, one chain copy per group
+static bool feat8_ok(const Tables& T, int G, int gp_private)
 {
+    const char* e = getenv("RANKFM_B200_FEAT8");                                   // experiments / tests: RANKFM_B200_FEAT8=0
+    const bool off = e && !strcmp(e, "0");
+    return !off && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8 && G >= 8 && (gp_private || G == 32);
+}
+
+template <int G, int QPL, typename F>
+static void with_pipe_kernel(bool feat, bool warp, bool tred, bool f8, F&& f)
+{
+    if constexpr (G >= 8) {
+        if (feat && f8 && tred) {
+            if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true>);
+            return;
+        }
+    }
     if (feat) {
         if (warp) { if (tred) f(sgd_pipe_kernel<G, QPL, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, true, false>); }
         else      { if (tred) f(sgd_pipe_kernel<G, QPL, true, false, true>); else f(sgd_pipe_kernel<G, QPL, true, false, false>); }
@@ -441,7 +462,7 @@ template <int G, int QPL>
 static cudaError_t launch_pipe(const TrainParams& p, bool feat, int grid, size_t smem, cudaStream_t st)
 {
     cudaError_t e = cudaSuccess;
-    with_pipe_kernel<G, QPL>(feat, p.max_samples > 1, use_tred(), [&](auto kernel) { e = launch_kernel(kernel, p, grid, smem, st); });
+    with_pipe_kernel<G, QPL>(feat, p.max_samples > 1, use_tred(), feat8_ok(p.T, G, p.gp_private), [&](auto kernel) { e = launch_kernel(kernel, p, grid, smem, st); });
     return e;
 }
 
@@ -469,7 +490,7 @@ static int occ_gq(const TrainParams& p)
     const bool feat = p.T.x_uf_any || p.T.x_if_any;
     const size_t smem = pipe_smem_bytes(p.T, G, pipe_depth(p.T, G));
     int n = 0;
-    with_pipe_kernel<G, QPL>(feat, p.max_samples > 1, use_tred(), [&](auto kernel) {
+    with_pipe_kernel<G, QPL>(feat, p.max_samples > 1, use_tred(), feat8_ok(p.T, G, gp_private_of(p.T, G, pipe_depth(p.T, G))), [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kTrainThreads, smem);
     });
@@ -501,6 +522,115 @@ int sgd_epoch_blocks_per_sm(const TrainParams& p)
         case 8:  return occ_gq<8, 1>(p);
         case 16: return occ_gq<16, 1>(p);
         default: return qpl == 1 ? occ_gq<32, 1>(p) : (qpl == 2 ? occ_gq<32, 2>(p) : occ_gq<32, 4>(p));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// self-test of the feat8 specialisation: one warp runs the generic and the specialised feature code on identical
+// pseudo-random inputs (user row, two item rows, chain copy) and reports the largest differences
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float selftest_value(uint32_t seed, uint32_t k) { return ((mix32(seed ^ (k * 0x9E3779B9u)) >> 8) * (1.0f / 16777216.0f) - 0.5f); }
+
+template <int G, int QPL>
+__global__ void __launch_bounds__(32) feat8_selftest_kernel(const Tables T, int gp_floats, uint32_t seed, float eta, float reg_b, float* __restrict__ out /* [4] */)
+{
+    extern __shared__ __align__(16) float sm[];
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x, sub = lane % G, gw = lane / G;
+    // per group: [user row | item row i | item row j | chain copy A | chain copy B | delta rows A (3) | delta rows B (3)]
+    const int rows = T.ldu + 2 * T.ldi;
+    float* mine = sm + (size_t)gw * (3 * rows + 2 * gp_floats);
+    float *urow = mine, *irow = urow + T.ldu, *jrow = irow + T.ldi, *gpa = jrow + T.ldi, *gpb = gpa + gp_floats, *da = gpb + gp_floats, *db = da + rows;
+    for (int e = sub; e < rows; e += G) {
+        const int col_u = e, col_i = e - T.ldu, col_j = e - T.ldu - T.ldi;
+        float v = selftest_value(seed + gw, e);
+        // pads must be zero, and some feature values exactly zero (the skip-if-zero branches)
+        if (e < T.ldu) { if ((col_u >= T.F && col_u < T.Fp) || col_u >= T.Fp + T.P || (col_u >= T.Fp && ((col_u + gw) % 3 == 0))) v = 0.f; }
+        else {
+            const int c = e < T.ldu + T.ldi ? col_i : col_j;
+            if ((c >= T.F && c < T.Fp) || (c > T.Fp && c < T.Fp + 4) || c >= T.Fp + 4 + T.Q) v = 0.f;
+            if (c >= T.Fp + 4 && (c % 4 == 1)) v = e < T.ldu + T.ldi ? 0.25f : 0.25f;          // equal on both items: dx == 0 there
+        }
+        mine[e] = v;
+    }
+    for (int e = sub; e < gp_floats; e += G) {
+        float v = 0.3f * selftest_value(seed * 7u + gw, e);
+        const int o = e >= T.gp_vif ? (e - T.gp_vif) % T.Fp : (e >= T.gp_vuf ? (e - T.gp_vuf) % T.Fp : 0);
+        if (o >= T.F || (e < T.gp_vuf && e >= T.Q)) v = 0.f;
+        gpa[e] = v; gpb[e] = v;
+    }
+    __syncwarp();
+    UserCtx<QPL> ua, ub;
+    ItemRow<QPL> pos, neg;
+    smem_user<G, QPL, true>(T, urow, sub, ua);
+    smem_item<G, QPL, true>(T, irow, sub, pos);
+    smem_item<G, QPL, true>(T, jrow, sub, neg);
+    ub = ua;
+    Feat8 f8;
+    user_precompute<G, QPL, true, true>(T, gpa, true, sub, ua);
+    feat8_user(T, urow, true, f8);
+    user_precompute8<G, QPL>(T, gpb, true, sub, f8, ub);
+    float d_a = 0.f, d_b = 0.f;
+#pragma unroll
+    for (int k = 0; k < QPL; ++k)
+        d_a = fmaxf(d_a, fmaxf(fmaxf(fabsf(ua.a[k].x - ub.a[k].x), fabsf(ua.a[k].y - ub.a[k].y)), fmaxf(fabsf(ua.a[k].z - ub.a[k].z), fabsf(ua.a[k].w - ub.a[k].w))));
+    d_b = fmaxf(fmaxf(fabsf(ua.b.x - ub.b.x), fabsf(ua.b.y - ub.b.y)), fmaxf(fabsf(ua.b.z - ub.b.z), fabsf(ua.b.w - ub.b.w)));
+    // one gradient step with each code path on its own chain copy
+    TrainParams p{};
+    p.T = T; p.eta = eta; p.reg_a = 0.02f; p.reg_b = reg_b; p.gp_private = 1;
+    __shared__ float mult_tab[2];
+    if (lane == 0) { mult_tab[0] = 0.f; mult_tab[1] = 0.9f; }
+    __syncwarp();
+    p.mult = mult_tab;
+    StepAcc acc_a, acc_b;
+    const int nu4 = T.ldu >> 2, ni4 = T.ldi >> 2;
+    const SmemSink sa{reinterpret_cast<float4*>(da), reinterpret_cast<float4*>(da) + nu4, reinterpret_cast<float4*>(da) + nu4 + ni4, T.NQ};
+    const SmemSink sb{reinterpret_cast<float4*>(db), reinterpret_cast<float4*>(db) + nu4, reinterpret_cast<float4*>(db) + nu4 + ni4, T.NQ};
+    for (int e = sub; e < rows; e += G) { da[e] = 0.f; db[e] = 0.f; }
+    __syncwarp();
+    const float pu = utility<G, QPL, true>(ua, pos) - utility<G, QPL, true>(ua, neg);
+    apply_update<G, QPL, true, false, true>(p, gpa, ua, pos, neg, 1, 1.3f, 1, pu, true, 0, sub, acc_a, sa);
+    apply_update<G, QPL, true, false, true, SmemSink, true>(p, gpb, ua, pos, neg, 1, 1.3f, 1, pu, true, 0, sub, acc_b, sb, &f8);
+    __syncwarp();
+    float d_gp = 0.f, d_rows = 0.f, moved = 0.f;
+    for (int e = sub; e < gp_floats; e += G) { d_gp = fmaxf(d_gp, fabsf(gpa[e] - gpb[e])); moved = fmaxf(moved, fabsf(gpa[e] - 0.3f * selftest_value(seed * 7u + gw, e))); }
+    for (int e = sub; e < rows; e += G) d_rows = fmaxf(d_rows, fabsf(da[e] - db[e]));
+    for (int off = 16; off > 0; off >>= 1) {
+        d_a = fmaxf(d_a, __shfl_xor_sync(0xffffffffu, d_a, off)); d_b = fmaxf(d_b, __shfl_xor_sync(0xffffffffu, d_b, off));
+        d_gp = fmaxf(d_gp, __shfl_xor_sync(0xffffffffu, d_gp, off)); d_rows = fmaxf(d_rows, __shfl_xor_sync(0xffffffffu, d_rows, off));
+        moved = fmaxf(moved, __shfl_xor_sync(0xffffffffu, moved, off));
+    }
+    if (lane == 0) { out[0] = d_a; out[1] = d_b; out[2] = d_gp; out[3] = d_rows; out[4] = moved; }
+    (void)GPW;
+}
+
+template <int G, int QPL>
+static cudaError_t feat8_selftest_gq(const Tables& T, int gp_floats, uint32_t seed, float eta, float reg_b, float* out, cudaStream_t st)
+{
+    if constexpr (G >= 8) {
+        const size_t smem = (size_t)(32 / G) * (3 * (T.ldu + 2 * T.ldi) + 2 * gp_floats) * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(feat8_selftest_kernel<G, QPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        feat8_selftest_kernel<G, QPL><<<1, 32, smem, st>>>(T, gp_floats, seed, eta, reg_b, out);
+        return cudaGetLastError();
+    } else {
+        return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_feat8_selftest(const Tables& T, uint32_t seed, float eta, float reg_b, float* out5, cudaStream_t st)
+{
+    int qpl = 1;
+    const int G = train_group_size(T, &qpl);
+    const int gpf = (int)gp_floats_of(T);
+    if (T.P > kFeat8 || T.Q > kFeat8 || G < 8) return cudaErrorInvalidValue;
+    switch (G) {
+        case 8:  return feat8_selftest_gq<8, 1>(T, gpf, seed, eta, reg_b, out5, st);
+        case 16: return feat8_selftest_gq<16, 1>(T, gpf, seed, eta, reg_b, out5, st);
+        default:
+            if (qpl == 1) return feat8_selftest_gq<32, 1>(T, gpf, seed, eta, reg_b, out5, st);
+            if (qpl == 2) return feat8_selftest_gq<32, 2>(T, gpf, seed, eta, reg_b, out5, st);
+            return feat8_selftest_gq<32, 4>(T, gpf, seed, eta, reg_b, out5, st);
     }
 }
 

@@ -69,27 +69,39 @@ class RankFM():
         """first fit: build the id <-> index maps, then interactions, features, weights (``rankfm.py:100-137``)"""
         self._check_interactions(interactions)
         raw = get_data(interactions)
-        self.user_id = pd.Series(unique_ids(raw[:, 0]))         # sorted, like np.unique
-        self.item_id = pd.Series(unique_ids(raw[:, 1]))
+        pairs = None
+        if (len(raw) >= _rankfm._PREP_DEVICE_MIN and raw[:, 0].dtype.kind in "iu" and raw[:, 1].dtype.kind in "iu" and _rankfm.device_count() > 0):
+            # integer ids, large input: sorted unique ids + the index of every id by device radix sort (rfm_prep_index_ids)
+            # instead of np.unique + a hash lookup per column
+            users, u_idx = _rankfm.prep_index_ids(raw[:, 0])
+            items, i_idx = _rankfm.prep_index_ids(raw[:, 1])
+            self.user_id = pd.Series(users.astype(raw[:, 0].dtype, copy=False))
+            self.item_id = pd.Series(items.astype(raw[:, 1].dtype, copy=False))
+            pairs = np.ascontiguousarray(np.stack([u_idx, i_idx], axis=1), dtype=np.int32)
+        else:
+            self.user_id = pd.Series(unique_ids(raw[:, 0]))     # sorted, like np.unique
+            self.item_id = pd.Series(unique_ids(raw[:, 1]))
         self.index_to_user, self.index_to_item = self.user_id, self.item_id
         self.user_to_index = pd.Series(data=self.index_to_user.index, index=self.index_to_user.values)
         self.item_to_index = pd.Series(data=self.index_to_item.index, index=self.index_to_item.values)
         self.user_idx = np.arange(len(self.user_id), dtype=np.int32)
         self.item_idx = np.arange(len(self.item_id), dtype=np.int32)
-        self._init_interactions(interactions, sample_weight)
+        self._init_interactions(interactions, sample_weight, pairs=pairs)
         self._init_features(user_features, item_features)
         self._init_weights(user_features, item_features)
 
-    def _init_interactions(self, interactions, sample_weight):
-        """ids -> int32 index pairs, sample weights, per-user observed item sets (``rankfm.py:140-177``)"""
+    def _init_interactions(self, interactions, sample_weight, pairs=None):
+        """ids -> int32 index pairs, sample weights, per-user observed item sets (``rankfm.py:140-177``); ``pairs`` = the
+        index pairs when the caller already has them (first fit on the device path)"""
         self._check_interactions(interactions)
-        raw = get_data(interactions)
-        u = self._lookup(raw[:, 0], self.user_id.values)
-        i = self._lookup(raw[:, 1], self.item_id.values)
-        if (u < 0).any() or (i < 0).any():
-            # the reference fails in `.astype(np.int32)` on the NaN produced by the id map (rankfm.py:154-155)
-            raise ValueError("[interactions] contains user/item identifiers that were not present in the initial fit")
-        pairs = np.ascontiguousarray(np.stack([u, i], axis=1), dtype=np.int32)
+        if pairs is None:
+            raw = get_data(interactions)
+            u = self._lookup(raw[:, 0], self.user_id.values)
+            i = self._lookup(raw[:, 1], self.item_id.values)
+            if (u < 0).any() or (i < 0).any():
+                # the reference fails in `.astype(np.int32)` on the NaN produced by the id map (rankfm.py:154-155)
+                raise ValueError("[interactions] contains user/item identifiers that were not present in the initial fit")
+            pairs = np.ascontiguousarray(np.stack([u, i], axis=1), dtype=np.int32)
 
         if sample_weight is not None:
             assert isinstance(sample_weight, (np.ndarray, pd.Series)), "[sample_weight] must be np.ndarray or pd.series"
@@ -107,9 +119,9 @@ class RankFM():
             keys = np.concatenate([old_users * len(self.item_idx) + old_idx, pairs[:, 0].astype(np.int64) * len(self.item_idx) + pairs[:, 1]])
             keys = np.unique(keys)
             merged = np.stack([keys // len(self.item_idx), keys % len(self.item_idx)], axis=1)
-            self.user_items = UserItems.from_interactions(merged, n_users)
+            self.user_items = UserItems.from_interactions(merged, n_users, len(self.item_idx))
         else:
-            self.user_items = UserItems.from_interactions(pairs, n_users)
+            self.user_items = UserItems.from_interactions(pairs, n_users, len(self.item_idx))
         self.interactions = pairs
 
     def _feature_matrix(self, features, known_ids, n_rows, what):

@@ -275,8 +275,27 @@ def test_parallel_fit_statistical_parity(gpu_lib, loss, max_samples, F):
         assert abs(np.linalg.norm(wg[k]) / np.linalg.norm(wo[k]) - 1) < 0.05, k
 
 
-def test_parallel_fit_with_features_statistical_parity(gpu_lib):
-    U, I, F, P, Q = 1500, 800, 12, 5, 6
+@pytest.mark.parametrize("F,P,Q", [(20, 8, 8), (64, 8, 8), (64, 3, 0), (128, 0, 5), (200, 8, 8), (33, 7, 2)])
+def test_feat8_side_feature_code_matches_the_generic_code(gpu_lib, F, P, Q):
+    """the P, Q <= 8 specialisation of the production kernel's side-feature math (csrc/rfm_feat8.cuh: compile-time unrolled
+    column loops, multi-value reduce-scatter butterfly, two-FMA chain updates) against the generic run-time loops on the
+    same pseudo-random rows (device self-test, one warp): hoisted user vectors a[] / b[], the feature parameters after
+    one gradient step and the row deltas agree to float32 reassociation"""
+    import ctypes as C
+    out = (C.c_float * 5)()
+    for seed in (1, 2, 3):
+        _lib.check(_lib.lib().rfm_debug_feat8(F, P, Q, seed, out))
+        d_a, d_b, d_gp, d_rows, moved = list(out)
+        assert d_a < 2e-6 and d_b < 2e-5 and d_gp < 2e-6 and d_rows < 2e-6, (F, P, Q, seed, list(out))
+        assert moved > 1e-4                                   # the step really changed the parameters
+
+
+@pytest.mark.parametrize("F,P,Q,feat8", [(12, 5, 6, "1"), (64, 8, 8, "1"), (64, 8, 8, "0"), (40, 3, 8, "1")])
+def test_parallel_fit_with_features_statistical_parity(gpu_lib, F, P, Q, feat8, monkeypatch):
+    """(64, 8, 8) is BASELINE.json configs[2]'s row shape: G = 16 lane groups on the feat8 code path (feat8 = "0": the
+    generic loops on the same shape)"""
+    monkeypatch.setenv("RANKFM_B200_FEAT8", feat8)
+    U, I = 1500, 800
     X = zipf_interactions(U, I, 40000, seed=5)
     U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
     indptr, indices = csr_of(X, U)

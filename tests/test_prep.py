@@ -78,3 +78,26 @@ def test_synthetic_generator_properties(gpu_lib):
     Z, _, _ = zipf_interactions_device(U, I, N, seed=10, offset_users=1000, perm_seed=42, reindex=False)
     assert Y[:, 0].min() >= 1000 and Y[:, 0].max() < 1000 + U and Y[:, 1].max() < I
     assert np.argmax(np.bincount(Y[:, 1], minlength=I)) == np.argmax(np.bincount(Z[:, 1], minlength=I))
+
+
+@pytest.mark.gpu
+def test_rankfm_class_device_prep_matches_host_prep(gpu_lib, monkeypatch):
+    """`RankFM._init_all` on the device path (id maps + user_items by radix sort) builds exactly the objects of the host path"""
+    from rankfm_b200.rankfm import RankFM
+    rng = np.random.default_rng(11)
+    uid = rng.choice(10**9, 40_000, replace=False)
+    iid = rng.choice(10**7, 9_000, replace=False)
+    inter = np.stack([uid[rng.integers(0, len(uid), 300_000)], iid[rng.integers(0, len(iid), 300_000)]], 1)
+
+    def build(device):
+        monkeypatch.setattr(_rankfm, "_PREP_DEVICE_MIN", 1000 if device else 10**12)
+        m = RankFM(factors=4)
+        np.random.seed(0)
+        m._init_all(inter)
+        return m
+    a, b = build(True), build(False)
+    assert np.array_equal(a.user_id.values, b.user_id.values) and np.array_equal(a.item_id.values, b.item_id.values)
+    assert a.user_id.dtype == b.user_id.dtype
+    assert np.array_equal(a.interactions, b.interactions) and a.interactions.dtype == np.int32
+    assert np.array_equal(a.user_items.indptr, b.user_items.indptr) and np.array_equal(a.user_items.indices, b.user_items.indices)
+    assert np.array_equal(a.v_u, b.v_u)                         # same np.random draws either way
