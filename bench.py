@@ -512,7 +512,7 @@ def measure_e2e(job, c, X, ui, w, epochs, steps):
     data_bytes = X.nbytes + c["sw"].nbytes + (hi - lo + 1) * 8 + int(ui.indptr[hi] - ui.indptr[lo]) * 4 + \
         ((hi - lo) * c["P"] * 4 if c["P"] else 0) + (c["x_if"].nbytes if c["Q"] else 0)
     out = []
-    for resident, warm, n in ((False, min(5, steps), steps), (True, min(3, steps), max(3, steps // 2))):
+    for resident, warm, n in ((False, min(10, steps), steps), (True, min(3, steps), max(3, steps // 2))):
         rfm.set_resident_training(resident)
         for _ in range(warm):                             # the block cache / lazy module loading settle over the first calls
             step()

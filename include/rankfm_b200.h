@@ -197,6 +197,15 @@ int rfm_session_trace_read(rfm_session *s, int32_t *neg_and_sampled /* [N,2] */)
 int rfm_session_debug_gemm(rfm_session *s, const float *users, int64_t n_users, float *scores_out /* [n_users, I] */);
 /* `rfm_similar` on a resident session (same arguments and result) */
 int rfm_session_similar(rfm_session *s, int32_t which, int32_t index, int32_t n, int32_t *out);
+/* many queries in one call (the batched all-items variant): out int32 [n_queries, n], -1 = no such row */
+int rfm_session_similar_batch(rfm_session *s, int32_t which, const int32_t *indexes, int64_t n_queries, int32_t n, int32_t *out);
+/* hold-out ranking metrics (`rankfm/evaluation.py:9-143`) computed on the device from the top-k of `users` (float32 indexes,
+ * all known) against each user's test items: test_indptr int64 [n_users+1] / test_items int32 (item INDEXES, ascending per
+ * user, unknown items left out) in the order of `users`; n_test [n_users] = the user's number of distinct test items
+ * (unknown ones included: the recall denominator).  out5 = mean over the users of { hit, reciprocal rank, DCG, precision,
+ * recall }; hits_out (optional) uint8 [n_users, k] = 1 where the r-th recommendation of the user is a test item. */
+int rfm_session_evaluate(rfm_session *s, const float *users, int64_t n_users, int32_t k, int32_t filter_previous,
+                         const int64_t *test_indptr, const int32_t *test_items, const int32_t *n_test, double *out5, uint8_t *hits_out);
 /* (re)attach the user_items CSR a scoring session filters with (`filter_previous`, `_rankfm.pyx:450`): lets a caller keep
  * one session resident across `_predict` / `_recommend` calls instead of re-uploading the weights every call */
 int rfm_session_attach_csr(rfm_session *s, const int64_t *csr_indptr /* [U+1] */, const int32_t *csr_indices /* [nnz] */);

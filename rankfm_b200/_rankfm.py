@@ -515,6 +515,39 @@ def _similar(which, index, n, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if):
     return out
 
 
+def _scoring_session(weights, user_items=None):
+    """a scoring session for these weights: the resident one when that switch is on, else a throw-away one
+    -> (session, close_after_use)"""
+    if _RESIDENT:
+        return _resident_session(weights, user_items), False
+    keep = []
+    sess = Session(_problem(*weights, keep), keep)
+    if user_items is not None:
+        indptr, indices = user_items_to_csr(user_items, weights[4].shape[0])
+        sess.attach_csr(np.ascontiguousarray(indptr, dtype=np.int64), np.ascontiguousarray(indices, dtype=np.int32))
+    return sess, True
+
+
+def _evaluate(users, test_indptr, test_items, n_test, k, filter_previous, user_items, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if, want_hits=False):
+    """hold-out metrics of ``rankfm/evaluation.py:9-143`` from the device top-k (``rfm_session_evaluate``)"""
+    sess, close = _scoring_session((x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if), user_items if filter_previous else None)
+    try:
+        return sess.evaluate(users, test_indptr, test_items, n_test, k, filter_previous, want_hits)
+    finally:
+        if close:
+            sess.close()
+
+
+def _similar_batch(which, indexes, n, x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if):
+    """``_similar`` for many query rows at once -> int32 [len(indexes), n] (-1 = no such row)"""
+    sess, close = _scoring_session((x_uf, x_if, w_i, w_if, v_u, v_i, v_uf, v_if))
+    try:
+        return sess.similar_batch(which, indexes, n)
+    finally:
+        if close:
+            sess.close()
+
+
 def shard_by_user(interactions, sample_weight, n_users, rank, world):
     """user-range partition with ~equal interaction counts: rank r gets the rows of users in [b_r, b_{r+1})"""
     counts = np.bincount(interactions[:, 0], minlength=n_users)
@@ -630,6 +663,24 @@ class Session:
         out = np.empty(n, dtype=np.int32)
         check(_lib.lib().rfm_session_similar(self._h, int(which), int(index), int(n), ptr(out)))
         return out
+
+    def similar_batch(self, which, indexes, n):
+        indexes = np.ascontiguousarray(indexes, dtype=np.int32)
+        out = np.empty((len(indexes), n), dtype=np.int32)
+        check(_lib.lib().rfm_session_similar_batch(self._h, int(which), ptr(indexes), len(indexes), int(n), ptr(out)))
+        return out
+
+    def evaluate(self, users, test_indptr, test_items, n_test, k, filter_previous=False, want_hits=False):
+        """the five hold-out metrics (hit rate, reciprocal rank, DCG, precision, recall) from the device top-k"""
+        users = np.ascontiguousarray(users, dtype=np.float32)
+        test_indptr = np.ascontiguousarray(test_indptr, dtype=np.int64)
+        test_items = np.ascontiguousarray(test_items, dtype=np.int32)
+        n_test = np.ascontiguousarray(n_test, dtype=np.int32)
+        out = np.zeros(5, dtype=np.float64)
+        hits = np.empty((len(users), k), dtype=np.uint8) if want_hits else None
+        check(_lib.lib().rfm_session_evaluate(self._h, ptr(users), len(users), int(k), int(bool(filter_previous)), ptr(test_indptr), ptr(test_items),
+                                              ptr(n_test), ptr(out), ptr(hits)))
+        return out, hits
 
     def attach_csr(self, indptr, indices):
         check(_lib.lib().rfm_session_attach_csr(self._h, ptr(indptr), ptr(indices)))

@@ -224,6 +224,7 @@ struct rfm_session {
     // only the users [T.u0, T.u0+T.Un) of a multi-GPU job: indexing them with a global user id lands in
     // the allocation; T.IT / T.GP / d_item_touch sit in the communicator's peer window when `p2p`
     float* ut_alloc = nullptr; int64_t* indptr_alloc = nullptr; int32_t* indices_alloc = nullptr; uint32_t* bitmap_alloc = nullptr;
+    uint32_t *bloom_alloc = nullptr, *d_bloom = nullptr;   // membership pre-filter when there is no bitmap (one word per CSR entry)
     // multi-GPU
     rfmh::Comm* comm = nullptr;
     bool p2p = false;
@@ -335,7 +336,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     dev_free(s->ut_alloc);
     if (!s->p2p) { dev_free(s->T.IT); dev_free(s->T.GP); dev_free(s->d_item_touch); }
     dev_free(s->d_inter); dev_free(s->d_sw); dev_free(s->indptr_alloc); dev_free(s->indices_alloc);
-    dev_free(s->bitmap_alloc); dev_free(s->d_perm); dev_free(s->d_mult); dev_free(s->d_mt); dev_free(s->d_acc);
+    dev_free(s->bitmap_alloc); dev_free(s->bloom_alloc); dev_free(s->d_perm); dev_free(s->d_mult); dev_free(s->d_mt); dev_free(s->d_acc);
     dev_free(s->d_it_snap); dev_free(s->d_gp_snap); dev_free(s->d_red); dev_free(s->d_flush); dev_free(s->d_gp_acc); dev_free(s->d_xuf); dev_free(s->d_xif);
     dev_free(s->d_snap_ut); dev_free(s->d_snap_it); dev_free(s->d_snap_gp); dev_free(s->d_trace);
     dev_free(s->d_gemm_B); dev_free(s->d_gemm_bias); dev_free(s->d_gemm_order);
@@ -471,6 +472,14 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
                 s->d_bitmap = s->bitmap_alloc - (ptrdiff_t)T.u0 * words;
                 CUB(cudaMemsetAsync(s->bitmap_alloc, 0, (size_t)T.Un * words * 4, s->st));
                 CUB(launch_build_bitmap(s->indptr_alloc, s->d_indices, T.Un, s->bitmap_alloc, words, s->st));
+                s->launches += 1;
+            } else if (s->nnz > 0 && !(getenv("RANKFM_B200_BLOOM") && !strcmp(getenv("RANKFM_B200_BLOOM"), "0"))) {
+                // catalogue too large for a bitmap: a filter word per CSR entry lets the sampler dismiss ~97 % of the candidates
+                // with one load instead of a search of the user's item list (exact: set bits are verified by the search)
+                TRY(dev_alloc(&s->bloom_alloc, (size_t)s->nnz));
+                s->d_bloom = s->bloom_alloc - nz0;
+                CUB(cudaMemsetAsync(s->bloom_alloc, 0, (size_t)s->nnz * 4, s->st));
+                CUB(launch_build_bloom(s->indptr_alloc, s->d_indices, T.Un, s->d_bloom, s->st));
                 s->launches += 1;
             }
         }
@@ -779,6 +788,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
     tp.interactions = s->d_inter; tp.sample_weight = s->d_sw; tp.indptr = s->d_indptr; tp.indices = s->d_indices;
     tp.mult = s->d_mult;
     tp.bitmap = s->d_bitmap; tp.bitmap_words = s->bitmap_words;
+    tp.bloom = s->d_bloom;
     tp.N = s->N;
     tp.reg_a = (float)(2.0 * p.alpha);                      // d_reg_a / d_reg_b, _rankfm.pyx:171-172
     tp.reg_b = (float)(2.0 * p.beta);
@@ -1205,6 +1215,50 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     return RFM_OK;
 }
 
+// evaluation.py:9-143 on the device: recommend top-k for the users, then test every recommendation against the user's
+// hold-out items; only the five sums (and optionally the hit matrix) travel back to the host
+extern "C" int rfm_session_evaluate(rfm_session* s, const float* users, int64_t n_users, int32_t k, int32_t filter_previous,
+                                    const int64_t* test_indptr, const int32_t* test_items, const int32_t* n_test, double* out5, uint8_t* hits_out)
+{
+    if (!s || !users || !test_indptr || !n_test || !out5 || n_users < 1) return fail(RFM_ERR_ARG, "bad argument");
+    int rc = recommend_checks(s, n_users, k, filter_previous);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    std::vector<int32_t> hu;
+    users_to_int(users, n_users, hu);
+    for (auto u : hu) if (u < s->T.u0 || u >= s->T.u0 + s->T.Un) return fail(RFM_ERR_ARG, "user index %d out of range [%d, %d)", u, s->T.u0, s->T.u0 + s->T.Un);
+    std::vector<int64_t> order;
+    const int64_t n_tc = recommend_plan(s, hu, k, filter_previous, order);
+    std::vector<int32_t> hp((size_t)n_users);
+    for (int64_t r = 0; r < n_users; ++r) hp[(size_t)r] = hu[(size_t)order[(size_t)r]];
+    const int64_t nnz = test_indptr[n_users];
+    if (nnz < 0 || (nnz > 0 && !test_items)) return fail(RFM_ERR_ARG, "bad test CSR");
+    DevBuf<int32_t> d_users, d_items, d_ntest; DevBuf<float> d_rec; DevBuf<int64_t> d_order, d_ptr; DevBuf<double> d_out; DevBuf<uint8_t> d_hits;
+    if ((rc = d_users.alloc((size_t)n_users))) return rc;
+    if ((rc = d_rec.alloc((size_t)n_users * k))) return rc;
+    if ((rc = d_order.alloc((size_t)n_users))) return rc;
+    if ((rc = d_ptr.alloc((size_t)n_users + 1))) return rc;
+    if ((rc = d_items.alloc((size_t)nnz))) return rc;
+    if ((rc = d_ntest.alloc((size_t)n_users))) return rc;
+    if ((rc = d_out.alloc(5))) return rc;
+    if (hits_out && (rc = d_hits.alloc((size_t)n_users * k))) return rc;
+    CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(d_order, order.data(), (size_t)n_users * 8, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(d_ptr, test_indptr, ((size_t)n_users + 1) * 8, cudaMemcpyHostToDevice, s->st));
+    if (nnz) CU(cudaMemcpyAsync(d_items, test_items, (size_t)nnz * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(d_ntest, n_test, (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemsetAsync(d_out, 0, 5 * sizeof(double), s->st));
+    if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, k, filter_previous, d_rec, nullptr))) return rc;
+    cudaError_t e = launch_eval_topk(d_rec, d_order, (int)n_users, k, d_ptr, d_items, d_ntest, d_out, hits_out ? (uint8_t*)d_hits : nullptr, s->st);
+    if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "eval_topk launch failed: %s", cudaGetErrorString(e));
+    s->launches += 1;
+    CU(cudaMemcpyAsync(out5, d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    if (hits_out) CU(cudaMemcpyAsync(hits_out, d_hits, (size_t)n_users * k, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    for (int m = 0; m < 5; ++m) out5[m] /= (double)n_users;
+    return RFM_OK;
+}
+
 extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, int64_t n_users, int32_t n_items, int32_t filter_previous,
                                           int32_t iters, float* ms_out, float* gemm_ms_out)
 {
@@ -1437,6 +1491,46 @@ extern "C" int rfm_session_similar(rfm_session* s, int32_t which, int32_t index,
     CU(cudaMemcpyAsync(rec.data(), d_rec, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     for (int k = 0; k < n; ++k) out[k] = std::isnan(rec[(size_t)k]) ? -1 : (int32_t)rec[(size_t)k];
+    return RFM_OK;
+}
+
+// similar_items / similar_users for MANY query rows in one call (SURVEY 8(f)4 "batched all-items variant"): the queries
+// are scored in chunks (one latent_scores pass per query into a [chunk, rows] score block) and every chunk gets ONE
+// top-n launch; out int32 [n_queries, n], -1 pads rows with fewer than n other rows
+extern "C" int rfm_session_similar_batch(rfm_session* s, int32_t which, const int32_t* indexes, int64_t n_queries, int32_t n, int32_t* out)
+{
+    if (!s || !indexes || !out || n_queries < 1) return fail(RFM_ERR_ARG, "bad argument");
+    if (which != 0 && which != 1) return fail(RFM_ERR_ARG, "which must be 0 (items) or 1 (users)");
+    const int rows = which == 0 ? s->T.I : s->T.U;
+    if (which == 1 && s->T.Un != s->T.U) return fail(RFM_ERR_UNSUPPORTED, "similar_users needs a session that holds all users");
+    if (n < 1 || n > 16384) return fail(RFM_ERR_ARG, "n out of range");
+    for (int64_t q = 0; q < n_queries; ++q) if (indexes[q] < 0 || indexes[q] >= rows) return fail(RFM_ERR_ARG, "index out of range");
+    CU(cudaSetDevice(s->device));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_queries, ((int64_t)1 << 28) / std::max(1, rows)));      // <= 1 GiB of scores
+    DevBuf<float> qc, S, d_rec; DevBuf<int32_t> d_zero, d_idx;
+    int rc;
+    const size_t qc_floats = (size_t)s->T.Fp + (size_t)std::max(s->T.Pp, s->T.Qp) + 4;
+    if ((rc = qc.alloc(qc_floats))) return rc;
+    if ((rc = S.alloc((size_t)chunk * rows))) return rc;
+    if ((rc = d_rec.alloc((size_t)chunk * n))) return rc;
+    if ((rc = d_zero.alloc((size_t)chunk))) return rc;
+    if ((rc = d_idx.alloc((size_t)n_queries))) return rc;
+    CU(cudaMemsetAsync(d_zero, 0, (size_t)chunk * 4, s->st));
+    CU(cudaMemcpyAsync(d_idx, indexes, (size_t)n_queries * 4, cudaMemcpyHostToDevice, s->st));
+    std::vector<float> rec((size_t)chunk * n);
+    for (int64_t off = 0; off < n_queries; off += chunk) {
+        const int nb = (int)std::min<int64_t>(chunk, n_queries - off);
+        for (int b = 0; b < nb; ++b) {
+            cudaError_t e = launch_latent_scores(s->T, which, indexes[off + b], qc, S + (size_t)b * rows, s->st);
+            if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "similar launch failed: %s", cudaGetErrorString(e));
+        }
+        cudaError_t e = launch_topn_select(S, rows, d_zero, nb, nullptr, nullptr, 0, n, d_rec, d_idx + off, s->st);
+        if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "similar top-n launch failed: %s", cudaGetErrorString(e));
+        s->launches += 2 * nb + 1;
+        CU(cudaMemcpyAsync(rec.data(), d_rec, (size_t)nb * n * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        for (int64_t e2 = 0; e2 < (int64_t)nb * n; ++e2) out[(size_t)off * n + e2] = std::isnan(rec[(size_t)e2]) ? -1 : (int32_t)rec[(size_t)e2];
+    }
     return RFM_OK;
 }
 

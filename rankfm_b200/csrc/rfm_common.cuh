@@ -68,6 +68,18 @@ __device__ __forceinline__ unsigned group_ballot(bool pred, int gw)
     else return (b >> (gw * G)) & ((1u << G) - 1u);
 }
 
+// bit index of `item` in the 32*deg-bit membership filter of a user with `deg` observed items (deg < 2^27)
+__host__ __device__ __forceinline__ uint32_t bloom_slot(int item, int deg)
+{
+    uint32_t x = (uint32_t)item * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+#ifdef __CUDA_ARCH__
+    return __umulhi(x, (uint32_t)deg << 5);
+#else
+    return (uint32_t)(((uint64_t)x * ((uint32_t)deg << 5)) >> 32);
+#endif
+}
+
 // Membership of `cand` in the sorted list items[0..deg): (G+1)-ary search, one probe per lane and round.
 // Replaces the reference's linear scan (`lsearch`, rankfm/_rankfm.pyx:20-27; `bsearch` :30-45 is dead code there).
 // Warp-uniform control flow: every lane of the warp calls with its group's arguments; `active` masks groups out.

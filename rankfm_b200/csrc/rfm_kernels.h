@@ -25,6 +25,11 @@ struct TrainParams {
     const int32_t* indices;
     const uint32_t* bitmap;  // optional [U, bitmap_words]: bit i of row u set <=> item i in user_items[u]; nullptr -> search the CSR
     int32_t bitmap_words;
+    // optional pre-filter of the CSR membership search when there is no bitmap: one 32-bit word per CSR entry, aligned
+    // with `indices` (user u owns the words [indptr[u], indptr[u+1]) = 32*deg bits); bit bloom_slot(item, deg) is set for
+    // every observed item.  A clear bit proves "not observed" (the common case, ~97 % of the candidates) with ONE load;
+    // a set bit is verified by the exact search, so the sampler's results are unchanged.
+    const uint32_t* bloom;
     const int32_t* perm;     // this epoch's order, or nullptr -> Feistel
     const float* mult;       // [max_samples+1]  WARP multiplier by number of draws
     Feistel feistel;
@@ -46,6 +51,7 @@ struct TrainParams {
 
 int train_group_size(const Tables& T, int* qpl_out);
 cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st);
+cudaError_t launch_build_bloom(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bloom, cudaStream_t st);
 cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bitmap, int words, cudaStream_t st);
 cudaError_t launch_gp_apply(float* gp, float* acc, int n, cudaStream_t st);
 size_t sgd_pipe_smem_bytes(const Tables& T);
@@ -79,6 +85,8 @@ constexpr int kShortWidth = 512;               // shortlist entries per row (n' 
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
                              int* flag, cudaStream_t st);
+cudaError_t launch_eval_topk(const float* rec, const int64_t* order, int n_users, int k, const int64_t* test_indptr, const int32_t* test_items,
+                             const int32_t* n_test, double* out5, uint8_t* hits_out, cudaStream_t st);
 cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);
 int sgd_epoch_blocks_per_sm(const TrainParams& p);
 

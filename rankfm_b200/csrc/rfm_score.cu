@@ -343,4 +343,61 @@ cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* q
     RFM_DISPATCH_GQ(latent_scores_gq, T, which, qc, S, st);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// hold-out ranking metrics straight from the device top-k (rankfm/evaluation.py:9-143): one warp per evaluated user
+// tests each recommended item against the user's sorted test items and adds the user's terms of the five metrics
+//   out5 += [ any hit, 1/(rank of first hit + 1), sum_hits 1/log2(rank+2), hits/k, hits/|test items| ]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eval_topk_kernel(const float* __restrict__ rec, const int64_t* __restrict__ order, int n_users, int k,
+                                                        const int64_t* __restrict__ test_indptr, const int32_t* __restrict__ test_items,
+                                                        const int32_t* __restrict__ n_test, double* __restrict__ out5, uint8_t* __restrict__ hits_out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (long long b = warp_global; b < n_users; b += n_warps) {
+        const long long orig = order ? order[b] : b;                  // row b of `rec` belongs to the orig-th requested user
+        const long long s0 = test_indptr[orig], s1 = test_indptr[orig + 1];
+        int cnt = 0, first = 0x7fffffff;
+        double dcg = 0.0;
+        for (int r = lane; r < k; r += 32) {
+            const float item_f = rec[(size_t)b * k + r];
+            bool hit = false;
+            if (!isnan(item_f)) {
+                const int item = (int)item_f;
+                long long lo = s0, hi = s1 - 1;
+                while (lo <= hi) {
+                    const long long md = (lo + hi) >> 1;
+                    const int e = __ldg(test_items + md);
+                    if (e == item) { hit = true; break; }
+                    if (e < item) lo = md + 1; else hi = md - 1;
+                }
+            }
+            if (hit) { ++cnt; first = min(first, r); dcg += 1.0 / log2((double)r + 2.0); }
+            if (hits_out) hits_out[(size_t)orig * k + r] = hit ? 1 : 0;
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+            dcg += __shfl_xor_sync(0xffffffffu, dcg, off);
+        }
+        if (lane == 0 && cnt > 0) {
+            const int nt = n_test[orig];
+            acc[0] += 1.0; acc[1] += 1.0 / (double)(first + 1); acc[2] += dcg; acc[3] += (double)cnt / (double)k;
+            acc[4] += nt > 0 ? (double)cnt / (double)nt : 0.0;
+        }
+    }
+    if (lane == 0)
+        for (int m = 0; m < 5; ++m) if (acc[m] != 0.0) atomicAdd(out5 + m, acc[m]);
+}
+
+cudaError_t launch_eval_topk(const float* rec, const int64_t* order, int n_users, int k, const int64_t* test_indptr, const int32_t* test_items,
+                             const int32_t* n_test, double* out5, uint8_t* hits_out, cudaStream_t st)
+{
+    const int grid = max(1, min(148 * 8, (n_users + 7) / 8));
+    eval_topk_kernel<<<grid, 256, 0, st>>>(rec, order, n_users, k, test_indptr, test_items, n_test, out5, hits_out);
+    return cudaGetLastError();
+}
+
 }  // namespace rfm

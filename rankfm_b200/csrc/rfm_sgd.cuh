@@ -107,6 +107,10 @@ __device__ __forceinline__ void sample_negatives_spec(const TrainParams& p, cons
             cj[w] = (int)__umulhi(word, (uint32_t)T.I);
             load_item<G, QPL, FEAT>(T, cj[w], live, sub, cand[w]);
             mword[w] = (live && p.bitmap) ? __ldg(p.bitmap + (size_t)u * p.bitmap_words + (cj[w] >> 5)) : 0u;
+            if (!p.bitmap && p.bloom) {                        // filter word of the candidate (users held in registers need none)
+                const uint32_t h = bloom_slot(cj[w], deg);
+                mword[w] = (live && !listed && deg > 0) ? ((__ldg(p.bloom + seg + (h >> 5)) >> (h & 31)) & 1u) : 1u;
+            }
         }
 #pragma unroll
         for (int w = 0; w < KMAX; ++w) {
@@ -117,7 +121,8 @@ __device__ __forceinline__ void sample_negatives_spec(const TrainParams& p, cons
             else {
                 const int c = cj[w];
                 const bool hit = group_ballot<G>(own[0] == c || own[1] == c || own[2] == c || own[3] == c, gw) != 0u;
-                const bool searched = group_member<G>(c, p.indices + seg, deg, live && !listed, sub, gw);
+                // without a filter every candidate is searched; with one only those whose bit is set (mword = 1)
+                const bool searched = group_member<G>(c, p.indices + seg, deg, live && !listed && (!p.bloom || mword[w] != 0u), sub, gw);
                 member = listed ? hit : searched;
             }
             const float pu = ut_ui - utility<G, QPL, FEAT>(uc, cand[w]);

@@ -152,8 +152,13 @@ __device__ __forceinline__ Tuple front_end(const TrainParams& p, long long r)
             const uint32_t word = c == 0u ? blk.x : (c == 1u ? blk.y : (c == 2u ? blk.z : blk.w));
             ++t.attempt;
             const int cj = (int)__umulhi(word, (uint32_t)p.T.I);
-            const bool member = p.bitmap ? ((__ldg(p.bitmap + (size_t)ui.x * p.bitmap_words + (cj >> 5)) >> (cj & 31)) & 1u) != 0u
-                                         : lane_member(cj, p.indices + seg, deg);
+            bool member;
+            if (p.bitmap) member = ((__ldg(p.bitmap + (size_t)ui.x * p.bitmap_words + (cj >> 5)) >> (cj & 31)) & 1u) != 0u;
+            else {
+                bool maybe = deg > 0;
+                if (p.bloom && maybe) { const uint32_t h = bloom_slot(cj, deg); maybe = ((__ldg(p.bloom + seg + (h >> 5)) >> (h & 31)) & 1u) != 0u; }
+                member = maybe && lane_member(cj, p.indices + seg, deg);      // the filter has no false negatives: a clear bit is final
+            }
             t.j = cj;
             if (!member || ++rejects >= p.max_rejects) break;
         }
@@ -659,6 +664,26 @@ __global__ void build_bitmap_kernel(const int64_t* __restrict__ indptr, const in
         const int it = indices[e];
         atomicOr(bitmap + (size_t)lo * words + (it >> 5), 1u << (it & 31));
     }
+}
+
+// membership filter for large catalogues (see TrainParams::bloom): word e of `bloom` belongs to the owner of CSR slot e
+__global__ void build_bloom_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int U, uint32_t* __restrict__ bloom)
+{
+    const long long first = indptr[0], nnz = indptr[U];
+    for (long long e = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = U;                                   // owner of CSR slot e: last u with indptr[u] <= e
+        while (hi - lo > 1) { const int md = (lo + hi) >> 1; if (indptr[md] <= e) lo = md; else hi = md; }
+        const long long seg = indptr[lo];
+        const int deg = (int)(indptr[lo + 1] - seg);
+        const uint32_t h = bloom_slot(indices[e], deg);
+        atomicOr(bloom + seg + (h >> 5), 1u << (h & 31));
+    }
+}
+
+cudaError_t launch_build_bloom(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bloom, cudaStream_t st)
+{
+    build_bloom_kernel<<<148 * 8, 256, 0, st>>>(indptr, indices, U, bloom);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, int U, uint32_t* bitmap, int words, cudaStream_t st)

@@ -11,7 +11,7 @@ import numpy as np
 import pandas as pd
 
 from rankfm_b200 import _rankfm
-from rankfm_b200._rankfm import _fit, _predict, _recommend, _similar, UserItems
+from rankfm_b200._rankfm import _fit, _predict, _recommend, _similar, _similar_batch, UserItems
 from rankfm_b200.utils import get_data, lookup_ids, unique_ids
 
 _LOSSES = ('bpr', 'warp')
@@ -245,6 +245,18 @@ class RankFM():
         assert item_id in self.item_id.values, "you must select an [item_id] present in the training data"
         assert self.is_fit, "you must fit the model prior to generating similarities"
         return self._most_similar(0, self.item_to_index.loc[item_id], n_items, self.index_to_item)
+
+    def similar_items_batch(self, item_ids=None, n_items=10):
+        """``similar_items`` for many items in ONE call (default: every item) -> DataFrame indexed by item id, ``n_items``
+        columns of item ids, most similar first (the batched all-items variant of ``rankfm.py:405-428``)"""
+        assert self.is_fit, "you must fit the model prior to generating similarities"
+        ids = self.item_id.values if item_ids is None else np.asarray(list(item_ids))
+        index = self._lookup(ids, self.item_id.values)
+        assert (index >= 0).all(), "you must select [item_ids] present in the training data"
+        n = min(int(n_items), max(len(self.item_id) - 1, 1))
+        top = _similar_batch(0, index.astype(np.int32), n, *self._weights())
+        out = np.where(top >= 0, self.index_to_item.values[np.maximum(top, 0)], None) if (top < 0).any() else self.index_to_item.values[top]
+        return pd.DataFrame(out, index=ids)
 
     def similar_users(self, user_id, n_users=10):
         """most similar users by latent inner product, the query excluded (``rankfm.py:431-454``)"""

@@ -220,6 +220,13 @@ def test_evaluation_matches_the_reference_evaluation_module(backend):
             assert both["hit_rate"] == pytest.approx(float(g["hit_rate" + tag]), rel=1e-12)
             assert both["discounted_cumulative_gain"] == pytest.approx(float(g["dcg" + tag]), rel=1e-12)
             assert both["recall"] == pytest.approx(float(g["recall" + tag]), rel=1e-12)
+    if backend == "cuda":
+        # the fused device evaluation (rfm_session_evaluate) and the host reduction of the recommend() table agree
+        import rankfm_b200.evaluation as ev
+        assert ev._device_path(model)
+        host = ev._hit_rate_host(model, test, 10, True), ev._recall_host(model, test, 10, True), ev._discounted_cumulative_gain_host(model, test, 10, True)
+        dev = ev._device_metrics(model, test, 10, True)
+        assert (dev["hit_rate"], dev["recall"], dev["discounted_cumulative_gain"]) == pytest.approx(host, rel=1e-12)
     div = diversity(model, test, k=10, filter_previous=True)
     ours = dict(zip(div['item_id'].values.tolist(), div['cnt_users'].values.tolist()))
     ref = dict(zip(g['diversity_item_id'].tolist(), g['diversity_cnt_users'].tolist()))

@@ -57,10 +57,14 @@ def test_serial_philox_fit_matches_oracle(gpu_lib, case):
     assert [s['draws'] for s in stats] == out['draws'].tolist()
 
 
+@pytest.mark.parametrize("bloom", ["1", "0"])
 @pytest.mark.parametrize("case", ["warp_f20", "warp_feat", "warp_if_only", "bpr_f16"])
-def test_serial_philox_without_bitmap_matches_oracle(gpu_lib, case, monkeypatch):
-    """membership through the CSR (register-resident short lists, (G+1)-ary search for long ones) instead of the bitmap"""
+def test_serial_philox_without_bitmap_matches_oracle(gpu_lib, case, bloom, monkeypatch):
+    """membership through the CSR (register-resident short lists, (G+1)-ary search for long ones) instead of the bitmap;
+    bloom = "1": the one-word-per-entry filter dismisses most candidates before the search (large catalogues' default) --
+    draw for draw the same negatives either way, the filter has no false negatives and its positives are verified"""
     monkeypatch.setenv("RANKFM_B200_BITMAP_MB", "0")
+    monkeypatch.setenv("RANKFM_B200_BLOOM", bloom)
     g = load_golden(case)
     deg = np.diff(g['indptr'])
     assert deg.max() > 32 and deg.min() <= 16            # both the listed and the searched path are exercised
@@ -487,6 +491,28 @@ def test_similar_items_and_users(gpu_lib):
             # exact top-8: only candidates closer than float32 rounding may swap (the reference sorts float32 sums too, in
             # BLAS order: rankfm.py:421-424)
             assert_topn_exact_up_to_rounding(got, sims, 8, tol)
+
+
+def test_similar_batch_matches_single_queries(gpu_lib):
+    """the batched all-items variant returns, row by row, what the one-query call returns"""
+    g = load_golden('warp_feat')
+    w = dict(zip(WEIGHTS, _weights(g, 'ref')))
+    for which, rows in ((0, len(w['v_i'])), (1, len(w['v_u']))):
+        queries = np.arange(rows, dtype=np.int32)                 # every row of the table
+        got = _rankfm._similar_batch(which, queries, 6, g['x_uf'], g['x_if'], *w.values())
+        assert got.shape == (rows, 6) and (got >= 0).all()
+        for idx in (0, 3, rows // 2, rows - 1):
+            assert np.array_equal(got[idx], _rankfm._similar(which, idx, 6, g['x_uf'], g['x_if'], *w.values()))
+            assert idx not in got[idx]
+    # through the class: a DataFrame of item ids indexed by item id
+    from rankfm_b200 import RankFM
+    ga = load_golden('api_warp_feat')
+    model = RankFM(factors=5, loss='warp', max_samples=6, learning_schedule='invscaling')
+    model.fit(ga['interactions'], user_features=ga['user_features'], item_features=ga['item_features'], epochs=1)
+    table = model.similar_items_batch(n_items=4)
+    assert table.shape == (len(model.item_id), 4) and np.array_equal(table.index.values, model.item_id.values)
+    some = model.item_id.values[5]
+    assert np.array_equal(table.loc[some].values, model.similar_items(some, 4))
 
 
 # ---------------------------------------------------------------------------------------------------------------
