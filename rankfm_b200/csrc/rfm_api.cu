@@ -182,7 +182,9 @@ extern "C" int rfm_debug_feat8(int32_t F, int32_t P, int32_t Q, uint32_t seed, f
     T.ldu = T.Fp + T.Pp; T.ldi = T.Fp + 4 + T.Qp;
     T.gp_vuf = (T.Q + 3) & ~3; T.gp_vif = T.gp_vuf + T.P * T.Fp;
     float* d = nullptr;
-    CU(cudaMalloc(&d, 5 * sizeof(float)));
+    const float init[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.9f};      // [6..7]: the WARP multiplier table the step reads
+    CU(cudaMalloc(&d, sizeof init));
+    CU(cudaMemcpy(d, init, sizeof init, cudaMemcpyHostToDevice));
     cudaError_t e = launch_feat8_selftest(T, seed, 0.05f, 0.2f, d, nullptr);
     if (e == cudaSuccess) e = cudaMemcpy(out5, d, 5 * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(d);

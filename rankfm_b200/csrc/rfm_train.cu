@@ -192,8 +192,10 @@ template <int QPL, bool FEAT, bool WARP>
 constexpr int pipe_min_blocks() { return QPL > 2 ? 1 : ((FEAT || WARP || QPL == 2) ? 2 : 3); }
 
 // F8: side-feature math specialised for P, Q <= 8 (rfm_feat8.cuh); needs G >= 8 and a chain copy per lane group
-template <int G, int QPL, bool FEAT, bool WARP, bool TRED, bool F8 = false>
-__global__ void __launch_bounds__(kTrainThreads, pipe_min_blocks<QPL, FEAT, WARP>()) sgd_pipe_kernel(const TrainParams p)
+// MINB > 0 overrides the resident-blocks target (experiments: the WARP kernel at 3 blocks/SM trades ~60 spilled words for
+// 50 % more warps to hide the L2 latency of the sampler's candidate rows)
+template <int G, int QPL, bool FEAT, bool WARP, bool TRED, bool F8 = false, int MINB = 0>
+__global__ void __launch_bounds__(kTrainThreads, MINB > 0 ? MINB : pipe_min_blocks<QPL, FEAT, WARP>()) sgd_pipe_kernel(const TrainParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Tables& T = p.T;
@@ -445,6 +447,12 @@ static bool feat8_ok(const Tables& T, int G, int gp_private)
     return !off && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8 && G >= 8 && (gp_private || G == 32);
 }
 
+static bool warp_occ3()
+{
+    const char* e = getenv("RANKFM_B200_WARP_OCC");                                // experiments: 3 = WARP kernel at 3 resident blocks per SM
+    return e && !strcmp(e, "3");
+}
+
 template <int G, int QPL, typename F>
 static void with_pipe_kernel(bool feat, bool warp, bool tred, bool f8, F&& f)
 {
@@ -453,6 +461,9 @@ static void with_pipe_kernel(bool feat, bool warp, bool tred, bool f8, F&& f)
             if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true>);
             return;
         }
+    }
+    if constexpr (QPL == 1) {
+        if (!feat && warp && tred && warp_occ3()) { f(sgd_pipe_kernel<G, QPL, false, true, true, false, 3>); return; }
     }
     if (feat) {
         if (warp) { if (tred) f(sgd_pipe_kernel<G, QPL, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, true, false>); }
@@ -537,7 +548,7 @@ int sgd_epoch_blocks_per_sm(const TrainParams& p)
 __device__ __forceinline__ float selftest_value(uint32_t seed, uint32_t k) { return ((mix32(seed ^ (k * 0x9E3779B9u)) >> 8) * (1.0f / 16777216.0f) - 0.5f); }
 
 template <int G, int QPL>
-__global__ void __launch_bounds__(32) feat8_selftest_kernel(const Tables T, int gp_floats, uint32_t seed, float eta, float reg_b, float* __restrict__ out /* [4] */)
+__global__ void __launch_bounds__(32) feat8_selftest_kernel(const Tables T, int gp_floats, uint32_t seed, float eta, float reg_b, float* __restrict__ out /* [8]: 0-4 results, 6-7 multiplier table */)
 {
     extern __shared__ __align__(16) float sm[];
     constexpr int GPW = 32 / G;
@@ -583,10 +594,7 @@ __global__ void __launch_bounds__(32) feat8_selftest_kernel(const Tables T, int 
     // one gradient step with each code path on its own chain copy
     TrainParams p{};
     p.T = T; p.eta = eta; p.reg_a = 0.02f; p.reg_b = reg_b; p.gp_private = 1;
-    __shared__ float mult_tab[2];
-    if (lane == 0) { mult_tab[0] = 0.f; mult_tab[1] = 0.9f; }
-    __syncwarp();
-    p.mult = mult_tab;
+    p.mult = out + 6;                        // WARP multiplier table {-, 0.9} in global memory (apply_update reads it with __ldg)
     StepAcc acc_a, acc_b;
     const int nu4 = T.ldu >> 2, ni4 = T.ldi >> 2;
     const SmemSink sa{reinterpret_cast<float4*>(da), reinterpret_cast<float4*>(da) + nu4, reinterpret_cast<float4*>(da) + nu4 + ni4, T.NQ};
