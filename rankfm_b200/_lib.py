@@ -62,9 +62,13 @@ def lib():
     if _lib is not None:
         return _lib
     from . import build as _build
-    if _build.needs_build():
-        _build.build()
-    L = C.CDLL(LIB_PATH)
+    variant = os.environ.get("RANKFM_B200_LIB")          # experiments: a variant build of the library (rankfm_b200/build.py --out=...)
+    if variant:
+        L = C.CDLL(variant)
+    else:
+        if _build.needs_build():
+            _build.build()
+        L = C.CDLL(LIB_PATH)
     L.rfm_version.restype = C.c_char_p
     L.rfm_last_error.restype = C.c_char_p
     L.rfm_device_count.restype = C.c_int

@@ -30,27 +30,32 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """`out` / `extra_flags`: build a VARIANT of the library next to the product one (A/B experiments, e.g.
+    extra_flags=["-DRFM_SAMPLER_ROUNDS"]); it is loaded with RANKFM_B200_LIB=<path>"""
+    if out is None and not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.splitext(os.path.basename(out))[0])
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs, procs = [], []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, pr in procs:
-        out, _ = pr.communicate()
+        log, _ = pr.communicate()
         if verbose or pr.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(log)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"], check=True)
-    return LIB
+    target = LIB if out is None else out
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target] + objs + ["-ldl"], check=True)
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    variant = [a for a in sys.argv[1:] if a.startswith("--out=")]
+    flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=variant[0][6:] if variant else None, extra_flags=flags))

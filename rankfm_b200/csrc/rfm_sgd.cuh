@@ -141,6 +141,113 @@ __device__ __forceinline__ void sample_negatives_spec(const TrainParams& p, cons
     }
 }
 
+// Pipelined variant of sample_negatives_spec (same results, attempt for attempt):
+//   * the Philox words of a positive are computed ONCE, one block per lane of the group (lane `sub` holds block b0 + sub:
+//     4 G consecutive attempts), and fetched with a shuffle -- the look-ahead loop above recomputes the same block on
+//     every lane in every round;
+//   * attempts are resolved in batches of K, and the NEXT batch's candidate rows / membership words are already in flight
+//     while the current batch is consumed (two batches = the same 4 candidate rows in registers as one round of the
+//     look-ahead loop), so a positive that needs several draws pays one L2/HBM round trip plus its arithmetic instead of
+//     one round trip per round.  Attempts issued past the terminating draw are discarded, like unread words of a block.
+template <int G, int QPL, bool FEAT>
+__device__ __forceinline__ void sample_negatives_pipe(const TrainParams& p, const UserCtx<QPL>& uc, float ut_ui, int row, int u, long long seg, int deg,
+                                                      int s, bool& done, uint32_t& attempt, int spec, int sub, int gw,
+                                                      ItemRow<QPL>& neg, float& min_pu, int& min_j, int& sampled)
+{
+    constexpr int K = (QPL == 1) ? 2 : 1;
+    const Tables& T = p.T;
+    int rejects = 0;
+    constexpr int OWN = 4;
+    int own[OWN];
+    const bool listed = !p.bitmap && deg <= OWN * G;
+#pragma unroll
+    for (int k = 0; k < OWN; ++k) own[k] = (!done && listed && sub + k * G < deg) ? __ldg(p.indices + seg + sub + k * G) : -1;
+
+    uint32_t b0 = attempt >> 2;                                  // first block of the word window held by the group
+    Philox4 blk = philox4x32_10((uint32_t)row, p.epoch_key, b0 + (uint32_t)sub, 0u, p.k0, p.k1);
+    uint32_t a_issue = attempt;                                  // next attempt to put in flight (>= attempt, the next to consume)
+
+    struct Batch { ItemRow<QPL> cand[K]; int cj[K]; uint32_t mw[K]; };
+    auto issue = [&](Batch& B) {
+        const bool refill = !done && ((a_issue + (uint32_t)(K - 1)) >> 2) - b0 >= (uint32_t)G;      // the batch leaves the window (rare)
+        if (__any_sync(0xffffffffu, refill)) {
+            const uint32_t nb0 = refill ? (a_issue >> 2) : b0;
+            const Philox4 nb = philox4x32_10((uint32_t)row, p.epoch_key, nb0 + (uint32_t)sub, 0u, p.k0, p.k1);
+            if (refill) { blk = nb; b0 = nb0; }
+        }
+#pragma unroll
+        for (int w = 0; w < K; ++w) {
+            const uint32_t a = a_issue + (uint32_t)w;
+            const uint32_t c = a & 3u;
+            const uint32_t mine = c == 0u ? blk.x : (c == 1u ? blk.y : (c == 2u ? blk.z : blk.w));
+            const uint32_t word = __shfl_sync(0xffffffffu, mine, (int)(((a >> 2) - b0) & (uint32_t)(G - 1)), G);
+            const bool live = !done;
+            B.cj[w] = (int)__umulhi(word, (uint32_t)T.I);
+            load_item<G, QPL, FEAT>(T, B.cj[w], live, sub, B.cand[w]);
+            B.mw[w] = (live && p.bitmap) ? __ldg(p.bitmap + (size_t)u * p.bitmap_words + (B.cj[w] >> 5)) : 0u;
+            if (!p.bitmap && p.bloom) {
+                const uint32_t h = bloom_slot(B.cj[w], deg);
+                B.mw[w] = (live && !listed && deg > 0) ? ((__ldg(p.bloom + seg + (h >> 5)) >> (h & 31)) & 1u) : 1u;
+            }
+        }
+        a_issue += (uint32_t)K;
+    };
+    auto consume = [&](const Batch& B) {
+#pragma unroll
+        for (int w = 0; w < K; ++w) {
+            const bool live = !done;
+            bool member;
+            if (p.bitmap) member = ((B.mw[w] >> (B.cj[w] & 31)) & 1u) != 0u;
+            else {
+                const int c = B.cj[w];
+                const bool hit = group_ballot<G>(own[0] == c || own[1] == c || own[2] == c || own[3] == c, gw) != 0u;
+                const bool searched = group_member<G>(c, p.indices + seg, deg, live && !listed && (!p.bloom || B.mw[w] != 0u), sub, gw);
+                member = listed ? hit : searched;
+            }
+            const float pu = ut_ui - utility<G, QPL, FEAT>(uc, B.cand[w]);
+            if (live) {
+                ++attempt;
+                if (member && ++rejects < p.max_rejects) {
+                    // observed item: rejected, the next attempt belongs to the same draw
+                } else {
+                    rejects = 0;
+                    sampled = ++s;
+                    if (pu < min_pu) { min_pu = pu; min_j = B.cj[w]; neg = B.cand[w]; }
+                    if (pu < 1.0f || s >= p.max_samples) done = true;          // MARGIN (:149,263) / loop bound (:247)
+                }
+            }
+        }
+    };
+    Batch A, B;
+    const bool ahead = spec > 1;                                 // early epochs stop at the first draws: no look-ahead then
+    issue(A);
+    for (;;) {
+        if (ahead) issue(B);
+        consume(A);
+        if (!__any_sync(0xffffffffu, !done)) break;
+        if (ahead) {
+            issue(A);
+            consume(B);
+            if (!__any_sync(0xffffffffu, !done)) break;
+        } else {
+            issue(A);
+        }
+    }
+}
+
+// sampler of the Philox schedules: the pipelined loop; -DRFM_SAMPLER_ROUNDS builds the round-based look-ahead loop instead (A/B)
+template <int G, int QPL, bool FEAT>
+__device__ __forceinline__ void sample_negatives_philox(const TrainParams& p, const UserCtx<QPL>& uc, float ut_ui, int row, int u, long long seg, int deg,
+                                                        int s, bool& done, uint32_t& attempt, int spec, int sub, int gw,
+                                                        ItemRow<QPL>& neg, float& min_pu, int& min_j, int& sampled)
+{
+#ifdef RFM_SAMPLER_ROUNDS
+    sample_negatives_spec<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, s, done, attempt, spec, sub, gw, neg, min_pu, min_j, sampled);
+#else
+    sample_negatives_pipe<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, s, done, attempt, spec, sub, gw, neg, min_pu, min_j, sampled);
+#endif
+}
+
 // Where the row deltas of one step go.
 //   RedSink   straight to HBM/L2 as per-lane vector reductions (REDG.E.ADD.F32x4)           -- serial schedule
 //   SmemSink  into the shared-memory slot the rows were staged in; the caller then ships each delta row with ONE TMA

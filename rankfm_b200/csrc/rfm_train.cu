@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(32) sgd_serial_kernel(const TrainParams p)
         for (int k = 0; k < QPL; ++k) neg.v[k] = zero4();
         neg.x = zero4(); neg.w = 0.f;
         if (MT) sample_negatives<G, QPL, FEAT, true>(p, uc, ut_ui, row, u, seg, deg, 1, done, attempt, &mt_smem, sub, gw, neg, min_pu, min_j, sampled);
-        else    sample_negatives_spec<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, 0, done, attempt, p.spec, sub, gw, neg, min_pu, min_j, sampled);
+        else    sample_negatives_philox<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, 0, done, attempt, p.spec, sub, gw, neg, min_pu, min_j, sampled);
         // ---- gradient step: _rankfm.pyx:267-326 ----
         const RedSink sink{T.UT + (size_t)u * T.ldu, T.IT + (size_t)i * T.ldi, T.IT + (size_t)(min_j >= 0 ? min_j : 0) * T.ldi, T.Fp};
         apply_update<G, QPL, FEAT, true, false>(p, T.GP, uc, pos, neg, min_j, sw, sampled, min_pu, valid, r, sub, acc, sink);
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kTrainThreads, MINB > 0 ? MINB : pipe_min_bloc
             if (WARP && __any_sync(0xffffffffu, !done)) {
                 long long seg = 0; int deg = 0;
                 if (!done && !p.bitmap) { seg = __ldg(p.indptr + u); deg = (int)(__ldg(p.indptr + u + 1) - seg); }
-                sample_negatives_spec<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, 1, done, attempt, spec, sub, gw, neg, min_pu, min_j, sampled);
+                sample_negatives_philox<G, QPL, FEAT>(p, uc, ut_ui, row, u, seg, deg, 1, done, attempt, spec, sub, gw, neg, min_pu, min_j, sampled);
             }
             const int jj = min_j >= 0 ? min_j : 0;
             if (TRED) {
@@ -449,8 +449,8 @@ static bool feat8_ok(const Tables& T, int G, int gp_private)
 
 static bool warp_occ3()
 {
-    const char* e = getenv("RANKFM_B200_WARP_OCC");                                // experiments: 3 = WARP kernel at 3 resident blocks per SM
-    return e && !strcmp(e, "3");
+    const char* e = getenv("RANKFM_B200_WARP_OCC");                                // experiments: 2 = the 128-register build at 2 blocks per SM
+    return !(e && !strcmp(e, "2"));
 }
 
 template <int G, int QPL, typename F>
