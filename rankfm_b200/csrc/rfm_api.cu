@@ -1000,7 +1000,7 @@ static int ensure_gemm_items(rfm_session* s)
         dev_free(s->d_gemm_B); dev_free(s->d_gemm_bias); dev_free(s->d_gemm_order);
         s->d_gemm_B = nullptr; s->d_gemm_bias = nullptr; s->d_gemm_order = nullptr;
         CU(dev_malloc(&s->d_gemm_B, (size_t)I_pad * Kp * 2));
-        int rc = dev_alloc(&s->d_gemm_bias, (size_t)I_pad);
+        int rc = dev_alloc(&s->d_gemm_bias, (size_t)I_pad + 4);          // [I_pad]: largest operand-row norm (shortlist guard)
         if (rc) return rc;
         if ((rc = dev_alloc(&s->d_gemm_order, (size_t)I_pad))) return rc;
         s->gemm_I_pad = I_pad;
@@ -1116,7 +1116,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e));
         if (gemm_ms) CU(cudaEventRecord(ev.back(), s->st));
         e = launch_shortlist(T, d_users + off, nb, cand, cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
-                             n_items, d_rec + (size_t)off * n_items, d_flag + off, s->st);
+                             n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
         s->launches += 5;
     }

@@ -447,9 +447,11 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
                                                                   const int* __restrict__ cand_cnt, int slots, int cap, const float* __restrict__ bias,
                                                                   const int32_t* __restrict__ order, const int* __restrict__ n_target,
                                                                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                                                  int filter_previous, int n_items, float* __restrict__ rec, int* __restrict__ flag)
+                                                                  int filter_previous, int n_items, float* __restrict__ rec, int* __restrict__ flag,
+                                                                  const float* __restrict__ tau, int I_pad, int guard)
 {
     extern __shared__ __align__(16) unsigned char short_smem[];
+    __shared__ float s_norm2;
     uint2* ent = reinterpret_cast<uint2*>(short_smem);               // [slots * cap] (ordered key of the bf16 score, position)
     __shared__ int32_t kept[kShortWidth];                            // item ids of the shortlist, in position order
     __shared__ unsigned long long sel[kShortWidth];                  // (ordered key of the exact score << 32) | shortlist slot
@@ -540,6 +542,13 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
     UserCtx<QPL> uc;
     load_user<G, QPL, FEAT>(T, u, true, sub, uc);
     user_precompute<G, QPL, FEAT>(T, T.GP, true, sub, uc);
+    {   // |A_u|^2 of the GEMM's user operand [ a | v_u ] (second half only with item features)
+        float n2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < QPL; ++k) { n2 = dot4(uc.a[k], uc.a[k], n2); if (FEAT && T.x_if_any) n2 = dot4(uc.vu[k], uc.vu[k], n2); }
+        n2 = group_sum<G>(n2);
+        if (tid == 0) s_norm2 = n2;
+    }
     long long seg = 0; int deg = 0;
     if (filter_previous) { seg = __ldg(indptr + u); deg = (int)(__ldg(indptr + u + 1) - seg); }
     constexpr int STRIDE = (kShortThreads / 32) * GPW;
@@ -580,23 +589,45 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
         const unsigned long long e = k < n_sort ? sel[k] : 0ull;
         out[k] = (e >> 32) == 0ull ? __int_as_float(0x7fc00000) : (float)kept[(uint32_t)(e & 0xffffffffull)];
     }
+    // 5. is the bf16 shortlist PROVABLY a superset of the exact top n_items?  Every item outside it has a bf16 score <= c
+    //    (the cut of step 2, or the row threshold tau when every candidate was kept), hence an exact score <= c + delta with
+    //    delta = 2^-8 |A_u| max_i |B_i| (both operands rounded to bf16: 2^-9 relative each, Cauchy-Schwarz over the sum).
+    //    If the n_items-th exact score found clears that, nothing outside can displace it; otherwise the row is redone on
+    //    the exact fp32 path (flag), like an overflowing candidate slot.
+    if (guard && tid == 0 && n_items <= n_sort) {
+        const uint32_t kn = (uint32_t)(sel[n_items - 1] >> 32);
+        if (kn != 0u) {
+            auto key_to_float = [](uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); };
+            const float e_n = key_to_float(kn);
+            const float c = want < total ? key_to_float(cut) : tau[b];
+            const float delta = 1.05f * 0.00390625f * sqrtf(s_norm2) * __ldg(bias + I_pad) + 1e-6f * fabsf(c);
+            if (!(e_n >= c + delta)) flag[b] = 1;
+        }
+    }
+}
+
+static bool shortlist_guard()
+{
+    const char* e = getenv("RANKFM_B200_TC_GUARD");            // experiments: 0 = trust the 2n+16 shortlist without the bf16 error bound
+    return !(e && !strcmp(e, "0"));
 }
 
 template <int G, int QPL>
 static cudaError_t shortlist_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                                 const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                                int* flag, cudaStream_t st)
+                                int* flag, const float* tau, int I_pad, cudaStream_t st)
 {
     const size_t smem = (size_t)slots * cap * sizeof(uint2);
+    const int guard = shortlist_guard() ? 1 : 0;
     cudaError_t e;
     if (T.x_uf_any || T.x_if_any) {
         e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, true><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag);
+        shortlist_kernel<G, QPL, true><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
     } else {
         e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, false><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag);
+        shortlist_kernel<G, QPL, false><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
     }
     return cudaGetLastError();
 }
@@ -604,12 +635,12 @@ static cudaError_t shortlist_gq(const Tables& T, const int32_t* users, int n_use
 // rec [n_users, n_items]: final rows (float item indexes, NaN-padded like topn_select_kernel); flag [n_users]
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                             int* flag, cudaStream_t st)
+                             int* flag, const float* tau, int I_pad, cudaStream_t st)
 {
     int qpl = 1;
     const int G = train_group_size(T, &qpl);
     if (max(T.Pp, T.Qp) > 4 * G || qpl > 4 || slots > 64 || (size_t)slots * cap * sizeof(uint2) > 160 * 1024) return cudaErrorInvalidValue;
-#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, st)
+#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, st)
     switch (G) {
         case 4:  RFM_SHORT(4, 1);
         case 8:  RFM_SHORT(8, 1);
@@ -668,7 +699,30 @@ int gemm_m_tile(const Tables& T) { return 128 * gemm_msub(T); }
 int gemm_slots_per_split(const Tables& T) { return gemm_msub(T) == 2 ? 1 : 2; }
 bool gemm_supported(const Tables& T) { return gemm_kp(T) <= 256; }
 
-// bias[I_pad] (sorted, descending), order[I_pad] (position -> item), B[I_pad, Kp]; once per weight state
+// largest Euclidean norm of a bf16 item operand row: |score_bf16 - score_fp32| <= 2^-8 |A_u| |B_i| bounds what the shortlist
+// can miss (see shortlist_kernel, step 5)
+__global__ void item_norm_max_kernel(const __nv_bfloat16* __restrict__ B, int I_pad, int Kp, float* __restrict__ out)
+{
+    float best = 0.f;
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < I_pad; pos += gridDim.x * blockDim.x) {
+        const uint4* row = reinterpret_cast<const uint4*>(B + (size_t)pos * Kp);
+        float n2 = 0.f;
+        for (int c = 0; c < Kp / 8; ++c) {
+            const uint4 v = row[c];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+                n2 = fmaf(lo, lo, fmaf(hi, hi, n2));
+            }
+        }
+        best = fmaxf(best, n2);
+    }
+    for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(sqrtf(best)));      // non-negative floats order like their bits
+}
+
+// bias[I_pad] (sorted, descending; bias[I_pad] = largest operand-row norm), order[I_pad] (position -> item), B[I_pad, Kp]; once per weight state
 cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, int32_t* order, cudaStream_t st)
 {
     float* raw = nullptr; int32_t* iota = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
@@ -683,6 +737,8 @@ cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, 
     if (e == cudaSuccess) e = cudaMemsetAsync(order + T.I, 0xff, (size_t)(I_pad - T.I) * 4, st);
     if (e == cudaSuccess) {
         pack_gemm_items_kernel<<<148 * 8, 256, 0, st>>>(T, Kp, I_pad, order, reinterpret_cast<__nv_bfloat16*>(B), bias);
+        cudaMemsetAsync(bias + I_pad, 0, 4 * sizeof(float), st);
+        item_norm_max_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(B), I_pad, Kp, bias + I_pad);
         e = cudaGetLastError();
     }
     cudaStreamSynchronize(st);

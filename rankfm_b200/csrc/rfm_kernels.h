@@ -84,7 +84,7 @@ constexpr int kTauBlock = 8;                   // items per pass-1 block bound
 constexpr int kShortWidth = 512;               // shortlist entries per row (n' <= 256 plus ties at the cut)
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                             int* flag, cudaStream_t st);
+                             int* flag, const float* tau, int I_pad, cudaStream_t st);
 cudaError_t launch_eval_topk(const float* rec, const int64_t* order, int n_users, int k, const int64_t* test_indptr, const int32_t* test_items,
                              const int32_t* n_test, double* out5, uint8_t* hits_out, cudaStream_t st);
 cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);

@@ -6,12 +6,13 @@ index-ordered, then re-indexed to the observed uniques like ``rankfm.py:115-116`
 import numpy as np
 
 CONFIGS = {
-    # name: U, I, N, factors, loss, max_samples, epochs, P, Q
+    # name: U, I, N, factors, loss, max_samples, epochs, P, Q   (BASELINE.json names epochs only for configs[0..1]; the large
+    # configurations run 4 epochs per bench step)
     "cfg1": dict(U=10_000, I=5_000, N=100_000, F=16, loss="bpr", max_samples=1, epochs=5, P=0, Q=0,
                  label="synthetic 10k users x 5k items, 100k interactions, factors=16, bpr, 5 epochs"),
     "cfg2": dict(U=6_040, I=3_706, N=1_000_000, F=20, loss="warp", max_samples=20, epochs=20, P=0, Q=0,
                  label="MovieLens-1M shape synthetic (6040x3706, 1M interactions), factors=20, warp, max_samples=20, 20 epochs"),
-    "cfg3": dict(U=1_000_000, I=200_000, N=50_000_000, F=64, loss="warp", max_samples=10, epochs=2, P=8, Q=8,
+    "cfg3": dict(U=1_000_000, I=200_000, N=50_000_000, F=64, loss="warp", max_samples=10, epochs=4, P=8, Q=8,
                  label="1M users x 200k items, 50M Zipf interactions, factors=64, warp, 8+8 side features"),
     "cfg3m": dict(U=250_000, I=50_000, N=8_000_000, F=64, loss="warp", max_samples=10, epochs=3, P=8, Q=8,
                   label="1/6 slice of cfg3: 250k users x 50k items, 8M interactions, factors=64, warp max_samples=10, 8+8 dense side features"),
@@ -19,7 +20,7 @@ CONFIGS = {
                   label="cfg3 shape without side features: 1M users x 200k items, 16M interactions, factors=64, warp max_samples=10 (tables 308 MB > L2)"),
     "cfg4m": dict(U=1_250_000, I=1_000_000, N=16_000_000, F=128, loss="bpr", max_samples=1, epochs=3, P=0, Q=0,
                   label="DRAM-resident slice of cfg4: 1.25M users x 1M items, 16M interactions, factors=128, bpr (tables 1.2 GB >> L2)"),
-    "cfg4s": dict(U=1_250_000, I=1_000_000, N=62_500_000, F=128, loss="bpr", max_samples=1, epochs=2, P=0, Q=0,
+    "cfg4s": dict(U=1_250_000, I=1_000_000, N=62_500_000, F=128, loss="bpr", max_samples=1, epochs=4, P=0, Q=0,
                   label="per-GPU shard of 10M users x 1M items, 500M interactions, factors=128, bpr (1/8 of cfg4)"),
 }
 
