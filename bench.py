@@ -576,12 +576,55 @@ def run_ours(args):
                 line["recommend"] = recommend_record(full=False, device=job.local_rank)["recommend"]
             except Exception as exc:
                 line["recommend"] = {"error": repr(exc)}
+        if job.world == 1 and args.workload == "cfg2":
+            try:
+                line["e2e_class_fit"] = class_fit_record(c)
+            except Exception as exc:
+                line["e2e_class_fit"] = {"error": repr(exc)}
     if job.dist is not None:
         job.barrier()
         job.rfm.release_comms()
         job.dist.destroy_process_group()
     if line is not None:
         emit(line)
+
+
+def class_fit_record(c):
+    """the call a user of the reference makes: `RankFM(...).fit(interactions, epochs=...)` on RAW (user_id, item_id) pairs --
+    id maps, index pairs, `user_items` (`RankFM._init_all`, rankfm.py:100-137: device radix sorts here, pandas in the
+    reference), weight initialisation (NumPy, the reference's draw order), then the plug-in `_fit`; and a following
+    `fit_partial` on the same interactions (warm start)"""
+    from rankfm_b200 import RankFM
+    X, epochs = c["X"], c["epochs"]
+    rng = np.random.default_rng(3)
+    uid = np.sort(rng.choice(10**9, c["U_global"], replace=False))         # scattered 64-bit ids: the maps do real work
+    iid = np.sort(rng.choice(10**8, c["I"], replace=False))
+    inter = np.ascontiguousarray(np.stack([uid[X[:, 0]], iid[X[:, 1]]], axis=1))
+    loss = "bpr" if c["max_samples"] == 1 else "warp"
+
+    def one():
+        model = RankFM(factors=c["F"], loss=loss, max_samples=max(c["max_samples"], 1), alpha=HYPER["alpha"], beta=HYPER["beta"],
+                       learning_rate=HYPER["learning_rate"], learning_schedule=HYPER["learning_schedule"], learning_exponent=HYPER["learning_exponent"])
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        model._init_all(inter)
+        t_init = time.perf_counter() - t0
+        model._reset_state()
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        model.fit(inter, epochs=epochs)
+        t_fit = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        model.fit_partial(inter, epochs=epochs)
+        t_partial = time.perf_counter() - t0
+        return t_init, t_fit, t_partial
+    one()                                                                  # warm-up (lazy loading, block cache)
+    runs = [one() for _ in range(3)]
+    t_init, t_fit, t_partial = [float(np.median([r[k] for r in runs])) for k in range(3)]
+    N = len(X)
+    return {"call": "rankfm_b200.RankFM(...).fit(raw int64 id pairs [N,2], epochs=%d), then fit_partial on the same pairs" % epochs,
+            "value": N * epochs / t_fit, "unit": "interactions/s", "ms_fit": 1e3 * t_fit, "ms_init_all_alone": 1e3 * t_init, "ms_fit_partial": 1e3 * t_partial,
+            "statistic": "median of 3", "h2d_bytes_per_step": int(inter.nbytes + X.nbytes + c["sw"].nbytes), "d2h_bytes_per_step": int(X.nbytes)}
 
 
 def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, device=0, iters=3, exact_users=4096):
