@@ -386,6 +386,19 @@ int train_group_size(const Tables& T, int* qpl_out)
     return G;
 }
 
+// Lane-group geometry of the SGD kernels.  Default: the narrowest group that covers a row with one quad per lane.
+// RANKFM_B200_GROUP_SHIFT=1 (experiment): half that width, two quads per lane -- twice the positives per warp instruction,
+// so the per-round scalar work of the WARP sampler (Philox, address arithmetic, bookkeeping) is shared by twice as many.
+static int sgd_group_size(const Tables& T, int* qpl_out)
+{
+    int qpl = 1;
+    int G = train_group_size(T, &qpl);
+    const char* e = getenv("RANKFM_B200_GROUP_SHIFT");
+    if (e && atoi(e) == 1 && G >= 8 && qpl == 1 && max(T.Pp, T.Qp) <= 2 * G && !(T.x_uf_any || T.x_if_any)) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
+    if (qpl_out) *qpl_out = qpl;
+    return G;
+}
+
 // depth of the staging pipeline: ~8 KB of rows in flight per warp, 2..8 stages
 static int pipe_depth(const Tables& T, int G)
 {
@@ -412,13 +425,13 @@ static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
 int sgd_pipe_chains_per_warp(const Tables& T)
 {
     int qpl = 1;
-    const int G = train_group_size(T, &qpl);
+    const int G = sgd_group_size(T, &qpl);
     return gp_private_of(T, G, pipe_depth(T, G)) ? 32 / G : 1;
 }
 size_t sgd_pipe_smem_bytes(const Tables& T)
 {
     int qpl = 1;
-    const int G = train_group_size(T, &qpl);
+    const int G = sgd_group_size(T, &qpl);
     return pipe_smem_bytes(T, G, pipe_depth(T, G));
 }
 
@@ -516,12 +529,12 @@ static int occ_gq(const TrainParams& p)
 cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st)
 {
     int qpl = 1;
-    const int G = train_group_size(p.T, &qpl);
+    const int G = sgd_group_size(p.T, &qpl);
     if (max(p.T.Pp, p.T.Qp) > 4 * G || qpl > 4) return cudaErrorInvalidValue;   // caller reports RFM_ERR_UNSUPPORTED
     switch (G) {
-        case 4:  return launch_gq<4, 1>(p, grid, st);
-        case 8:  return launch_gq<8, 1>(p, grid, st);
-        case 16: return launch_gq<16, 1>(p, grid, st);
+        case 4:  return qpl == 2 ? launch_gq<4, 2>(p, grid, st) : launch_gq<4, 1>(p, grid, st);
+        case 8:  return qpl == 2 ? launch_gq<8, 2>(p, grid, st) : launch_gq<8, 1>(p, grid, st);
+        case 16: return qpl == 2 ? launch_gq<16, 2>(p, grid, st) : launch_gq<16, 1>(p, grid, st);
         default:
             if (qpl == 1) return launch_gq<32, 1>(p, grid, st);
             if (qpl == 2) return launch_gq<32, 2>(p, grid, st);
@@ -532,11 +545,11 @@ cudaError_t launch_sgd_epoch(const TrainParams& p, int grid, cudaStream_t st)
 int sgd_epoch_blocks_per_sm(const TrainParams& p)
 {
     int qpl = 1;
-    const int G = train_group_size(p.T, &qpl);
+    const int G = sgd_group_size(p.T, &qpl);
     switch (G) {
-        case 4:  return occ_gq<4, 1>(p);
-        case 8:  return occ_gq<8, 1>(p);
-        case 16: return occ_gq<16, 1>(p);
+        case 4:  return qpl == 2 ? occ_gq<4, 2>(p) : occ_gq<4, 1>(p);
+        case 8:  return qpl == 2 ? occ_gq<8, 2>(p) : occ_gq<8, 1>(p);
+        case 16: return qpl == 2 ? occ_gq<16, 2>(p) : occ_gq<16, 1>(p);
         default: return qpl == 1 ? occ_gq<32, 1>(p) : (qpl == 2 ? occ_gq<32, 2>(p) : occ_gq<32, 4>(p));
     }
 }
