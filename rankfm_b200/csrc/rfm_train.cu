@@ -386,15 +386,18 @@ int train_group_size(const Tables& T, int* qpl_out)
     return G;
 }
 
-// Lane-group geometry of the SGD kernels.  Default: the narrowest group that covers a row with one quad per lane.
-// RANKFM_B200_GROUP_SHIFT=1 (experiment): half that width, two quads per lane -- twice the positives per warp instruction,
-// so the per-round scalar work of the WARP sampler (Philox, address arithmetic, bookkeeping) is shared by twice as many.
+// Lane-group geometry of the SGD kernels.  Without side features: HALF the narrowest group that covers a row, two quads
+// per lane -- twice the positives per warp instruction, so the scalar work per step and per sampler round (Philox, address
+// arithmetic, bookkeeping, TMA issue) is shared by twice as many positives: cfg2 0.97 -> 0.86 ms, cfg3n 27.9 -> 21.5 ms,
+// cfg4s 10.85 -> 10.00 ms per launch (profiles/r02_ab_sampler_occupancy.md).  RANKFM_B200_GROUP_SHIFT=0 restores one quad
+// per lane.  With side features the lane-group-private chain copies (shared memory per group) keep the wide groups.
 static int sgd_group_size(const Tables& T, int* qpl_out)
 {
     int qpl = 1;
     int G = train_group_size(T, &qpl);
     const char* e = getenv("RANKFM_B200_GROUP_SHIFT");
-    if (e && atoi(e) == 1 && G >= 8 && qpl == 1 && max(T.Pp, T.Qp) <= 2 * G && !(T.x_uf_any || T.x_if_any)) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
+    const bool halve = !(e && atoi(e) == 0);
+    if (halve && G >= 8 && qpl == 1 && !(T.x_uf_any || T.x_if_any)) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
     if (qpl_out) *qpl_out = qpl;
     return G;
 }
@@ -475,7 +478,7 @@ static void with_pipe_kernel(bool feat, bool warp, bool tred, bool f8, F&& f)
             return;
         }
     }
-    if constexpr (QPL == 1) {
+    if constexpr (QPL <= 2) {
         if (!feat && warp && tred && warp_occ3()) { f(sgd_pipe_kernel<G, QPL, false, true, true, false, 3>); return; }
     }
     if (feat) {

@@ -47,7 +47,7 @@ class RankFM():
 
     _STATE = ('user_id', 'item_id', 'user_idx', 'item_idx', 'index_to_user', 'index_to_item', 'user_to_index',
               'item_to_index', 'interactions', 'sample_weight', 'user_items', 'x_uf', 'x_if', 'w_i', 'w_if',
-              'v_u', 'v_i', 'v_uf', 'v_if')
+              'v_u', 'v_i', 'v_uf', 'v_if', '_prepared_stamp')
 
     def _reset_state(self):
         """clear every fitted attribute (``rankfm.py:60-97``)"""
@@ -64,6 +64,17 @@ class RankFM():
     def _lookup(ids, known):
         """index of each id in the unique array ``known`` (-1 when absent); any id dtype"""
         return lookup_ids(ids, known)
+
+    def _lookup_known(self, ids, known):
+        """`_lookup` for a long column of integer ids: the distinct ids and their positions come from one device radix sort
+        (rfm_prep_index_ids), only the distinct ones are then matched against the model's (sorted) id list"""
+        ids = np.asarray(ids)
+        if len(ids) >= _rankfm._PREP_DEVICE_MIN and ids.dtype.kind in "iu" and known.dtype.kind in "iu" and _rankfm.device_count() > 0:
+            distinct, where = _rankfm.prep_index_ids(ids)
+            pos = np.searchsorted(known, distinct)
+            pos = np.where((pos < len(known)) & (known[np.minimum(pos, len(known) - 1)] == distinct), pos, -1).astype(np.int64)
+            return pos[where]
+        return self._lookup(ids, known)
 
     def _init_all(self, interactions, user_features=None, item_features=None, sample_weight=None):
         """first fit: build the id <-> index maps, then interactions, features, weights (``rankfm.py:100-137``)"""
@@ -96,8 +107,8 @@ class RankFM():
         self._check_interactions(interactions)
         if pairs is None:
             raw = get_data(interactions)
-            u = self._lookup(raw[:, 0], self.user_id.values)
-            i = self._lookup(raw[:, 1], self.item_id.values)
+            u = self._lookup_known(raw[:, 0], self.user_id.values)
+            i = self._lookup_known(raw[:, 1], self.item_id.values)
             if (u < 0).any() or (i < 0).any():
                 # the reference fails in `.astype(np.int32)` on the NaN produced by the id map (rankfm.py:154-155)
                 raise ValueError("[interactions] contains user/item identifiers that were not present in the initial fit")
@@ -123,6 +134,24 @@ class RankFM():
         else:
             self.user_items = UserItems.from_interactions(pairs, n_users, len(self.item_idx))
         self.interactions = pairs
+
+    @staticmethod
+    def _input_stamp(interactions, sample_weight):
+        """identity of the training input: (address, shape, dtype, CRC32) of the interaction and weight buffers -- the whole
+        buffer up to 64 MB, 2^20 strided samples beyond; None when the container has no single buffer to stamp"""
+        import zlib
+        out = []
+        for obj in (interactions, sample_weight):
+            if obj is None:
+                out.append(None)
+                continue
+            a = get_data(obj)
+            if not isinstance(a, np.ndarray) or a.dtype == object:
+                return None
+            flat = a.reshape(-1) if a.flags.c_contiguous else np.ascontiguousarray(a).reshape(-1)
+            sample = flat if flat.nbytes <= (64 << 20) else np.ascontiguousarray(flat[::max(1, flat.size >> 20)])
+            out.append((a.__array_interface__['data'][0], a.shape, a.dtype.str, zlib.crc32(sample.view(np.uint8))))
+        return tuple(out)
 
     def _feature_matrix(self, features, known_ids, n_rows, what):
         """[id, f_1..f_n] table -> float32 matrix row-ordered by index (``rankfm.py:189-211``)"""
@@ -175,10 +204,18 @@ class RankFM():
         assert isinstance(verbose, bool), "[verbose] must be a boolean value"
 
         if self.is_fit:
-            self._init_interactions(interactions, sample_weight)
+            # warm start (rankfm.py:269-327).  A loop of fit_partial() on the SAME interactions -- the usual way to train
+            # with per-epoch evaluation -- would redo the id lookups and the user_items union every call (two hash joins
+            # and a sort in the reference); identical input (same buffer, same shape, same CRC) keeps the prepared arrays,
+            # which also lets the plug-in reuse its resident training session
+            stamp = self._input_stamp(interactions, sample_weight)
+            if stamp is None or stamp != getattr(self, "_prepared_stamp", None):
+                self._init_interactions(interactions, sample_weight)
+                self._prepared_stamp = stamp
             self._init_features(user_features, item_features)
         else:
             self._init_all(interactions, user_features, item_features, sample_weight)
+            self._prepared_stamp = self._input_stamp(interactions, sample_weight)
 
         if self.loss == 'bpr':
             max_samples = 1                      # BPR == one negative per positive (rankfm.py:294-295)

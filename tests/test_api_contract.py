@@ -232,3 +232,22 @@ def test_evaluation_matches_the_reference_evaluation_module(backend):
     ref = dict(zip(g['diversity_item_id'].tolist(), g['diversity_cnt_users'].tolist()))
     assert ours == ref                                                       # the order among equal counts is unspecified (unstable sort)
     assert np.array_equal(div['cnt_users'].values, g['diversity_cnt_users']) and np.allclose(div['pct_users'].values, g['diversity_pct_users'], rtol=1e-12)
+
+
+def test_fit_partial_on_the_same_input_keeps_the_prepared_arrays(backend):
+    """a loop of fit_partial() on the same interactions must not redo the id lookups / the user_items union every call; any
+    other input (another buffer, or the same buffer edited in place) is prepared afresh"""
+    X = np.array(PAIRS * 50, dtype=np.int64)
+    model = RankFM(factors=2).fit(X, epochs=1)
+    prepared, items = model.interactions, model.user_items
+    model.fit_partial(X, epochs=1)
+    assert model.interactions is prepared and model.user_items is items
+    X[0] = (3, 1)                                       # edited in place: same address, other content
+    model.fit_partial(X, epochs=1)
+    assert model.interactions is not prepared and model.interactions[0].tolist() == [2, 0]
+    prepared = model.interactions
+    model.fit_partial(X.copy(), epochs=1)               # equal content in another buffer: prepared again (the stamp includes the address)
+    assert model.interactions is not prepared
+    w = np.ones(len(X), dtype=np.float32)
+    model.fit_partial(X, sample_weight=w, epochs=1)     # other sample weights: prepared again
+    assert model.sample_weight is not None and np.array_equal(model.sample_weight, w)
