@@ -391,6 +391,12 @@ int train_group_size(const Tables& T, int* qpl_out)
 // arithmetic, bookkeeping, TMA issue) is shared by twice as many positives: cfg2 0.97 -> 0.86 ms, cfg3n 27.9 -> 21.5 ms,
 // cfg4s 10.85 -> 10.00 ms per launch (profiles/r02_ab_sampler_occupancy.md).  RANKFM_B200_GROUP_SHIFT=0 restores one quad
 // per lane.  With side features the lane-group-private chain copies (shared memory per group) keep the wide groups.
+static bool feat_halve()
+{
+    const char* e = getenv("RANKFM_B200_FEAT_HALVE");
+    return e && atoi(e) == 1;
+}
+
 static int sgd_group_size(const Tables& T, int* qpl_out)
 {
     int qpl = 1;
@@ -398,6 +404,9 @@ static int sgd_group_size(const Tables& T, int* qpl_out)
     const char* e = getenv("RANKFM_B200_GROUP_SHIFT");
     const bool halve = !(e && atoi(e) == 0);
     if (halve && G >= 8 && qpl == 1 && !(T.x_uf_any || T.x_if_any)) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
+    // experiment (RANKFM_B200_FEAT_HALVE=1): the same for the feat8 side-feature kernel -- four chain copies per warp, one
+    // 256-thread block per SM (the same number of positives in flight per SM as two blocks of wide groups)
+    if (feat_halve() && G >= 16 && qpl == 1 && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8 && max(T.Pp, T.Qp) <= 2 * G) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
     if (qpl_out) *qpl_out = qpl;
     return G;
 }
@@ -419,7 +428,8 @@ static size_t pipe_smem_bytes_copies(const Tables& T, int G, int depth, int copi
 // group-private feature-parameter chains when two blocks of them still fit an SM, else one (atomic) chain per warp
 static int gp_private_of(const Tables& T, int G, int depth)
 {
-    return (32 / G) > 1 && pipe_smem_bytes_copies(T, G, depth, 32 / G) <= 100 * 1024 ? 1 : 0;
+    const size_t budget = feat_halve() ? 200 * 1024 : 100 * 1024;      // one block per SM in the half-width experiment
+    return (32 / G) > 1 && pipe_smem_bytes_copies(T, G, depth, 32 / G) <= budget ? 1 : 0;
 }
 static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
 {
@@ -474,7 +484,11 @@ static void with_pipe_kernel(bool feat, bool warp, bool tred, bool f8, F&& f)
 {
     if constexpr (G >= 8) {
         if (feat && f8 && tred) {
-            if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true>);
+            if constexpr (QPL == 2) {          // half-width groups: one block per SM, the whole register file
+                if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true, 1>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true, 1>);
+            } else {
+                if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true>);
+            }
             return;
         }
     }
