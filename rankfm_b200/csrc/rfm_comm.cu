@@ -14,6 +14,7 @@
 // Ranks meet at two in-kernel barriers (release/acquire flags at system scope in each other's window headers).
 // NCCL is used for the bootstrap (exchange of the 64-byte IPC handles), for tiny end-of-training reductions, and as the
 // fallback data path when peer mapping is not available.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -322,7 +323,7 @@ __device__ void exchange_barrier(const ExchParams& p, uint32_t seq, uint32_t arr
         for (int r = 0; r < p.world; ++r) {
             while ((int32_t)(ld_acquire_sys(&me->flag[32 * r]) - seq) < 0) {
                 if (clock64() - t0 > kBarrierTimeoutCycles) { me->err = 1u; break; }
-                __nanosleep(100);
+                __nanosleep(20);
             }
         }
         __threadfence_system();
@@ -420,14 +421,18 @@ int comm_exchange_p2p(Comm* c, cudaStream_t st, float* snap_it, float* snap_gp, 
     p.seq = c->seq; p.arrivals = c->arrivals;
     p.acc = acc;
     p.gp_new = reinterpret_cast<float*>(static_cast<char*>(c->win) + c->off_gpnew);
-    // every block spins at the barriers: the whole grid must be resident (2 blocks of 256 threads and no shared memory per
-    // SM always are, and nothing else runs on the session's stream at this point)
-    if (c->world <= 2) exchange_kernel<2><<<c->grid, 256, 0, st>>>(p);
-    else if (c->world <= 4) exchange_kernel<4><<<c->grid, 256, 0, st>>>(p);
-    else exchange_kernel<8><<<c->grid, 256, 0, st>>>(p);
+    // every block spins at the barriers: the whole grid must be resident (at most 2 blocks of 256 threads and no shared
+    // memory per SM always are, and nothing else runs on the session's stream at this point).  Small tables get a small
+    // grid: the exchange of a 350 KB table is two barriers and a few microseconds of copies, and every block more is one
+    // more arrival to count and one more spinner.
+    const long long quads = (long long)p.I * (p.NQ + 1);
+    const int grid = (int)std::min<long long>(c->grid, std::max<long long>(8, (quads + 1023) / 1024));
+    if (c->world <= 2) exchange_kernel<2><<<grid, 256, 0, st>>>(p);
+    else if (c->world <= 4) exchange_kernel<4><<<grid, 256, 0, st>>>(p);
+    else exchange_kernel<8><<<grid, 256, 0, st>>>(p);
     CU(cudaGetLastError());
     c->seq += 2u;
-    c->arrivals += 2u * (uint32_t)c->grid;
+    c->arrivals += 2u * (uint32_t)grid;
     return RFM_OK;
 }
 
