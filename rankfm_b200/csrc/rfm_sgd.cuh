@@ -184,10 +184,12 @@ __device__ __forceinline__ void sample_negatives_pipe(const TrainParams& p, cons
             const bool live = !done;
             B.cj[w] = (int)__umulhi(word, (uint32_t)T.I);
             load_item<G, QPL, FEAT>(T, B.cj[w], live, sub, B.cand[w]);
+            // membership word (bitmap word, or filter word of the candidate); stored RAW: the bit is extracted when the
+            // batch is consumed, so issuing a batch never waits for its own loads
             B.mw[w] = (live && p.bitmap) ? __ldg(p.bitmap + (size_t)u * p.bitmap_words + (B.cj[w] >> 5)) : 0u;
             if (!p.bitmap && p.bloom) {
                 const uint32_t h = bloom_slot(B.cj[w], deg);
-                B.mw[w] = (live && !listed && deg > 0) ? ((__ldg(p.bloom + seg + (h >> 5)) >> (h & 31)) & 1u) : 1u;
+                B.mw[w] = (live && !listed && deg > 0) ? __ldg(p.bloom + seg + (h >> 5)) : 0xffffffffu;
             }
         }
         a_issue += (uint32_t)K;
@@ -201,7 +203,9 @@ __device__ __forceinline__ void sample_negatives_pipe(const TrainParams& p, cons
             else {
                 const int c = B.cj[w];
                 const bool hit = group_ballot<G>(own[0] == c || own[1] == c || own[2] == c || own[3] == c, gw) != 0u;
-                const bool searched = group_member<G>(c, p.indices + seg, deg, live && !listed && (!p.bloom || B.mw[w] != 0u), sub, gw);
+                // without a filter every candidate is searched; with one only those whose bit is set
+                const bool maybe = !p.bloom || ((B.mw[w] >> (bloom_slot(c, deg) & 31u)) & 1u) != 0u;
+                const bool searched = group_member<G>(c, p.indices + seg, deg, live && !listed && maybe, sub, gw);
                 member = listed ? hit : searched;
             }
             const float pu = ut_ui - utility<G, QPL, FEAT>(uc, B.cand[w]);

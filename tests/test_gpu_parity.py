@@ -428,6 +428,38 @@ def test_nonfinite_weights_raise_like_the_reference(gpu_lib):
     assert not np.isfinite(w['v_i']).all()        # weights are written back in the non-finite state, like the reference
 
 
+@pytest.mark.parametrize("case", ["bpr_f16", "warp_feat"])
+def test_epoch_end_penalty_and_verbose_line_match_the_reference_formulas(gpu_lib, case, capsys):
+    """epoch end (`_rankfm.pyx:328-336`): the penalty reported with the last epoch is the reference's `reg_penalty` (`:106-116`:
+    alpha * sum(w_i^2, v_u^2, v_i^2) + beta * sum(w_if^2, v_uf^2, v_if^2)) of the weights the call returns, and a verbose fit
+    prints, per epoch, the two lines of `:332-336` with round(log-likelihood - penalty, 2)"""
+    g = load_golden(case)
+    args, w, _ = golden_fit_args(g)
+    stats = _rankfm.fit_ex(*args, g['epochs'], mode="replay", perms=g['perms'])
+    alpha, beta = float(g['hyper'][0]), float(g['hyper'][1])
+    sq = lambda a: float(np.sum(np.square(a.astype(np.float64))))
+    want = alpha * (sq(w['w_i']) + sq(w['v_u']) + sq(w['v_i']))
+    if g['x_if'].any():
+        want += beta * (sq(w['w_if']) + sq(w['v_if']))
+    if g['x_uf'].any():
+        want += beta * sq(w['v_uf'])
+    assert stats[-1]['penalty'] == pytest.approx(want, rel=1e-5)
+    # the log-likelihood of the replay run is the reference's (oracle) to float32 accumulation noise
+    args_o, wo, _ = golden_fit_args(g)
+    out = oracle.fit_ex(*args_o, g['epochs'], perms=g['perms'])
+    assert stats[-1]['log_likelihood'] == pytest.approx(float(out['ll'][-1]), rel=2e-4)
+    # verbose: one "training epoch" / "log likelihood" pair per epoch, printed by the plug-in like the reference
+    args_v, _, _ = golden_fit_args(g)
+    capsys.readouterr()
+    _rankfm._fit(*args_v, 2, True)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert [l.split(":")[0] for l in lines] == ["training epoch", "log likelihood"] * 2
+    assert lines[0] == "training epoch: 0" and lines[2] == "training epoch: 1"
+    ll_printed = float(lines[3].split(":")[1])
+    assert ll_printed == pytest.approx(round(_rankfm.last_stats[-1]['log_likelihood'] - _rankfm.last_stats[-1]['penalty'], 2), abs=0.011)
+    _rankfm.drop_training()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # predict / recommend / similar
 # ---------------------------------------------------------------------------------------------------------------
