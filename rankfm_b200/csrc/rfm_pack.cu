@@ -55,7 +55,7 @@ __global__ void pack_globals_kernel(const Tables T, const float* __restrict__ w_
 {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_total; e += gridDim.x * blockDim.x) {
         float v = 0.f;
-        if (e < T.gp_vuf) { if (e < T.Q && T.x_if_any) v = w_if[e]; }
+        if (e < T.gp_vuf) { if (e < T.Q) v = w_if[e]; }          // inactive blocks are packed too: epoch-end statistics cover all six arrays
         else if (e < T.gp_vif) { const int o = e - T.gp_vuf, p = o / T.Fp, f = o % T.Fp; if (f < T.F) v = v_uf[p * T.F + f]; }
         else { const int o = e - T.gp_vif, q = o / T.Fp, f = o % T.Fp; if (f < T.F) v = v_if[q * T.F + f]; }
         T.GP[e] = v;

@@ -752,7 +752,8 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const Tables T, doubl
         s[0] += w; s2[0] += (double)w * w;
     }
     if (T.GP) {
-        const long long n_wif = T.Qp, n_vuf = (long long)T.P * T.Fp * (T.x_uf_any ? 1 : 0), n_vif = (long long)T.Q * T.Fp * (T.x_if_any ? 1 : 0);
+        // all six arrays count, active or not, like the reference's assert_finite / reg_penalty (:95-116); pads are zero
+        const long long n_wif = T.gp_vuf, n_vuf = (long long)T.P * T.Fp, n_vif = (long long)T.Q * T.Fp;
         for (long long e = tid; e < n_wif; e += nth) { const float w = ld_cg1(T.GP + e); s[1] += w; s2[1] += (double)w * w; }
         for (long long e = tid; e < n_vuf; e += nth) { const float w = ld_cg1(T.GP + T.gp_vuf + e); s[4] += w; s2[4] += (double)w * w; }
         for (long long e = tid; e < n_vif; e += nth) { const float w = ld_cg1(T.GP + T.gp_vif + e); s[5] += w; s2[5] += (double)w * w; }

@@ -438,11 +438,7 @@ def test_epoch_end_penalty_and_verbose_line_match_the_reference_formulas(gpu_lib
     stats = _rankfm.fit_ex(*args, g['epochs'], mode="replay", perms=g['perms'])
     alpha, beta = float(g['hyper'][0]), float(g['hyper'][1])
     sq = lambda a: float(np.sum(np.square(a.astype(np.float64))))
-    want = alpha * (sq(w['w_i']) + sq(w['v_u']) + sq(w['v_i']))
-    if g['x_if'].any():
-        want += beta * (sq(w['w_if']) + sq(w['v_if']))
-    if g['x_uf'].any():
-        want += beta * sq(w['v_uf'])
+    want = alpha * (sq(w['w_i']) + sq(w['v_u']) + sq(w['v_i'])) + beta * (sq(w['w_if']) + sq(w['v_uf']) + sq(w['v_if']))
     assert stats[-1]['penalty'] == pytest.approx(want, rel=1e-5)
     # the log-likelihood of the replay run is the reference's (oracle) to float32 accumulation noise
     args_o, wo, _ = golden_fit_args(g)
