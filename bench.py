@@ -494,6 +494,18 @@ def measure_training(job, name, steps, warmup, e2e_steps, sample_clocks=False):
     return rec, c
 
 
+def fit_phases():
+    """{create+H2D, train, D2H, destroy} milliseconds of this thread's last rfm_fit (None before the first call)"""
+    import ctypes as C
+    from rankfm_b200 import _lib
+    out = (C.c_double * 4)()
+    try:
+        _lib.lib().rfm_last_fit_phases(out)
+    except Exception:
+        return None
+    return [float(v) for v in out]
+
+
 def measure_e2e(job, c, X, ui, w, epochs, steps):
     rfm, world = job.rfm, job.world
     N = len(X)
@@ -501,12 +513,16 @@ def measure_e2e(job, c, X, ui, w, epochs, steps):
     pinned = [X, c["sw"], ui.indptr, ui.indices] + [w[k] if k != "v_u" else w[k][lo:hi] for k in WEIGHTS]
     rfm.pin(*pinned)
 
+    phases = []
+
     def step():
         reset_weights(c, w)
         job.barrier()
         t0 = time.perf_counter()
         rfm._fit(X, c["sw"], ui, c["x_uf"], c["x_if"], *[w[k] for k in WEIGHTS], *HYPER_ARGS, c["max_samples"], epochs, False)
-        return job.max_over_ranks(time.perf_counter() - t0)
+        dt = time.perf_counter() - t0
+        phases.append(fit_phases())
+        return job.max_over_ranks(dt)
 
     w_bytes = sum(v.nbytes for v in c["w0"].values())                    # v_u: the owned rows only
     data_bytes = X.nbytes + c["sw"].nbytes + (hi - lo + 1) * 8 + int(ui.indptr[hi] - ui.indptr[lo]) * 4 + \
@@ -516,14 +532,22 @@ def measure_e2e(job, c, X, ui, w, epochs, steps):
         rfm.set_resident_training(resident)
         for _ in range(warm):                             # the block cache / lazy module loading settle over the first calls
             step()
+        del phases[:]
         dts = [step() for _ in range(n)]
         dt_med = float(np.median(dts))
+        # where a stateless call spends its wall time on THIS rank (library clock): median call and slowest call
+        ph = None
+        if not resident and phases and phases[0] is not None:
+            order = np.argsort(dts)
+            names = ("create_h2d_ms", "train_ms", "d2h_ms", "destroy_ms")
+            ph = {"median_call": dict(zip(names, [round(v, 2) for v in phases[order[len(order) // 2]]])),
+                  "slowest_call": dict(zip(names, [round(v, 2) for v in phases[order[-1]]]))}
         # wall-clock steps on a shared host see occasional scheduling hiccups: the value is the MEDIAN step, every sample
         # and the mean are reported next to it
         out.append({"value": N * epochs * world / dt_med, "unit": "interactions/s",
                     "h2d_bytes_per_step": int((w_bytes + (0 if resident else data_bytes)) * world), "d2h_bytes_per_step": int(w_bytes * world),
                     "ms_per_step": 1e3 * dt_med, "statistic": "median of %d steps%s" % (len(dts), ", max over ranks" if world > 1 else ""),
-                    "mean_ms_per_step": 1e3 * float(np.mean(dts)), "ms_each": [round(1e3 * d, 2) for d in dts],
+                    "mean_ms_per_step": 1e3 * float(np.mean(dts)), "ms_each": [round(1e3 * d, 2) for d in dts], "library_phases": ph,
                     "call": "rankfm_b200._rankfm._fit(page-locked host ndarray buffers) -> ctypes -> C ABI, on every rank; " +
                             ("the plug-in keeps the training session of the previous call (fit_partial pattern): only the weight arrays move"
                              if resident else "stateless: every call uploads interactions, user_items CSR, features and weights; the job's communicator is cached by the library")})

@@ -150,6 +150,10 @@ int rfm_synth_zipf(int32_t U, int32_t I, int64_t N, double a_u, double a_i, uint
  * `perms` = int32 [epochs,N] when order==RFM_ORDER_HOST, else NULL.  `stats` = [epochs] or NULL. */
 int rfm_fit(const rfm_problem *p, int32_t epochs, const int32_t *perms, rfm_epoch_stats *stats);
 
+/* wall-clock phases of this thread's last rfm_fit call, milliseconds: { session create + H2D, training, D2H, destroy }
+ * (bench.py reports them next to the end-to-end time of the stateless plug-in call) */
+int rfm_last_fit_phases(double *out4);
+
 /* replaces `_predict` (`_rankfm.pyx:345-390`): pairs f32 [n,2] hold indexes as floats, NaN = unknown id */
 int rfm_predict(const rfm_problem *p, const float *pairs, int64_t n, float *scores);
 

@@ -309,6 +309,44 @@ static int upload_weights(rfm_session* s, const float* w_i, const float* w_if, c
     return RFM_OK;
 }
 
+// Streams and events are pooled per device like the device blocks: a stateless `_fit` call would otherwise create and
+// destroy one stream and 4 x epochs events (160+ driver calls at 20 epochs), each of which takes the driver's locks and
+// is exposed to whatever else the host is doing -- measured as 10-70 ms spikes of the call on busy hosts.
+namespace {
+struct StreamPool {
+    std::mutex mu;
+    std::vector<std::pair<int, cudaStream_t>> streams;
+    std::vector<std::pair<int, cudaEvent_t>> events;
+};
+StreamPool g_pool;
+}  // namespace
+
+static cudaError_t pool_stream(int dev, cudaStream_t* out)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        for (size_t k = 0; k < g_pool.streams.size(); ++k)
+            if (g_pool.streams[k].first == dev) { *out = g_pool.streams[k].second; g_pool.streams.erase(g_pool.streams.begin() + (long)k); return cudaSuccess; }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+static cudaError_t pool_event(int dev, cudaEvent_t* out)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        for (size_t k = g_pool.events.size(); k-- > 0;)
+            if (g_pool.events[k].first == dev) { *out = g_pool.events[k].second; g_pool.events.erase(g_pool.events.begin() + (long)k); return cudaSuccess; }
+    }
+    return cudaEventCreate(out);
+}
+static void pool_return(int dev, cudaStream_t st, std::vector<cudaEvent_t>& ev)
+{
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    if (st) g_pool.streams.push_back({dev, st});
+    for (auto e : ev) g_pool.events.push_back({dev, e});
+    ev.clear();
+}
+
 // 32-bit pivot arithmetic of group_member (rfm_common.cuh): G * degree < 2^32 with G <= 32
 constexpr int64_t kMaxUserDegree = ((int64_t)1 << 32) / 32;
 
@@ -334,7 +372,6 @@ extern "C" int rfm_session_destroy(rfm_session* s)
         rfmh::comm_window_detach(s->comm, s);
         rfmh::comm_release(s->comm);
     }
-    for (auto e : s->ev) cudaEventDestroy(e);
     dev_free(s->ut_alloc);
     if (!s->p2p) { dev_free(s->T.IT); dev_free(s->T.GP); dev_free(s->d_item_touch); }
     dev_free(s->d_inter); dev_free(s->d_sw); dev_free(s->indptr_alloc); dev_free(s->indices_alloc);
@@ -343,9 +380,9 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     dev_free(s->d_snap_ut); dev_free(s->d_snap_it); dev_free(s->d_snap_gp); dev_free(s->d_trace);
     dev_free(s->d_gemm_B); dev_free(s->d_gemm_bias); dev_free(s->d_gemm_order);
     for (void* q : s->scratch) dev_free(q);
-    if (s->t0) cudaEventDestroy(s->t0);
-    if (s->t1) cudaEventDestroy(s->t1);
-    if (s->st) cudaStreamDestroy(s->st);
+    if (s->t0) s->ev.push_back(s->t0);
+    if (s->t1) s->ev.push_back(s->t1);
+    pool_return(s->device, s->st, s->ev);               // the stream is idle: every dev_free above synchronised the device
     delete s;
     return RFM_OK;
 }
@@ -389,7 +426,7 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
             if (s->device < 64) sm_count_cache[s->device] = n;
         }
     }
-    CUB(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CUB(pool_stream(s->device, &s->st));
 
     Tables& T = s->T;
     T.U = p->U; T.I = p->I; T.F = p->F; T.P = p->P; T.Q = p->Q;
@@ -463,11 +500,11 @@ extern "C" int rfm_session_create(const rfm_problem* p, rfm_session** out)
             // membership bitmap when (owned users) x I bits fit the budget: default min(8 GiB, a quarter of the free HBM);
             // RANKFM_B200_BITMAP_MB overrides, 0 disables (the kernels then search the CSR)
             const char* env = getenv("RANKFM_B200_BITMAP_MB");
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            const double budget_mb = env ? atof(env) : std::min(8192.0, (double)free_b / (4.0 * 1024.0 * 1024.0));
             const int words = (p->I + 31) / 32;
             const double need_mb = (double)T.Un * words * 4.0 / (1024.0 * 1024.0);
+            size_t free_b = (size_t)64 << 30, total_b = 0;
+            if (!env && need_mb > 64.0) cudaMemGetInfo(&free_b, &total_b);       // small bitmaps always fit: skip the driver call
+            const double budget_mb = env ? atof(env) : std::min(8192.0, (double)free_b / (4.0 * 1024.0 * 1024.0));
             if (need_mb <= budget_mb) {
                 s->bitmap_words = words;
                 TRY(dev_alloc(&s->bitmap_alloc, (size_t)T.Un * words));
@@ -567,7 +604,7 @@ extern "C" int rfm_session_timer_start(rfm_session* s)
 {
     if (!s) return fail(RFM_ERR_ARG, "NULL session");
     CU(cudaSetDevice(s->device));
-    if (!s->t0) { CU(cudaEventCreate(&s->t0)); CU(cudaEventCreate(&s->t1)); }
+    if (!s->t0) { CU(pool_event(s->device, &s->t0)); CU(pool_event(s->device, &s->t1)); }
     CU(cudaStreamSynchronize(s->st));
     CU(cudaEventRecord(s->t0, s->st));
     return RFM_OK;
@@ -779,7 +816,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
         s->acc_cap = epochs;
     }
     CU(cudaMemsetAsync(s->d_acc, 0, (size_t)epochs * sizeof(EpochAcc), s->st));
-    while ((int)s->ev.size() < 4 * epochs) { cudaEvent_t e; CU(cudaEventCreate(&e)); s->ev.push_back(e); }
+    while ((int)s->ev.size() < 4 * epochs) { cudaEvent_t e; CU(pool_event(s->device, &e)); s->ev.push_back(e); }
     if (s->comm) {
         CU(cudaMemcpyAsync(s->d_it_snap, s->T.IT, (size_t)s->T.I * s->T.ldi * 4, cudaMemcpyDeviceToDevice, s->st));
         CU(cudaMemcpyAsync(s->d_gp_snap, s->T.GP, s->gp_floats * 4, cudaMemcpyDeviceToDevice, s->st));
@@ -840,7 +877,7 @@ extern "C" int rfm_session_train(rfm_session* s, int32_t epochs, const int32_t* 
             // private feature-parameter chains: one per lane group (or warp) that owns >= 1 batch
             const double n_batches = std::ceil((double)s->N / 32.0);
             chains = std::min((double)grid * (kTrainThreads / 32), n_batches) * sgd_pipe_chains_per_warp(s->T);
-            steps_per_chain = (double)s->N / chains;
+            steps_per_chain = (double)s->N / chains / sgd_pipe_groups_per_chain(s->T);   // a racing per-warp chain advances once per warp step
             tp.gp_acc = s->d_gp_acc;
             tp.gp_gain = fold_gain((double)tp.reg_b * eta, steps_per_chain, chains);
         }
@@ -1391,6 +1428,15 @@ static double now_ms()
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+static thread_local double g_fit_phases[4] = {0, 0, 0, 0};
+
+extern "C" int rfm_last_fit_phases(double* out4)
+{
+    if (!out4) return fail(RFM_ERR_ARG, "out4 is NULL");
+    for (int k = 0; k < 4; ++k) out4[k] = g_fit_phases[k];
+    return RFM_OK;
+}
+
 extern "C" int rfm_fit(const rfm_problem* p, int32_t epochs, const int32_t* perms, rfm_epoch_stats* stats)
 {
     const bool timing = getenv("RANKFM_B200_TIMING") != nullptr;
@@ -1409,7 +1455,9 @@ extern "C" int rfm_fit(const rfm_problem* p, int32_t epochs, const int32_t* perm
     }
     const double t3 = now_ms();
     rfm_session_destroy(s);
-    if (timing) fprintf(stderr, "[rfm_fit] create+H2D %.2f ms, train %.2f ms, D2H %.2f ms, destroy %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
+    const double t4 = now_ms();
+    g_fit_phases[0] = t1 - t0; g_fit_phases[1] = t2 - t1; g_fit_phases[2] = t3 - t2; g_fit_phases[3] = t4 - t3;
+    if (timing) fprintf(stderr, "[rfm_fit] create+H2D %.2f ms, train %.2f ms, D2H %.2f ms, destroy %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3);
     return rc;
 }
 

@@ -43,6 +43,7 @@ struct TrainParams {
     float gp_gain;           // weight of each warp's delta when the chains are folded (see rfm_session_train)
     int32_t gp_floats;
     int32_t gp_private;      // 1: one feature-parameter chain per lane group (plain RMW), 0: one per warp (atomics)
+    int32_t gp_race;         // 1: one chain per warp, the lane groups' plain stores race (one update lands per step)
     uint32_t k0, k1, epoch_key;
     MtState* mt;             // non-null -> MT19937 sampler (serial only)
     EpochAcc* acc;
@@ -56,6 +57,7 @@ cudaError_t launch_build_bitmap(const int64_t* indptr, const int32_t* indices, i
 cudaError_t launch_gp_apply(float* gp, float* acc, int n, cudaStream_t st);
 size_t sgd_pipe_smem_bytes(const Tables& T);
 int sgd_pipe_chains_per_warp(const Tables& T);
+int sgd_pipe_groups_per_chain(const Tables& T);
 // self-test of the P, Q <= 8 specialisation of the side-feature math (rfm_feat8.cuh) against the generic code: out5 =
 // max |difference| of a[], b[], the chain copy after one step, the row deltas; and the largest chain movement (non-zero)
 cudaError_t launch_feat8_selftest(const Tables& T, uint32_t seed, float eta, float reg_b, float* out5, cudaStream_t st);

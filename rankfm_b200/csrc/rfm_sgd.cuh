@@ -383,7 +383,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
                 const float4 w = gp_ld4<GPS>(gp + 4 * sub);
                 float4 d;
                 d.x = RFM_G(dx.x, w.x); d.y = RFM_G(dx.y, w.y); d.z = RFM_G(dx.z, w.z); d.w = RFM_G(dx.w, w.w);
-                gp_add4<G, GPS>(gp + 4 * sub, w, d, p.gp_private != 0);
+                gp_add4<G, GPS>(gp + 4 * sub, w, d, (p.gp_private | p.gp_race) != 0);
             }
         }
         if (T.x_uf_any) {                                                  // v_uf[p] for x_uf[u,p] != 0 (:313-318)
@@ -399,7 +399,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
                         float4 d;
                         d.x = RFM_G(xp * dij_new[k].x, w.x); d.y = RFM_G(xp * dij_new[k].y, w.y);
                         d.z = RFM_G(xp * dij_new[k].z, w.z); d.w = RFM_G(xp * dij_new[k].w, w.w);
-                        gp_add4<G, GPS>(wp, w, d, p.gp_private != 0);
+                        gp_add4<G, GPS>(wp, w, d, (p.gp_private | p.gp_race) != 0);
                     }
                 }
             }
@@ -417,7 +417,7 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
                         float4 d;
                         d.x = RFM_G(dxq * vu_new[k].x, w.x); d.y = RFM_G(dxq * vu_new[k].y, w.y);
                         d.z = RFM_G(dxq * vu_new[k].z, w.z); d.w = RFM_G(dxq * vu_new[k].w, w.w);
-                        gp_add4<G, GPS>(wp, w, d, p.gp_private != 0);
+                        gp_add4<G, GPS>(wp, w, d, (p.gp_private | p.gp_race) != 0);
                     }
                 }
             }

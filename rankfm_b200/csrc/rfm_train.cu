@@ -391,6 +391,16 @@ int train_group_size(const Tables& T, int* qpl_out)
 // arithmetic, bookkeeping, TMA issue) is shared by twice as many positives: cfg2 0.97 -> 0.86 ms, cfg3n 27.9 -> 21.5 ms,
 // cfg4s 10.85 -> 10.00 ms per launch (profiles/r02_ab_sampler_occupancy.md).  RANKFM_B200_GROUP_SHIFT=0 restores one quad
 // per lane.  With side features the lane-group-private chain copies (shared memory per group) keep the wide groups.
+// experiment (RANKFM_B200_CHAIN=warp): ONE feature-parameter chain per warp instead of one per lane group.  All lane groups
+// of the warp read it, compute their update of the same step and store it with plain stores: one of them lands (per
+// element), i.e. the chain advances by ONE positive per warp step -- the same dynamics as a group-private chain (which also
+// sees one positive per step), with 1/GPW of the shared memory, which is what lets half-width groups keep two blocks per SM
+static bool chain_per_warp()
+{
+    const char* e = getenv("RANKFM_B200_CHAIN");
+    return e && !strcmp(e, "warp");
+}
+
 static bool feat_halve()
 {
     const char* e = getenv("RANKFM_B200_FEAT_HALVE");
@@ -428,6 +438,7 @@ static size_t pipe_smem_bytes_copies(const Tables& T, int G, int depth, int copi
 // group-private feature-parameter chains when two blocks of them still fit an SM, else one (atomic) chain per warp
 static int gp_private_of(const Tables& T, int G, int depth)
 {
+    if (chain_per_warp()) return 0;                                    // one racing copy per warp (see chain_per_warp)
     const size_t budget = feat_halve() ? 200 * 1024 : 100 * 1024;      // one block per SM in the half-width experiment
     return (32 / G) > 1 && pipe_smem_bytes_copies(T, G, depth, 32 / G) <= budget ? 1 : 0;
 }
@@ -435,6 +446,14 @@ static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
 {
     return pipe_smem_bytes_copies(T, G, depth, gp_private_of(T, G, depth) ? 32 / G : 1);
 }
+// lane groups of a warp that share one chain copy and race for its update: the chain advances once per warp step
+int sgd_pipe_groups_per_chain(const Tables& T)
+{
+    int qpl = 1;
+    const int G = sgd_group_size(T, &qpl);
+    return chain_per_warp() ? 32 / G : 1;
+}
+
 int sgd_pipe_chains_per_warp(const Tables& T)
 {
     int qpl = 1;
@@ -470,7 +489,7 @@ static bool feat8_ok(const Tables& T, int G, int gp_private)
 {
     const char* e = getenv("RANKFM_B200_FEAT8");                                   // experiments / tests: RANKFM_B200_FEAT8=0
     const bool off = e && !strcmp(e, "0");
-    return !off && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8 && G >= 8 && (gp_private || G == 32);
+    return !off && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8 && G >= 8 && (gp_private || G == 32 || chain_per_warp());
 }
 
 static bool warp_occ3()
@@ -484,8 +503,9 @@ static void with_pipe_kernel(bool feat, bool warp, bool tred, bool f8, F&& f)
 {
     if constexpr (G >= 8) {
         if (feat && f8 && tred) {
-            if constexpr (QPL == 2) {          // half-width groups: one block per SM, the whole register file
-                if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true, 1>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true, 1>);
+            if constexpr (QPL == 2) {          // half-width groups: 2 blocks/SM with one chain per warp, else 1 (chain copies)
+                if (chain_per_warp()) { if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true, 2>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true, 2>); }
+                else { if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true, 1>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true, 1>); }
             } else {
                 if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true>);
             }
@@ -526,6 +546,7 @@ static cudaError_t launch_gq(const TrainParams& p0, int grid, cudaStream_t st)
     p.depth = pipe_depth(p.T, G);
     p.gp_floats = (int)gp_floats_of(p.T);
     p.gp_private = gp_private_of(p.T, G, p.depth);
+    p.gp_race = chain_per_warp() ? 1 : 0;
     const size_t smem = pipe_smem_bytes(p.T, G, p.depth);
     return launch_pipe<G, QPL>(p, feat, grid, smem, st);
 }

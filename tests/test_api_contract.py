@@ -237,14 +237,16 @@ def test_evaluation_matches_the_reference_evaluation_module(backend):
 def test_fit_partial_on_the_same_input_keeps_the_prepared_arrays(backend):
     """a loop of fit_partial() on the same interactions must not redo the id lookups / the user_items union every call; any
     other input (another buffer, or the same buffer edited in place) is prepared afresh"""
-    X = np.array(PAIRS * 50, dtype=np.int64)
+    rng = np.random.default_rng(5)       # 200 users x 100 items (a 3 x 6 toy repeated 50x is no workload for a Hogwild schedule)
+    X = np.unique(np.stack([rng.integers(1, 201, 3000), rng.integers(1, 101, 3000)], 1), axis=0).astype(np.int64)
+    X = np.concatenate([X, np.stack([np.arange(1, 201), rng.integers(1, 101, 200)], 1), np.stack([rng.integers(1, 201, 100), np.arange(1, 101)], 1)])
     model = RankFM(factors=2).fit(X, epochs=1)
     prepared, items = model.interactions, model.user_items
     model.fit_partial(X, epochs=1)
     assert model.interactions is prepared and model.user_items is items
     X[0] = (3, 1)                                       # edited in place: same address, other content
     model.fit_partial(X, epochs=1)
-    assert model.interactions is not prepared and model.interactions[0].tolist() == [2, 0]
+    assert model.interactions is not prepared and model.interactions[0].tolist() == [2, 0]      # ids 1..N -> indexes 0..N-1
     prepared = model.interactions
     model.fit_partial(X.copy(), epochs=1)               # equal content in another buffer: prepared again (the stamp includes the address)
     assert model.interactions is not prepared
