@@ -390,21 +390,30 @@ int train_group_size(const Tables& T, int* qpl_out)
 // per lane -- twice the positives per warp instruction, so the scalar work per step and per sampler round (Philox, address
 // arithmetic, bookkeeping, TMA issue) is shared by twice as many positives: cfg2 0.97 -> 0.86 ms, cfg3n 27.9 -> 21.5 ms,
 // cfg4s 10.85 -> 10.00 ms per launch (profiles/r02_ab_sampler_occupancy.md).  RANKFM_B200_GROUP_SHIFT=0 restores one quad
-// per lane.  With side features the lane-group-private chain copies (shared memory per group) keep the wide groups.
-// experiment (RANKFM_B200_CHAIN=warp): ONE feature-parameter chain per warp instead of one per lane group.  All lane groups
-// of the warp read it, compute their update of the same step and store it with plain stores: one of them lands (per
-// element), i.e. the chain advances by ONE positive per warp step -- the same dynamics as a group-private chain (which also
-// sees one positive per step), with 1/GPW of the shared memory, which is what lets half-width groups keep two blocks per SM
-static bool chain_per_warp()
+// per lane.
+// Side features with at most 8 + 8 columns (the feat8 code path, rfm_feat8.cuh) keep ONE feature-parameter chain per warp
+// instead of one per lane group.  All lane groups of the warp read it, compute their update of the same step and store it
+// with plain stores: one of them lands (per element), i.e. the chain advances by ONE positive per warp step -- the same
+// dynamics as a group-private chain (which also sees one positive per warp step), with 1/GPW of the shared memory.  That is
+// what lets this kernel use half-width lane groups too (two quads per lane, four positives per warp step at F=64) at two
+// blocks per SM: cfg3 56.3 -> 44.0 ms, cfg3m 21.4 -> 16.7 ms per launch (profiles/r02_ab_sampler_occupancy.md).
+// RANKFM_B200_CHAIN=group restores one chain per lane group, RANKFM_B200_FEAT_HALVE=0 the wide groups.
+static bool feat8_shape(const Tables& T)
+{
+    const char* e = getenv("RANKFM_B200_FEAT8");                                   // experiments / tests: RANKFM_B200_FEAT8=0
+    const bool off = e && !strcmp(e, "0");
+    return !off && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8;
+}
+static bool chain_per_warp(const Tables& T, int G)
 {
     const char* e = getenv("RANKFM_B200_CHAIN");
-    return e && !strcmp(e, "warp");
+    if (e && !strcmp(e, "group")) return false;
+    return feat8_shape(T) && G >= 8 && G < 32;
 }
-
 static bool feat_halve()
 {
     const char* e = getenv("RANKFM_B200_FEAT_HALVE");
-    return e && atoi(e) == 1;
+    return !(e && atoi(e) == 0);
 }
 
 static int sgd_group_size(const Tables& T, int* qpl_out)
@@ -414,9 +423,8 @@ static int sgd_group_size(const Tables& T, int* qpl_out)
     const char* e = getenv("RANKFM_B200_GROUP_SHIFT");
     const bool halve = !(e && atoi(e) == 0);
     if (halve && G >= 8 && qpl == 1 && !(T.x_uf_any || T.x_if_any)) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
-    // experiment (RANKFM_B200_FEAT_HALVE=1): the same for the feat8 side-feature kernel -- four chain copies per warp, one
-    // 256-thread block per SM (the same number of positives in flight per SM as two blocks of wide groups)
-    if (feat_halve() && G >= 16 && qpl == 1 && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8 && max(T.Pp, T.Qp) <= 2 * G) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
+    // the feat8 side-feature kernel: half-width groups as well (its chain is per warp, see chain_per_warp)
+    if (feat_halve() && G >= 16 && qpl == 1 && feat8_shape(T) && max(T.Pp, T.Qp) <= 2 * G && chain_per_warp(T, G >> 1)) { G >>= 1; qpl = (T.NQ + G - 1) / G; }
     if (qpl_out) *qpl_out = qpl;
     return G;
 }
@@ -438,9 +446,8 @@ static size_t pipe_smem_bytes_copies(const Tables& T, int G, int depth, int copi
 // group-private feature-parameter chains when two blocks of them still fit an SM, else one (atomic) chain per warp
 static int gp_private_of(const Tables& T, int G, int depth)
 {
-    if (chain_per_warp()) return 0;                                    // one racing copy per warp (see chain_per_warp)
-    const size_t budget = feat_halve() ? 200 * 1024 : 100 * 1024;      // one block per SM in the half-width experiment
-    return (32 / G) > 1 && pipe_smem_bytes_copies(T, G, depth, 32 / G) <= budget ? 1 : 0;
+    if (chain_per_warp(T, G)) return 0;                                // one racing copy per warp (see chain_per_warp)
+    return (32 / G) > 1 && pipe_smem_bytes_copies(T, G, depth, 32 / G) <= 100 * 1024 ? 1 : 0;
 }
 static size_t pipe_smem_bytes(const Tables& T, int G, int depth)
 {
@@ -451,7 +458,7 @@ int sgd_pipe_groups_per_chain(const Tables& T)
 {
     int qpl = 1;
     const int G = sgd_group_size(T, &qpl);
-    return chain_per_warp() ? 32 / G : 1;
+    return chain_per_warp(T, G) ? 32 / G : 1;
 }
 
 int sgd_pipe_chains_per_warp(const Tables& T)
@@ -484,12 +491,11 @@ static bool use_tred()
     return cached == 1;
 }
 
-// the feat8 specialisation applies to: at most 8 + 8 active feature columns, lane groups of >= 8, one chain copy per group
+// the feat8 specialisation applies to: at most 8 + 8 active feature columns, lane groups of >= 8, and a chain copy that a
+// lane group may update with plain stores (its own, or the warp's racing one)
 static bool feat8_ok(const Tables& T, int G, int gp_private)
 {
-    const char* e = getenv("RANKFM_B200_FEAT8");                                   // experiments / tests: RANKFM_B200_FEAT8=0
-    const bool off = e && !strcmp(e, "0");
-    return !off && (T.x_uf_any || T.x_if_any) && T.P <= kFeat8 && T.Q <= kFeat8 && G >= 8 && (gp_private || G == 32 || chain_per_warp());
+    return feat8_shape(T) && G >= 8 && (gp_private || G == 32 || chain_per_warp(T, G));
 }
 
 static bool warp_occ3()
@@ -503,9 +509,8 @@ static void with_pipe_kernel(bool feat, bool warp, bool tred, bool f8, F&& f)
 {
     if constexpr (G >= 8) {
         if (feat && f8 && tred) {
-            if constexpr (QPL == 2) {          // half-width groups: 2 blocks/SM with one chain per warp, else 1 (chain copies)
-                if (chain_per_warp()) { if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true, 2>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true, 2>); }
-                else { if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true, 1>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true, 1>); }
+            if constexpr (QPL == 2) {          // half-width groups (only chosen together with the per-warp chain): 2 blocks/SM
+                if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true, 2>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true, 2>);
             } else {
                 if (warp) f(sgd_pipe_kernel<G, QPL, true, true, true, true>); else f(sgd_pipe_kernel<G, QPL, true, false, true, true>);
             }
@@ -546,7 +551,7 @@ static cudaError_t launch_gq(const TrainParams& p0, int grid, cudaStream_t st)
     p.depth = pipe_depth(p.T, G);
     p.gp_floats = (int)gp_floats_of(p.T);
     p.gp_private = gp_private_of(p.T, G, p.depth);
-    p.gp_race = chain_per_warp() ? 1 : 0;
+    p.gp_race = chain_per_warp(p.T, G) ? 1 : 0;
     const size_t smem = pipe_smem_bytes(p.T, G, p.depth);
     return launch_pipe<G, QPL>(p, feat, grid, smem, st);
 }

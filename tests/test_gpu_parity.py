@@ -294,11 +294,14 @@ def test_feat8_side_feature_code_matches_the_generic_code(gpu_lib, F, P, Q):
         assert moved > 1e-4                                   # the step really changed the parameters
 
 
-@pytest.mark.parametrize("F,P,Q,feat8", [(12, 5, 6, "1"), (64, 8, 8, "1"), (64, 8, 8, "0"), (40, 3, 8, "1")])
-def test_parallel_fit_with_features_statistical_parity(gpu_lib, F, P, Q, feat8, monkeypatch):
-    """(64, 8, 8) is BASELINE.json configs[2]'s row shape: G = 16 lane groups on the feat8 code path (feat8 = "0": the
-    generic loops on the same shape)"""
+@pytest.mark.parametrize("F,P,Q,feat8,chain", [(12, 5, 6, "1", "warp"), (64, 8, 8, "1", "warp"), (64, 8, 8, "1", "group"), (64, 8, 8, "0", "warp"),
+                                               (40, 3, 8, "1", "warp"), (128, 8, 8, "1", "warp")])
+def test_parallel_fit_with_features_statistical_parity(gpu_lib, F, P, Q, feat8, chain, monkeypatch):
+    """(64, 8, 8) is BASELINE.json configs[2]'s row shape.  Default: the feat8 code path on half-width lane groups (G = 8, two
+    quads per lane) with ONE racing chain per warp; chain = "group": wide groups, one chain per lane group (round-2 first
+    version); feat8 = "0": the generic run-time loops with group-private chains"""
     monkeypatch.setenv("RANKFM_B200_FEAT8", feat8)
+    monkeypatch.setenv("RANKFM_B200_CHAIN", chain)
     U, I = 1500, 800
     X = zipf_interactions(U, I, 40000, seed=5)
     U, I = int(X[:, 0].max()) + 1, int(X[:, 1].max()) + 1
