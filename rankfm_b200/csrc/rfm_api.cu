@@ -1025,7 +1025,11 @@ static int recommend_exact(rfm_session* s, const int32_t* d_users, int64_t n_use
     return RFM_OK;
 }
 
-constexpr int kCandCap = 256;        // smallest candidate-slot capacity; also the largest shortlist the tensor-core path accepts
+// Shortlist tiers of the tensor-core path.  A user's shortlist n' = 2 n_items + 16 (+ the items it has seen when filtering)
+// must fit the candidate buffers: users up to kCandCap go through the narrow tier (small buffers, 512-entry shortlist
+// kernel), users with long histories up to kCandCapWide through the wide tier (4x the buffers, 2048-entry shortlist) --
+// round 1 sent everybody above 256 to the exact fp32 path, 150x slower per user.
+constexpr int kCandCap = 256, kCandCapWide = 1024;
 
 static int ensure_gemm_items(rfm_session* s)
 {
@@ -1090,7 +1094,7 @@ static int tau_blocks(const Tables& T, int stride)
 // tensor-core path (rfm_gemm.cu): pass 1 block bounds -> per-row threshold -> pass 2 candidates -> shortlist (n' best by
 // bf16 score, exact fp32 re-score) -> top-n
 static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
-                        float* d_rec, float* gemm_ms)
+                        float* d_rec, float* gemm_ms, int cand_cap)
 {
     const Tables& T = s->T;
     if (n_users <= 0) return RFM_OK;
@@ -1099,12 +1103,13 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     const int Kp = gemm_kp(T), MT = gemm_m_tile(T), SPS = gemm_slots_per_split(T), I_pad = s->gemm_I_pad;
     const int stride = tau_stride(T, n_items), n_sub1 = tau_blocks(T, stride), n_tiles1 = n_sub1 / (gemm_block_n(T) / kTauBlock);
     // candidate entries per row: ~1-2 n' with a full pass 1, ~stride x n' with a strided one (n' <= kCandCap)
-    const int width = stride == 1 ? 8 * kCandCap : 4 * kCandCap * stride;
+    // (the shortlist kernel stages a row's candidates in shared memory: at most 16384 entries = 128 KB)
+    const int width = std::min(16384, stride == 1 ? 8 * cand_cap : 4 * cand_cap * stride);
     // one wave: at most n_sm CTAs (one resident per SM), user tiles x item splits; >= 2 splits keep a partial last batch balanced
     int64_t max_rows = (int64_t)std::max(1, s->n_sm / 2) * MT;
     max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)4 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
-    const int split_cap = std::max(1, std::min(n_tiles1, width / (kCandCap * SPS)));
+    const int split_cap = std::max(1, std::min(n_tiles1, width / (cand_cap * SPS)));
     // The user batches run back to back on the session's stream; targets of all batches are uploaded once and the redo
     // flags of all rows are read once, so the loop never synchronises with the host.  (Running the shortlist kernel of
     // batch b on a second stream next to the GEMM of batch b+1 was measured and bought nothing: a GEMM CTA holds ~200 KB
@@ -1153,7 +1158,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e));
         if (gemm_ms) CU(cudaEventRecord(ev.back(), s->st));
         e = launch_shortlist(T, d_users + off, nb, cand, cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
-                             n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, s->st);
+                             n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, 2 * cand_cap, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
         s->launches += 5;
     }
@@ -1188,10 +1193,12 @@ static int recommend_mode()
     return !strcmp(e, "tc") ? 1 : (!strcmp(e, "exact") ? 2 : 0);
 }
 
-// Plan: users whose shortlist (2n+16 [+ seen items]) fits the candidate buffer go through the tensor cores, the rest (and
+// Plan: users whose shortlist (2n+16 [+ seen items]) fits a candidate tier go through the tensor cores, the rest (and
 // everything when the shape is not supported / too small to pay off) through the exact path.  `order` receives a
-// permutation of [0,n_users): tensor-core users first.  Returns the number of tensor-core users.
-static int64_t recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, int32_t n_items, int32_t filter_previous, std::vector<int64_t>& order)
+// permutation of [0,n_users): narrow-tier users first, then wide-tier users, then the exact-path users.
+struct RecommendPlan { int64_t n_narrow = 0, n_wide = 0; };
+
+static RecommendPlan recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, int32_t n_items, int32_t filter_previous, std::vector<int64_t>& order)
 {
     const int64_t n = (int64_t)hu.size();
     order.resize((size_t)n);
@@ -1199,23 +1206,33 @@ static int64_t recommend_plan(rfm_session* s, const std::vector<int32_t>& hu, in
     const Tables& T = s->T;
     bool tc = mode != 2 && gemm_supported(T) && encode_ok() && (mode == 1 || ((int64_t)T.I >= 32768 && n * (int64_t)T.I >= ((int64_t)1 << 26)));
     // the per-row threshold is the n'-th largest bound over 8-item blocks: needs comfortably more blocks than n'
-    const int limit = std::min(kCandCap, tau_blocks(T, tau_stride(T, n_items)) / 2);
-    if (2 * n_items + 16 > limit) tc = false;
-    int64_t lo = 0, hi = n;
+    const int blocks_half = tau_blocks(T, tau_stride(T, n_items)) / 2;
+    const int limit_narrow = std::min(kCandCap, blocks_half), limit_wide = std::min(kCandCapWide, blocks_half);
+    if (2 * n_items + 16 > limit_wide) tc = false;
+    std::vector<int64_t> wide, exact;
+    RecommendPlan plan;
     for (int64_t k = 0; k < n; ++k) {
-        const bool light = tc && shortlist_target(s, hu[(size_t)k], n_items, filter_previous) <= limit;
-        if (light) order[(size_t)lo++] = k; else order[(size_t)--hi] = k;
+        const int need = tc ? shortlist_target(s, hu[(size_t)k], n_items, filter_previous) : 0;
+        if (tc && need <= limit_narrow) order[(size_t)plan.n_narrow++] = k;
+        else if (tc && need <= limit_wide) wide.push_back(k);
+        else exact.push_back(k);
     }
-    return lo;
+    plan.n_wide = (int64_t)wide.size();
+    std::copy(wide.begin(), wide.end(), order.begin() + plan.n_narrow);
+    std::copy(exact.begin(), exact.end(), order.begin() + plan.n_narrow + plan.n_wide);
+    return plan;
 }
 
-static int recommend_dev(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_tc, int64_t n_users, int32_t n_items,
+static int recommend_dev(rfm_session* s, const int32_t* d_users, const int32_t* h_users, const RecommendPlan& plan, int64_t n_users, int32_t n_items,
                          int32_t filter_previous, float* d_rec, float* gemm_ms)
 {
     if (gemm_ms) *gemm_ms = 0.f;
-    int rc = recommend_tc(s, d_users, h_users, n_tc, n_items, filter_previous, d_rec, gemm_ms);
+    int rc = recommend_tc(s, d_users, h_users, plan.n_narrow, n_items, filter_previous, d_rec, gemm_ms, kCandCap);
     if (rc) return rc;
-    return recommend_exact(s, d_users + n_tc, n_users - n_tc, n_items, filter_previous, d_rec + (size_t)n_tc * n_items, gemm_ms);
+    const int64_t o1 = plan.n_narrow, o2 = plan.n_narrow + plan.n_wide;
+    rc = recommend_tc(s, d_users + o1, h_users + o1, plan.n_wide, n_items, filter_previous, d_rec + (size_t)o1 * n_items, gemm_ms, kCandCapWide);
+    if (rc) return rc;
+    return recommend_exact(s, d_users + o2, n_users - o2, n_items, filter_previous, d_rec + (size_t)o2 * n_items, gemm_ms);
 }
 
 static int recommend_checks(rfm_session* s, int64_t n_users, int32_t n_items, int32_t filter_previous)
@@ -1238,14 +1255,14 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     users_to_int(users, n_users, hu);
     for (auto u : hu) if (u >= 0 && (u < s->T.u0 || u >= s->T.u0 + s->T.Un)) return fail(RFM_ERR_ARG, "user index %d out of range [%d, %d)", u, s->T.u0, s->T.u0 + s->T.Un);
     std::vector<int64_t> order;
-    const int64_t n_tc = recommend_plan(s, hu, n_items, filter_previous, order);
+    const RecommendPlan plan = recommend_plan(s, hu, n_items, filter_previous, order);
     std::vector<int32_t> hp((size_t)n_users);
     for (int64_t k = 0; k < n_users; ++k) hp[(size_t)k] = hu[(size_t)order[(size_t)k]];
     DevBuf<int32_t> d_users; DevBuf<float> d_rec;
     if ((rc = d_users.alloc((size_t)n_users))) return rc;
     if ((rc = d_rec.alloc((size_t)n_users * n_items))) return rc;
     CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
-    if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
+    if ((rc = recommend_dev(s, d_users, hp.data(), plan, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
     std::vector<float> tmp((size_t)n_users * n_items);
     CU(cudaMemcpyAsync(tmp.data(), d_rec, (size_t)n_users * n_items * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
@@ -1267,7 +1284,7 @@ extern "C" int rfm_session_evaluate(rfm_session* s, const float* users, int64_t 
     users_to_int(users, n_users, hu);
     for (auto u : hu) if (u < s->T.u0 || u >= s->T.u0 + s->T.Un) return fail(RFM_ERR_ARG, "user index %d out of range [%d, %d)", u, s->T.u0, s->T.u0 + s->T.Un);
     std::vector<int64_t> order;
-    const int64_t n_tc = recommend_plan(s, hu, k, filter_previous, order);
+    const RecommendPlan plan = recommend_plan(s, hu, k, filter_previous, order);
     std::vector<int32_t> hp((size_t)n_users);
     for (int64_t r = 0; r < n_users; ++r) hp[(size_t)r] = hu[(size_t)order[(size_t)r]];
     const int64_t nnz = test_indptr[n_users];
@@ -1287,7 +1304,7 @@ extern "C" int rfm_session_evaluate(rfm_session* s, const float* users, int64_t 
     if (nnz) CU(cudaMemcpyAsync(d_items, test_items, (size_t)nnz * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemcpyAsync(d_ntest, n_test, (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaMemsetAsync(d_out, 0, 5 * sizeof(double), s->st));
-    if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, k, filter_previous, d_rec, nullptr))) return rc;
+    if ((rc = recommend_dev(s, d_users, hp.data(), plan, n_users, k, filter_previous, d_rec, nullptr))) return rc;
     cudaError_t e = launch_eval_topk(d_rec, d_order, (int)n_users, k, d_ptr, d_items, d_ntest, d_out, hits_out ? (uint8_t*)d_hits : nullptr, s->st);
     if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "eval_topk launch failed: %s", cudaGetErrorString(e));
     s->launches += 1;
@@ -1308,21 +1325,21 @@ extern "C" int rfm_session_time_recommend(rfm_session* s, const float* users, in
     std::vector<int32_t> hu;
     users_to_int(users, n_users, hu);
     std::vector<int64_t> order;
-    const int64_t n_tc = recommend_plan(s, hu, n_items, filter_previous, order);
+    const RecommendPlan plan = recommend_plan(s, hu, n_items, filter_previous, order);
     std::vector<int32_t> hp((size_t)n_users);
     for (int64_t k = 0; k < n_users; ++k) hp[(size_t)k] = hu[(size_t)order[(size_t)k]];
     DevBuf<int32_t> d_users; DevBuf<float> d_rec;
     if ((rc = d_users.alloc((size_t)n_users))) return rc;
     if ((rc = d_rec.alloc((size_t)n_users * n_items))) return rc;
     CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
-    if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;   // warm-up
+    if ((rc = recommend_dev(s, d_users, hp.data(), plan, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;   // warm-up
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
     float gemm_total = 0.f;
     CU(cudaEventRecord(a, s->st));
     for (int k = 0; k < iters; ++k) {
         float g = 0.f;
-        if ((rc = recommend_dev(s, d_users, hp.data(), n_tc, n_users, n_items, filter_previous, d_rec, gemm_ms_out ? &g : nullptr))) return rc;
+        if ((rc = recommend_dev(s, d_users, hp.data(), plan, n_users, n_items, filter_previous, d_rec, gemm_ms_out ? &g : nullptr))) return rc;
         gemm_total += g;
     }
     CU(cudaEventRecord(b, s->st));

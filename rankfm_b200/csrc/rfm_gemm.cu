@@ -442,7 +442,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kShortThreads = 256;
 
-template <int G, int QPL, bool FEAT>
+template <int G, int QPL, bool FEAT, int SW>
 __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T, const int32_t* __restrict__ users, const float2* __restrict__ cand,
                                                                   const int* __restrict__ cand_cnt, int slots, int cap, const float* __restrict__ bias,
                                                                   const int32_t* __restrict__ order, const int* __restrict__ n_target,
@@ -453,8 +453,8 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
     extern __shared__ __align__(16) unsigned char short_smem[];
     __shared__ float s_norm2;
     uint2* ent = reinterpret_cast<uint2*>(short_smem);               // [slots * cap] (ordered key of the bf16 score, position)
-    __shared__ int32_t kept[kShortWidth];                            // item ids of the shortlist, in position order
-    __shared__ unsigned long long sel[kShortWidth];                  // (ordered key of the exact score << 32) | shortlist slot
+    __shared__ int32_t kept[SW];                            // item ids of the shortlist, in position order
+    __shared__ unsigned long long sel[SW];                  // (ordered key of the exact score << 32) | shortlist slot
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining;
     __shared__ int s_off[65], s_over, s_base, wsum[kShortThreads / 32];
@@ -524,18 +524,18 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
         int before = s_base, all = 0;
         for (int w = 0; w < kShortThreads / 32; ++w) { if (w < warp) before += wsum[w]; all += wsum[w]; }
         const int mine = before + __popc(bal & ((1u << lane) - 1u));
-        if (keep && mine < kShortWidth) kept[mine] = __ldg(order + ent[e].y);
+        if (keep && mine < SW) kept[mine] = __ldg(order + ent[e].y);
         __syncthreads();
         if (tid == 0) s_base += all;
         __syncthreads();
     }
     const int n_kept = s_base;
-    if (n_kept > kShortWidth) {                                        // > kShortWidth - n' ties at the cut: exact path
+    if (n_kept > SW) {                                        // > SW - n' ties at the cut: exact path
         if (tid == 0) flag[b] = 1;
         return;
     }
     if (tid == 0) flag[b] = 0;
-    const int n_sort = n_kept <= kShortWidth / 2 ? kShortWidth / 2 : kShortWidth;             // power of two >= n_kept
+    const int n_sort = n_kept <= SW / 2 ? SW / 2 : SW;             // power of two >= n_kept
     for (int e = tid; e < n_sort; e += kShortThreads) sel[e] = 0ull;                            // key 0 sorts last
     __syncthreads();
     // 3. exact fp32 re-score
@@ -612,35 +612,44 @@ static bool shortlist_guard()
     return !(e && !strcmp(e, "0"));
 }
 
+template <int G, int QPL, int SW>
+static cudaError_t shortlist_launch(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
+                                    const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
+                                    int* flag, const float* tau, int I_pad, int guard, size_t smem, cudaStream_t st)
+{
+    cudaError_t e;
+    if (T.x_uf_any || T.x_if_any) {
+        e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, true, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        shortlist_kernel<G, QPL, true, SW><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
+    } else {
+        e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, false, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        shortlist_kernel<G, QPL, false, SW><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
+    }
+    return cudaGetLastError();
+}
+
 template <int G, int QPL>
 static cudaError_t shortlist_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                                 const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                                int* flag, const float* tau, int I_pad, cudaStream_t st)
+                                int* flag, const float* tau, int I_pad, int short_width, cudaStream_t st)
 {
     const size_t smem = (size_t)slots * cap * sizeof(uint2);
     const int guard = shortlist_guard() ? 1 : 0;
-    cudaError_t e;
-    if (T.x_uf_any || T.x_if_any) {
-        e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, true><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
-    } else {
-        e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, false><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
-    }
-    return cudaGetLastError();
+    if (short_width > kShortWidth) return shortlist_launch<G, QPL, kShortWidthWide>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, smem, st);
+    return shortlist_launch<G, QPL, kShortWidth>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, smem, st);
 }
 
 // rec [n_users, n_items]: final rows (float item indexes, NaN-padded like topn_select_kernel); flag [n_users]
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                             int* flag, const float* tau, int I_pad, cudaStream_t st)
+                             int* flag, const float* tau, int I_pad, int short_width, cudaStream_t st)
 {
     int qpl = 1;
     const int G = train_group_size(T, &qpl);
     if (max(T.Pp, T.Qp) > 4 * G || qpl > 4 || slots > 64 || (size_t)slots * cap * sizeof(uint2) > 160 * 1024) return cudaErrorInvalidValue;
-#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, st)
+#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, short_width, st)
     switch (G) {
         case 4:  RFM_SHORT(4, 1);
         case 8:  RFM_SHORT(8, 1);

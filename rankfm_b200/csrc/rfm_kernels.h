@@ -83,10 +83,11 @@ cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const 
                                 int tile_stride, float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st);
 cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st);
 constexpr int kTauBlock = 8;                   // items per pass-1 block bound
-constexpr int kShortWidth = 512;               // shortlist entries per row (n' <= 256 plus ties at the cut)
+constexpr int kShortWidth = 512;               // shortlist entries per row, narrow tier (n' <= 256 plus ties at the cut)
+constexpr int kShortWidthWide = 2048;          // wide tier (n' <= 1024: users with long histories under filter_previous)
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                             int* flag, const float* tau, int I_pad, cudaStream_t st);
+                             int* flag, const float* tau, int I_pad, int short_width, cudaStream_t st);
 cudaError_t launch_eval_topk(const float* rec, const int64_t* order, int n_users, int k, const int64_t* test_indptr, const int32_t* test_items,
                              const int32_t* n_test, double* out5, uint8_t* hits_out, cudaStream_t st);
 cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);

@@ -709,6 +709,41 @@ def test_recommend_tensor_core_many_batches(gpu_lib, monkeypatch):
     assert np.isnan(fast[[7, 20000, 44999]]).all()
 
 
+def test_recommend_tensor_core_long_histories_use_the_wide_tier(gpu_lib, monkeypatch):
+    """filter_previous with long user histories: the shortlist n' = 2 n + 16 + (items seen) of these users exceeds the narrow
+    tier (256) -- round 1 sent them to the exact path; the wide tier (n' <= 1024, 2048-entry shortlist) keeps them on the
+    tensor cores.  Users beyond 1024 still take the exact path inside the same call; every row must match the exact path."""
+    rng = np.random.default_rng(21)
+    U, I, F, n = 600, 40000, 24, 100
+    w = init_weights(U, I, F, seed=21, sigma=0.3)
+    w['w_i'][:] = rng.normal(0, 0.5, I).astype(np.float32)
+    x_uf, x_if = features(U, I, 0, 0)
+    deg = np.concatenate([np.full(200, 5), rng.integers(100, 750, 380), np.full(20, 1500)])       # narrow / wide / exact users
+    rng.shuffle(deg)
+    # long histories are made of LIKELY recommendations (high-bias items), so filtering really removes top candidates
+    popular = np.argsort(-w['w_i'])[:4000]
+    X = np.concatenate([np.stack([np.full(d, u), rng.choice(popular, d, replace=False)], 1) for u, d in enumerate(deg)]).astype(np.int32)
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    keep = []
+    prob = _rankfm.fit_problem(X, np.ones(len(X), np.float32), ui, x_uf, x_if, *[w[k] for k in WEIGHTS], 0.01, 0.1, 0.1, 'constant', 0.25, 1, keep=keep)
+    sess = _rankfm.Session(prob, keep)
+    users = np.arange(U, dtype=np.float32)
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    fast = sess.recommend(users, n, True)
+    tc_rows, tc_redone = sess.recommend_stats()
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "exact")
+    exact = sess.recommend(users, n, True)
+    sess.close()
+    need = 2 * n + 16 + deg
+    assert tc_rows == int(np.sum(need <= 1024)) and tc_rows > int(np.sum(need <= 256)) > 0, (tc_rows, np.sum(need <= 256), np.sum(need <= 1024))
+    assert tc_redone <= tc_rows // 20
+    seen = [set(indices[indptr[u]:indptr[u + 1]].tolist()) for u in range(U)]
+    assert all(not (set(fast[u].astype(int).tolist()) & seen[u]) for u in range(U))            # nothing seen is recommended
+    assert topk_overlap(fast, exact) >= 0.999
+    assert np.mean(fast == exact) >= 0.99
+
+
 @pytest.mark.parametrize("case", ["flat_bias", "all_tied"])
 def test_recommend_tensor_core_degenerate_scores(gpu_lib, case, monkeypatch):
     """flat_bias: every item bias equal (bias order degenerates to item order) -> still served by the tensor-core path;
