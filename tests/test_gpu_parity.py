@@ -744,6 +744,27 @@ def test_recommend_tensor_core_long_histories_use_the_wide_tier(gpu_lib, monkeyp
     assert np.mean(fast == exact) >= 0.99
 
 
+def test_recommend_tensor_core_path_matches_the_oracle_on_a_thousand_users(gpu_lib, monkeypatch):
+    """north_star: recommend() top-k set overlap >= 0.99 -- the tcgen05 path against the ORACLE's `_recommend` (the C
+    restatement of `_rankfm.pyx:393-460`, all-item fp32 scoring + full sort), 1,024 users x 40,000 items, with and without
+    filter_previous"""
+    rng = np.random.default_rng(33)
+    U, I, F = 1024, 40000, 24
+    w = init_weights(U, I, F, seed=33, sigma=0.3)
+    w['w_i'][:] = rng.normal(0, 0.5, I).astype(np.float32)
+    x_uf, x_if = features(U, I, 0, 0)
+    X = np.unique(np.stack([rng.integers(0, U, 20 * U), rng.integers(0, I, 20 * U)], 1), axis=0).astype(np.int32)
+    indptr, indices = csr_of(X, U)
+    ui = CSRItems(indptr, indices)
+    users = np.arange(U, dtype=np.float32)
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    for filt in (False, True):
+        got = _rankfm._recommend(users, ui, 20, filt, x_uf, x_if, *[w[k] for k in WEIGHTS])
+        want = oracle._recommend(users, ui, 20, filt, x_uf, x_if, *[w[k] for k in WEIGHTS])
+        assert topk_overlap(got, want) >= 0.99, filt
+        assert np.mean(got == want) >= 0.97, filt                  # order too, up to float32 near-ties
+
+
 @pytest.mark.parametrize("case", ["flat_bias", "all_tied"])
 def test_recommend_tensor_core_degenerate_scores(gpu_lib, case, monkeypatch):
     """flat_bias: every item bias equal (bias order degenerates to item order) -> still served by the tensor-core path;
