@@ -670,6 +670,7 @@ def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, de
     os.environ["RANKFM_B200_RECOMMEND"] = "tc"
     ms, gemm_ms = sess.time_recommend(users, topn, False, iters=iters)
     tc_rows, tc_redone = sess.recommend_stats()
+    tc_retried = sess.recommend_retried()
     # e2e: the call a user makes -- host user indexes in, host item indexes out (H2D of the user list, D2H of the top-n table)
     t0 = time.perf_counter()
     sess.recommend(users, topn, False)
@@ -692,7 +693,9 @@ def recommend_probe(n_users=65536, n_items_cat=262144, factors=128, topn=100, de
             "e2e_users_per_s": n_users / e2e_s, "e2e_ms": 1e3 * e2e_s, "h2d_bytes": int(users.nbytes), "d2h_bytes": int(n_users * topn * 4),
             "exact_fp32_path_users_per_s": (exact_users / (ms_exact * 1e-3)) if ms_exact else None, "topk_overlap_vs_exact": overlap,
             "rows_redone_on_exact_path": "%d of %d" % (tc_redone, tc_rows),
-            "variant": {k: os.environ.get(k, "default") for k in ("RANKFM_B200_GEMM_MSUB", "RANKFM_B200_TAU_STRIDE")}}
+            "rows_redone_with_provable_threshold": "%d of %d" % (tc_retried, tc_rows),
+            "variant": {k: os.environ.get(k, "default") for k in ("RANKFM_B200_GEMM_MSUB", "RANKFM_B200_GEMM_EW", "RANKFM_B200_TAU_MODE", "RANKFM_B200_TAU_STRIDE",
+                                                                  "RANKFM_B200_TAU_MIN", "RANKFM_B200_TAU_Z")}}
 
 
 def recommend_record(full, device, iters=3):
@@ -708,7 +711,8 @@ def recommend_record(full, device, iters=3):
             "data": "synthetic", "config": {"workload": r["workload"]},
             "roofline": {"bound": "tensor", "kernel": "score_filter_kernel (pass 1 + pass 2)", "achieved": r["tflops_gemm_filter"], "peak": r["bf16_peak_tflops"],
                          "unit": "TFLOP/s", "frac": r["frac_of_bf16_peak"], "traffic": None, "peak_source": r["peak_source"],
-                         "note": "useful FLOPs 2*U*I*K over the CUDA-event time of both GEMM passes + threshold kernels"},
+                         "note": "useful FLOPs 2*U*I*K over the CUDA-event time of both GEMM passes + threshold kernels; pass 2 is bound by the TMEM read of its fp32 "
+                                 "accumulators (tcgen05.ld ~64 B/clk/SM, measured 61): with K=128 that caps it at 0.5 of the tensor pipe's rate (DESIGN.md 3.4)"},
             "e2e": {"value": r["e2e_users_per_s"], "unit": "users/s", "h2d_bytes_per_step": r["h2d_bytes"], "d2h_bytes_per_step": r["d2h_bytes"], "ms_per_step": r["e2e_ms"],
                     "call": "Session.recommend(host float32 user indexes) -> host float32 [users, 100] item indexes"},
             "recommend": r}

@@ -216,6 +216,9 @@ int rfm_session_attach_csr(rfm_session *s, const int64_t *csr_indptr /* [U+1] */
 /* tensor-core recommend bookkeeping since session creation: rows served by the tcgen05 path, and how many of those had to
  * be redone on the exact fp32 path because a candidate slot overflowed */
 int rfm_session_recommend_stats(rfm_session *s, int64_t *tc_rows, int64_t *tc_redone);
+/* ... and how many rows were served a second time with the provable row threshold because the estimated one (taken from a
+ * 1-in-k sample of the item tiles, see rfm_api.cu "ESTIMATED") came out too high for them; results never depend on it */
+int rfm_session_recommend_retried(rfm_session *s, int64_t *tc_retried);
 /* the library keeps freed device blocks for the next call of the same shape (one-shot calls create and destroy a session
  * each; see rfm_api.cu "Device block cache"; limit RANKFM_B200_CACHE_MB, default 4096): give them back to the driver */
 int rfm_trim_device_cache(void);

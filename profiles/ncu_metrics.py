@@ -21,4 +21,8 @@ for r in rows[2:]:
         if w in hdr:
             k = hdr.index(w)
             print("%-88s %s %s" % (w, r[k], units[k]))
+    for k, h in enumerate(hdr):                      # tensor-core / TMEM / clock metrics, whatever this ncu version calls them
+        hl = h.lower()
+        if h not in want and any(t in hl for t in ("tmem", "tensor", "sm__cycles_elapsed.avg ", "sm__cycles_elapsed.max", "cycles_elapsed.avg.per_second", "pipe_tc", "pipe_uniform")):
+            print("%-88s %s %s" % (h, r[k], units[k]))
     print("-" * 60)

@@ -24,7 +24,7 @@ EXPORTS = [
     "rfm_session_create", "rfm_session_train", "rfm_session_set_epoch_callback", "rfm_session_set_weights", "rfm_session_download",
     "rfm_session_snapshot", "rfm_session_restore", "rfm_session_timer_start", "rfm_session_timer_stop",
     "rfm_session_predict", "rfm_session_recommend", "rfm_session_time_predict", "rfm_session_time_recommend",
-    "rfm_session_trace_enable", "rfm_session_trace_read", "rfm_session_debug_gemm", "rfm_session_recommend_stats", "rfm_session_attach_csr", "rfm_session_similar", "rfm_session_similar_batch", "rfm_session_evaluate", "rfm_session_flush_l2", "rfm_session_launch_count", "rfm_session_exchange_path", "rfm_session_destroy",
+    "rfm_session_trace_enable", "rfm_session_trace_read", "rfm_session_debug_gemm", "rfm_session_recommend_stats", "rfm_session_recommend_retried", "rfm_session_attach_csr", "rfm_session_similar", "rfm_session_similar_batch", "rfm_session_evaluate", "rfm_session_flush_l2", "rfm_session_launch_count", "rfm_session_exchange_path", "rfm_session_destroy",
 ]
 
 
@@ -104,6 +104,7 @@ def lib():
     L.rfm_session_trace_read.argtypes = [vp, vp]
     L.rfm_session_debug_gemm.argtypes = [vp, vp, i64, vp]
     L.rfm_session_recommend_stats.argtypes = [vp, vp, vp]
+    L.rfm_session_recommend_retried.argtypes = [vp, vp]
     L.rfm_session_attach_csr.argtypes = [vp, vp, vp]
     L.rfm_session_similar.argtypes = [vp, i32, i32, i32, vp]
     L.rfm_session_similar_batch.argtypes = [vp, i32, vp, i64, i32, vp]

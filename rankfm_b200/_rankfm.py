@@ -691,6 +691,12 @@ class Session:
         check(_lib.lib().rfm_session_recommend_stats(self._h, C.byref(rows), C.byref(redo)))
         return rows.value, redo.value
 
+    def recommend_retried(self):
+        """rows served a second time with the provable row threshold (the estimated one came out too high for them)"""
+        n = C.c_int64()
+        check(_lib.lib().rfm_session_recommend_retried(self._h, C.byref(n)))
+        return n.value
+
     def flush_l2(self):
         check(_lib.lib().rfm_session_flush_l2(self._h))
 

@@ -244,6 +244,9 @@ struct rfm_session {
     void* d_gemm_B = nullptr; float* d_gemm_bias = nullptr; int32_t* d_gemm_order = nullptr; int gemm_I_pad = 0; bool gemm_valid = false;
     void* scratch[12] = {nullptr}; size_t scratch_bytes[12] = {0};   // grow-only device scratch of the recommend paths
     int64_t tc_rows = 0, tc_redo = 0;   // tensor-core recommend: rows served / rows redone on the exact path (candidate overflow)
+    int64_t tc_retry = 0;               // ... rows redone with the provable threshold (estimated threshold too high)
+    bool tau_spec_off = false;          // the speculative row threshold failed too often on this catalogue: conservative one until the weights change
+    bool tau_spec_ok = false;           // ... or was verified on a batch of this weight state
     std::vector<int64_t> h_indptr;      // host copy of the CSR row pointers (degrees for the recommend planner)
     float* d_flush = nullptr; size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;
@@ -1049,6 +1052,7 @@ static int ensure_gemm_items(rfm_session* s)
     CU(launch_pack_gemm_items(T, Kp, I_pad, s->d_gemm_B, s->d_gemm_bias, s->d_gemm_order, s->st));
     s->launches += 3;
     s->gemm_valid = true;
+    s->tau_spec_off = false; s->tau_spec_ok = false;
     return RFM_OK;
 }
 
@@ -1059,22 +1063,82 @@ static int shortlist_target(rfm_session* s, int32_t u, int32_t n_items, int32_t 
     return need;
 }
 
-// Pass 1 (block bounds -> per-row threshold) may visit only 1/k of the item tiles: the n'-th largest block bound of a
-// SUBSET of the items is still a lower bound of the row's n'-th best score, just a looser one -- pass 2 then collects
-// up to k x n' candidates instead of ~n', which costs a few KB of writes per row, against (1 - 1/k) of a GEMM pass saved.
-// k is the largest of {8, 4, 2, 1} that leaves the subset >= 256 n' items (a smaller sample makes the bound collapse);
-// RANKFM_B200_TAU_STRIDE = 1 | 2 | 4 | 8 caps k.  Which tiles: the catalogue is in descending bias order, so the FIRST 1/k of the tiles hold the
-// items with the largest biases -- where popularity drives the ranking their scores bound the row's best scores almost
-// as tightly as the whole catalogue, and where it does not they are as good as any other sample
-// (RANKFM_B200_TAU_SUBSET=stride takes every k-th tile instead).
+// Pass 1 (block bounds -> per-row threshold) visits only 1/k of the item tiles.  Three ways to choose them and turn the
+// bounds into tau (tau_mode); all of them end in the same verified shortlist, so results never depend on the choice:
+//
+//  0  CONSERVATIVE   tau = the n'-th largest block bound of the subset: a PROVABLE lower bound of the row's n'-th best
+//      score, just a looser one than the whole catalogue would give.  Subset: the catalogue is in descending bias order,
+//      so the FIRST 1/k of the tiles hold the items with the largest biases (RANKFM_B200_TAU_SUBSET=stride takes every
+//      k-th tile instead); k is the largest of {8, 4, 2, 1} that leaves the subset >= 256 n' items, so that even a
+//      catalogue whose biases say nothing about the ranking yields at most ~k n' candidates per row.
+//  2  HEAD (default)  the same provable threshold from a much smaller head subset: the largest k <= 32 that leaves
+//      4 block bounds per wanted candidate.  Pass 2 is bound by the TMEM read of the accumulators (see rfm_gemm.cu), so
+//      pass 1 + threshold are pure overhead: k = 4 -> 32 takes them from 28 % to 5 % of the GEMM + filter time at 262 k
+//      items.  Where item biases carry part of the ranking (any popularity signal) the head's n'-th best bound is as
+//      tight as the whole catalogue's; where they carry none, the threshold is loose, rows collect ~k n' candidates and
+//      overflow their slots (flag 1).  That is detected, not assumed away: flagged rows are served again in mode 0, and
+//      if more than 1/32 of the first batch's rows are flagged the rest of the call -- and the session, until the weights
+//      change -- runs in mode 0.  One verified batch per weight state switches the check (a stream sync) off.
+//  1  ESTIMATED (RANKFM_B200_TAU_MODE=estimate)   every k-th tile (bias order makes that a stratified sample) and tau =
+//      the m-th largest bound with m ~ n'/k plus z-sigma head room (tau_rank in rfm_kernels.h): an ESTIMATE of the n'-th
+//      best score of the whole catalogue, ~2 n' candidates even without any bias signal.  It can come out too high:
+//      shortlist_kernel checks the one thing that matters (did n' candidates reach tau?) and flags the row (2) otherwise,
+//      with the same second serving and switch-off as mode 2.  Measured no better than mode 2 on catalogues with a bias
+//      signal (the sample sees fewer head items than the head subset), hence opt-in.
+//  RANKFM_B200_TAU_MODE=head|safe|estimate, RANKFM_B200_TAU_Z (default 4.5), RANKFM_B200_TAU_STRIDE caps k.
+static int tau_mode_default()
+{
+    const char* e = getenv("RANKFM_B200_TAU_MODE");
+    if (e && !strcmp(e, "estimate")) return 1;
+    if (e && !strcmp(e, "safe")) return 0;
+    return 2;
+}
+static float tau_z()
+{
+    const char* e = getenv("RANKFM_B200_TAU_Z");
+    const float z = e ? (float)atof(e) : 4.5f;
+    return z > 0.f ? z : 1e-3f;
+}
+// block bounds (one per kTauBlock items) pass 1 produces per row
+static int tau_blocks(const Tables& T, int stride)
+{
+    const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN;
+    return (n_tiles + stride - 1) / stride * (BN / kTauBlock);
+}
 static int tau_stride(const Tables& T, int32_t n_items)
 {
     const char* e = getenv("RANKFM_B200_TAU_STRIDE");
     const int cap = e ? std::max(1, atoi(e)) : 8;
     const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN, want = 2 * n_items + 16;
+    const char* m = getenv("RANKFM_B200_TAU_MIN");                   // experiments: items the subset keeps per wanted candidate
+    const int per = m ? std::max(16, atoi(m)) : 256;
     int best = 1;
-    for (int k = 2; k <= std::min(cap, 8); k *= 2)
-        if ((int64_t)((n_tiles + k - 1) / k) * BN >= (int64_t)256 * want) best = k;          // the subset keeps >= 256 n' items
+    for (int k = 2; k <= std::min(cap, 16); k *= 2)
+        if ((int64_t)((n_tiles + k - 1) / k) * BN >= (int64_t)per * want) best = k;          // the subset keeps >= 256 n' items
+    return best;
+}
+// estimated threshold: the m-th largest bound must sit in the sparse upper tail of the sample (<= 1/32 of its blocks),
+// where block maxima and item scores rank alike; `want_max` = the largest n' of the candidate tier
+static int tau_stride_estimate(const Tables& T, int want_max, float z)
+{
+    const char* e = getenv("RANKFM_B200_TAU_STRIDE");
+    const int cap = e ? std::max(1, atoi(e)) : 8;
+    const char* t = getenv("RANKFM_B200_TAU_TAIL");                  // tests: smaller catalogues through the estimate
+    const int tail = t ? std::max(2, atoi(t)) : 32;
+    int best = 1;
+    for (int k = 2; k <= std::min(cap, 16); k *= 2)
+        if ((int64_t)tau_blocks(T, k) >= (int64_t)tail * tau_rank(want_max, k, z)) best = k;
+    return best;
+}
+
+// mode 2: the smallest head subset that still has 4 block bounds per wanted candidate of the tier
+static int tau_stride_head(const Tables& T, int want_max)
+{
+    const char* e = getenv("RANKFM_B200_TAU_STRIDE");
+    const int cap = e ? std::max(1, atoi(e)) : 32;
+    int best = 1;
+    for (int k = 2; k <= std::min(cap, 32); k *= 2)
+        if ((int64_t)tau_blocks(T, k) >= (int64_t)4 * want_max) best = k;
     return best;
 }
 
@@ -1084,40 +1148,58 @@ static bool tau_subset_head()
     return !(e && !strcmp(e, "stride"));
 }
 
-// block bounds (one per kTauBlock items) pass 1 produces per row
-static int tau_blocks(const Tables& T, int stride)
+// rows [0, n) of `src` -> rows `rows[k]` of d_rec
+static int scatter_rows(rfm_session* s, float* d_rec, const float* src, const std::vector<int64_t>& rows, int32_t n_items)
 {
-    const int BN = gemm_block_n(T), n_tiles = (T.I + BN - 1) / BN;
-    return (n_tiles + stride - 1) / stride * (BN / kTauBlock);
+    for (size_t k = 0; k < rows.size(); ++k)
+        CU(cudaMemcpyAsync(d_rec + (size_t)rows[k] * n_items, src + k * n_items, (size_t)n_items * 4, cudaMemcpyDeviceToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return RFM_OK;
 }
 
 // tensor-core path (rfm_gemm.cu): pass 1 block bounds -> per-row threshold -> pass 2 candidates -> shortlist (n' best by
-// bf16 score, exact fp32 re-score) -> top-n
+// bf16 score, exact fp32 re-score) -> top-n.  `top_level`: the caller's rows (counted in tc_rows), not a redo.
 static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
-                        float* d_rec, float* gemm_ms, int cand_cap)
+                        float* d_rec, float* gemm_ms, int cand_cap, int tau_mode, bool top_level = true)
 {
     const Tables& T = s->T;
     if (n_users <= 0) return RFM_OK;
     int rc = ensure_gemm_items(s);
     if (rc) return rc;
+    const float z = tau_z();
     const int Kp = gemm_kp(T), MT = gemm_m_tile(T), SPS = gemm_slots_per_split(T), I_pad = s->gemm_I_pad;
-    const int stride = tau_stride(T, n_items), n_sub1 = tau_blocks(T, stride), n_tiles1 = n_sub1 / (gemm_block_n(T) / kTauBlock);
-    // candidate entries per row: ~1-2 n' with a full pass 1, ~stride x n' with a strided one (n' <= kCandCap)
-    // (the shortlist kernel stages a row's candidates in shared memory: at most 16384 entries = 128 KB)
-    const int width = std::min(16384, stride == 1 ? 8 * cand_cap : 4 * cand_cap * stride);
+    int stride = tau_stride(T, n_items);
+    if (tau_mode == 1) {
+        const int k = tau_stride_estimate(T, cand_cap, z);
+        if (k > 1) stride = k; else tau_mode = 0;                    // nothing to estimate from a full pass 1
+    } else if (tau_mode == 2) {
+        const int k = tau_stride_head(T, cand_cap);
+        if (k > stride) stride = k; else tau_mode = 0;               // the conservative subset is already that small
+    }
+    const int n_sub1 = tau_blocks(T, stride), n_tiles1 = n_sub1 / (gemm_block_n(T) / kTauBlock);
+    // candidate entries per row (the shortlist kernel stages a row's candidates in shared memory: at most 16384 entries =
+    // 128 KB): provable threshold ~1-2 n' with a full pass 1, ~stride x n' with a partial one; estimated threshold ~k m
+    // expected, 6x head room (bias-dominated rows collect more: one bound per 8-item block hides up to 7 items)
+    int width = std::min(16384, stride == 1 ? 8 * cand_cap : 4 * cand_cap * stride);
+    if (tau_mode) {                                                  // speculative modes: sized for what they expect, not for the worst case
+        const int expect = tau_mode == 1 ? 6 * stride * tau_rank(cand_cap, stride, z) : 12 * cand_cap;
+        int w = 2048;
+        while (w < 16384 && w < expect) w *= 2;
+        width = w;
+    }
     // one wave: at most n_sm CTAs (one resident per SM), user tiles x item splits; >= 2 splits keep a partial last batch balanced
     int64_t max_rows = (int64_t)std::max(1, s->n_sm / 2) * MT;
     max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)4 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
     const int64_t rows_alloc = std::min<int64_t>(max_rows, (n_users + MT - 1) / MT * MT);
     const int split_cap = std::max(1, std::min(n_tiles1, width / (cand_cap * SPS)));
     // The user batches run back to back on the session's stream; targets of all batches are uploaded once and the redo
-    // flags of all rows are read once, so the loop never synchronises with the host.  (Running the shortlist kernel of
+    // flags of all rows are read once, so the loop never synchronises with the host (except once after the first batch of
+    // an estimated-threshold call, to see whether the estimate works on this catalogue).  (Running the shortlist kernel of
     // batch b on a second stream next to the GEMM of batch b+1 was measured and bought nothing: a GEMM CTA holds ~200 KB
     // of an SM's shared memory, so shortlist blocks cannot co-reside with it and only delay the next wave -- GEMM + filter
     // 6.2 -> 8.3 ms per 65,536 users for the same 9.0 ms total.)
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr;
     float *d_rowmax = nullptr, *d_tau = nullptr; int* d_flag = nullptr;
-    DevBuf<float> d_fix; DevBuf<int32_t> d_fix_users;               // rows redone on the exact path
     const int64_t n_batches = (n_users + rows_alloc - 1) / rows_alloc;
     struct Events : std::vector<cudaEvent_t> { ~Events() { for (auto e : *this) cudaEventDestroy(e); } } ev;    // timing pairs (GEMM + filter of each batch)
     if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
@@ -1134,6 +1216,8 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
             ntgt[(size_t)k] = shortlist_target(s, k < n_users ? h_users[k] : -1, n_items, filter_previous);
         }
     CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), ntgt.size() * 4, cudaMemcpyHostToDevice, s->st));
+    std::vector<int> flag_h((size_t)n_users);
+    int64_t served = n_users;                                        // rows this invocation's loop handles
     for (int64_t bi = 0; bi < n_batches; ++bi) {
         const int64_t off = bi * rows_alloc;
         const int nb = (int)std::min<int64_t>(rows_alloc, n_users - off);
@@ -1150,9 +1234,10 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
             ev.push_back(ta); ev.push_back(tb);
             CU(cudaEventRecord(ta, s->st));
         }
-        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, tau_subset_head() ? -stride : stride, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
+        const int subset = (tau_mode == 1 || (tau_mode == 0 && !tau_subset_head())) ? stride : -stride;
+        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, subset, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e));
-        e = launch_row_threshold(d_rowmax, M_pad, n_sub1, tgt, d_tau, s->st);
+        e = launch_row_threshold(d_rowmax, M_pad, n_sub1, tgt, d_tau, tau_mode == 1 ? stride : 1, tau_mode == 1 ? z : 0.f, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "row_threshold launch failed: %s", cudaGetErrorString(e));
         e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, cand, cnt, d_tau, cap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e));
@@ -1161,26 +1246,59 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
                              n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, 2 * cand_cap, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
         s->launches += 5;
+        if (tau_mode && bi == 0 && n_batches > 1 && !s->tau_spec_ok) {      // does the speculation work on this catalogue?
+            CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->st));
+            CU(cudaStreamSynchronize(s->st));
+            int64_t missed = 0;
+            for (int r = 0; r < nb; ++r) missed += flag_h[(size_t)r] != 0;
+            if (missed * 32 > nb) { s->tau_spec_off = true; served = off + nb; break; }
+            s->tau_spec_ok = true;
+        }
     }
     CU(cudaStreamSynchronize(s->st));
     if (gemm_ms)
         for (size_t k = 0; k + 1 < ev.size(); k += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); *gemm_ms += ms; }
-    // rows whose candidates overflowed (pathological ties / clustered scores) are redone on the exact path
-    std::vector<int> flag_h((size_t)n_users);
-    CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)n_users * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)served * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
-    std::vector<int32_t> redo_users; std::vector<int64_t> redo_rows;
-    for (int64_t r = 0; r < n_users; ++r)
-        if (flag_h[(size_t)r]) { redo_users.push_back(h_users[r]); redo_rows.push_back(r); }
-    s->tc_rows += n_users; s->tc_redo += (int64_t)redo_users.size();
+    // flag 1: candidates overflowed (pathological ties / clustered scores) or the bf16 guard could not prove the shortlist;
+    // flag 2: the estimated threshold came out too high.  Provable threshold: 1 -> exact path (2 cannot happen).  Estimated
+    // threshold: both -> once more with the provable threshold and its wider candidate buffers, which sends what it
+    // cannot serve either to the exact path.
+    std::vector<int32_t> redo_users, retry_users; std::vector<int64_t> redo_rows, retry_rows;
+    for (int64_t r = 0; r < served; ++r) {
+        const int f = flag_h[(size_t)r];
+        if (f == 0) continue;
+        if (tau_mode || f == 2) { retry_users.push_back(h_users[r]); retry_rows.push_back(r); }
+        else { redo_users.push_back(h_users[r]); redo_rows.push_back(r); }
+    }
+    if (top_level) s->tc_rows += n_users;
+    s->tc_redo += (int64_t)redo_users.size(); s->tc_retry += (int64_t)retry_users.size();
+    if (tau_mode && n_batches == 1 && top_level) {
+        if ((int64_t)retry_users.size() * 32 > n_users) { s->tau_spec_off = true; s->tau_spec_ok = false; }
+        else if (n_users >= 1024) s->tau_spec_ok = true;
+    }
+    if (!tau_mode && !retry_users.empty()) return fail(RFM_ERR_CUDA, "recommend: %zu rows fell short of a provable threshold (internal error)", retry_users.size());
+    // (the scratch buffers above are reused by the calls below: everything this invocation needed from them is on the host)
+    if (served < n_users) {                                          // the estimate was switched off after the first batch
+        rc = recommend_tc(s, d_users + served, h_users + served, n_users - served, n_items, filter_previous, d_rec + (size_t)served * n_items, gemm_ms,
+                          cand_cap, 0, false);
+        if (rc) return rc;
+    }
+    if (!retry_users.empty()) {
+        DevBuf<float> d_fix; DevBuf<int32_t> d_fix_users;
+        if ((rc = d_fix_users.alloc(retry_users.size()))) return rc;
+        if ((rc = d_fix.alloc(retry_users.size() * n_items))) return rc;
+        CU(cudaMemcpyAsync(d_fix_users, retry_users.data(), retry_users.size() * 4, cudaMemcpyHostToDevice, s->st));
+        if ((rc = recommend_tc(s, d_fix_users, retry_users.data(), (int64_t)retry_users.size(), n_items, filter_previous, d_fix, gemm_ms, cand_cap, 0, false))) return rc;
+        if ((rc = scatter_rows(s, d_rec, d_fix, retry_rows, n_items))) return rc;
+    }
     if (!redo_users.empty()) {
+        DevBuf<float> d_fix; DevBuf<int32_t> d_fix_users;
         if ((rc = d_fix_users.alloc(redo_users.size()))) return rc;
         if ((rc = d_fix.alloc(redo_users.size() * n_items))) return rc;
         CU(cudaMemcpyAsync(d_fix_users, redo_users.data(), redo_users.size() * 4, cudaMemcpyHostToDevice, s->st));
         if ((rc = recommend_exact(s, d_fix_users, (int64_t)redo_users.size(), n_items, filter_previous, d_fix, nullptr))) return rc;
-        for (size_t k = 0; k < redo_rows.size(); ++k)
-            CU(cudaMemcpyAsync(d_rec + (size_t)redo_rows[k] * n_items, d_fix + k * n_items, (size_t)n_items * 4, cudaMemcpyDeviceToDevice, s->st));
-        CU(cudaStreamSynchronize(s->st));
+        if ((rc = scatter_rows(s, d_rec, d_fix, redo_rows, n_items))) return rc;
     }
     return RFM_OK;
 }
@@ -1227,10 +1345,11 @@ static int recommend_dev(rfm_session* s, const int32_t* d_users, const int32_t* 
                          int32_t filter_previous, float* d_rec, float* gemm_ms)
 {
     if (gemm_ms) *gemm_ms = 0.f;
-    int rc = recommend_tc(s, d_users, h_users, plan.n_narrow, n_items, filter_previous, d_rec, gemm_ms, kCandCap);
+    const int tau_mode = s->tau_spec_off ? 0 : tau_mode_default();
+    int rc = recommend_tc(s, d_users, h_users, plan.n_narrow, n_items, filter_previous, d_rec, gemm_ms, kCandCap, tau_mode);
     if (rc) return rc;
     const int64_t o1 = plan.n_narrow, o2 = plan.n_narrow + plan.n_wide;
-    rc = recommend_tc(s, d_users + o1, h_users + o1, plan.n_wide, n_items, filter_previous, d_rec + (size_t)o1 * n_items, gemm_ms, kCandCapWide);
+    rc = recommend_tc(s, d_users + o1, h_users + o1, plan.n_wide, n_items, filter_previous, d_rec + (size_t)o1 * n_items, gemm_ms, kCandCapWide, tau_mode);
     if (rc) return rc;
     return recommend_exact(s, d_users + o2, n_users - o2, n_items, filter_previous, d_rec + (size_t)o2 * n_items, gemm_ms);
 }
@@ -1398,6 +1517,13 @@ extern "C" int rfm_session_trace_read(rfm_session* s, int32_t* out)
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(out, s->d_trace, (size_t)s->N * 8, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
+    return RFM_OK;
+}
+
+extern "C" int rfm_session_recommend_retried(rfm_session* s, int64_t* tc_retried)
+{
+    if (!s || !tc_retried) return fail(RFM_ERR_ARG, "NULL argument");
+    *tc_retried = s->tc_retry;
     return RFM_OK;
 }
 

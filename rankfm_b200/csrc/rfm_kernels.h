@@ -81,7 +81,21 @@ cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, 
 cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st);
 cudaError_t launch_score_filter(const Tables& T, int mode, const void* A, const void* B, const float* bias, int n_users, int M_pad, int I_pad, int n_splits,
                                 int tile_stride, float2* cand, int* cand_cnt, const float* tau, int cap, float* rowmax, float* S, cudaStream_t st);
-cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, cudaStream_t st);
+// Rank of the block bound that becomes the row threshold when pass 1 saw a 1-in-k sample of the item tiles.
+//   z == 0, k == 1: the n'-th largest bound -- a PROVABLE lower bound of the row's n'-th best score (the "safe" threshold).
+//   z  > 0:         the m-th largest bound of the sample, m ~ n'/k + z-sigma head room: an ESTIMATE of the n'-th best score
+//                   of the whole catalogue.  With m sample items above tau the catalogue holds ~ k m of them, standard
+//                   deviation ~ k sqrt(m) (negative binomial); m solves k m - z k sqrt(m) = n'.  The estimate can be
+//                   too high; shortlist_kernel VERIFIES it (>= n' candidates reached tau) and flags the row otherwise,
+//                   so results never depend on it.
+__host__ __device__ inline int tau_rank(int want, int k, float z)
+{
+    if (k <= 1 || !(z > 0.f)) return want;
+    const float r = 0.5f * (z + sqrtf(z * z + 4.f * (float)want / (float)k));
+    const int m = (int)ceilf(r * r) + 1;
+    return m < want ? m : want;
+}
+cudaError_t launch_row_threshold(const float* rowmax, int n_rows, int n_blocks, const int* n_target, float* tau, int sample_k, float z, cudaStream_t st);
 constexpr int kTauBlock = 8;                   // items per pass-1 block bound
 constexpr int kShortWidth = 512;               // shortlist entries per row, narrow tier (n' <= 256 plus ties at the cut)
 constexpr int kShortWidthWide = 2048;          // wide tier (n' <= 1024: users with long histories under filter_previous)

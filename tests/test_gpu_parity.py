@@ -688,6 +688,93 @@ def test_recommend_tensor_core_eighth_of_catalogue(gpu_lib, monkeypatch):
         assert not set(row.astype(int).tolist()) & set(ui[int(u)].tolist())
 
 
+@pytest.mark.parametrize("mode,z,stride,ew", [("head", "4.5", "32", "8"), ("head", "4.5", "32", "16"), ("estimate", "4.5", "8", "16"), ("estimate", "4.5", "16", "8"),
+                                              ("estimate", "4.5", "2", "8"), ("estimate", "0.001", "8", "16"), ("estimate", "0.001", "4", "8")])
+@pytest.mark.parametrize("filt", [False, True])
+def test_recommend_speculative_thresholds_equal_the_conservative_one(gpu_lib, mode, z, stride, ew, filt, monkeypatch):
+    """The row threshold from a small head subset ("head", the default) or estimated from a 1-in-k sample of the item
+    tiles ("estimate") must never change a result (rfm_api.cu, tau_mode): rows it does not serve are detected by the
+    shortlist kernel and served again with the conservative threshold.  z = 0.001 removes the estimate's head room, so
+    most rows take that way.  Also covers 8 vs 16 epilogue warps (different candidate layouts, identical rows)."""
+    U = 600
+    monkeypatch.setenv("RANKFM_B200_TAU_TAIL", "4")                 # lets a 130 k-item catalogue through the estimate
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    sess, ui = _sparse_scoring_session(U, 130000, 24, seed=5)
+    users = np.arange(U, dtype=np.float32)
+    users[17] = np.nan
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "safe")
+    safe = sess.recommend(users, 20, filt)
+    assert sess.recommend_retried() == 0
+    monkeypatch.setenv("RANKFM_B200_GEMM_EW", ew)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", mode)
+    monkeypatch.setenv("RANKFM_B200_TAU_Z", z)
+    monkeypatch.setenv("RANKFM_B200_TAU_STRIDE", stride)
+    spec = sess.recommend(users, 20, filt)
+    retried = sess.recommend_retried()
+    tc_rows, tc_redone = sess.recommend_stats()
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "exact")
+    exact = sess.recommend(users, 20, filt)
+    sess.close()
+    assert np.array_equal(spec, safe, equal_nan=True)
+    assert tc_rows == 2 * U and tc_redone <= U // 50, (tc_rows, tc_redone)
+    if z == "0.001":
+        assert retried >= U // 10, retried                           # the detection + second serving was exercised
+    else:
+        assert retried <= U // 20, retried
+    assert topk_overlap(spec, exact) >= 0.99
+    assert np.mean(spec[~np.isnan(exact)] == exact[~np.isnan(exact)]) >= 0.99
+
+
+def test_recommend_head_threshold_falls_back_on_a_catalogue_without_bias_signal(gpu_lib, monkeypatch):
+    """every item bias equal: the head subset is an arbitrary 1/16 of the catalogue, its threshold is loose, rows collect
+    ~16 n' candidates and slots overflow -- those rows are served again conservatively, the results are the conservative
+    ones, and once more than 1/32 of a call's rows needed that the session stops speculating"""
+    U = 600
+
+    def mutate(w):
+        w['w_i'][:] = 0.25
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    sess, ui = _sparse_scoring_session(U, 130000, 24, seed=6, mutate=mutate)
+    users = np.arange(U, dtype=np.float32)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "safe")
+    safe = sess.recommend(users, 100, False)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "head")
+    head = sess.recommend(users, 100, False)
+    first = sess.recommend_retried()
+    again = sess.recommend(users, 100, False)
+    second = sess.recommend_retried()
+    tc_rows, tc_redone = sess.recommend_stats()
+    sess.close()
+    assert np.array_equal(head, safe) and np.array_equal(again, safe)
+    assert first > 0, first
+    if first * 32 > U:
+        assert second == first                                       # the second call did not speculate
+    assert tc_rows == 3 * U and tc_redone <= U // 20, (tc_rows, tc_redone)
+
+
+def test_recommend_estimated_threshold_is_switched_off_when_it_fails(gpu_lib, monkeypatch):
+    """several batches, estimate without head room: the first batch shows that too many rows fall short, the remaining
+    batches (and the session's next call) use the conservative threshold; every row equals the conservative result"""
+    U = 45000
+    monkeypatch.setenv("RANKFM_B200_TAU_TAIL", "2")
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    sess, ui = _sparse_scoring_session(U, 33000, 16, seed=12)
+    users = np.arange(U, dtype=np.float32)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "safe")
+    safe = sess.recommend(users, 10, True)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "estimate")
+    monkeypatch.setenv("RANKFM_B200_TAU_Z", "0.001")
+    est = sess.recommend(users, 10, True)
+    first = sess.recommend_retried()
+    again = sess.recommend(users[:5000], 10, True)
+    second = sess.recommend_retried()
+    sess.close()
+    assert np.array_equal(est, safe)
+    assert np.array_equal(again, safe[:5000])
+    assert 0 < first < 30000, first                                  # only the first batch (<= 18,944 rows) was served twice
+    assert second == first                                           # the next call started with the provable threshold
+
+
 def test_recommend_tensor_core_many_batches(gpu_lib, monkeypatch):
     """more users than one wave of CTAs holds: several batches back to back (targets uploaded once, redo flags read once);
     rows from every batch must match the exact path"""
