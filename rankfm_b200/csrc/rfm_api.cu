@@ -1382,11 +1382,22 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     if ((rc = d_rec.alloc((size_t)n_users * n_items))) return rc;
     CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
     if ((rc = recommend_dev(s, d_users, hp.data(), plan, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
-    std::vector<float> tmp((size_t)n_users * n_items);
-    CU(cudaMemcpyAsync(tmp.data(), d_rec, (size_t)n_users * n_items * 4, cudaMemcpyDeviceToHost, s->st));
+    // back to the caller's order on the device (nothing to do when every user took the same path), then ONE copy straight
+    // into the caller's buffer: a host staging vector + row-wise memcpy cost more than the GPU work at 1 M users x 100
+    bool identity = true;
+    for (int64_t k = 0; k < n_users && identity; ++k) identity = order[(size_t)k] == k;
+    const float* d_final = d_rec;
+    DevBuf<float> d_perm; DevBuf<int64_t> d_order;
+    if (!identity) {
+        if ((rc = d_perm.alloc((size_t)n_users * n_items))) return rc;
+        if ((rc = d_order.alloc((size_t)n_users))) return rc;
+        CU(cudaMemcpyAsync(d_order, order.data(), (size_t)n_users * 8, cudaMemcpyHostToDevice, s->st));
+        CU(launch_scatter_rows(d_rec, d_order, n_users, n_items, d_perm, s->st));
+        s->launches += 1;
+        d_final = d_perm;
+    }
+    CU(cudaMemcpyAsync(rec_items, d_final, (size_t)n_users * n_items * 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
-    for (int64_t k = 0; k < n_users; ++k)
-        memcpy(rec_items + (size_t)order[(size_t)k] * n_items, tmp.data() + (size_t)k * n_items, (size_t)n_items * 4);
     return RFM_OK;
 }
 

@@ -104,6 +104,7 @@ cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users,
                              int* flag, const float* tau, int I_pad, int short_width, cudaStream_t st);
 cudaError_t launch_eval_topk(const float* rec, const int64_t* order, int n_users, int k, const int64_t* test_indptr, const int32_t* test_items,
                              const int32_t* n_test, double* out5, uint8_t* hits_out, cudaStream_t st);
+cudaError_t launch_scatter_rows(const float* src, const int64_t* order, long long n_rows, int n_items, float* dst, cudaStream_t st);
 cudaError_t launch_latent_scores(const Tables& T, int which, int index, float* qvec, float* S, cudaStream_t st);
 int sgd_epoch_blocks_per_sm(const TrainParams& p);
 

@@ -400,4 +400,20 @@ cudaError_t launch_eval_topk(const float* rec, const int64_t* order, int n_users
     return cudaGetLastError();
 }
 
+// rows of `src` (in the planner's order: narrow tier, wide tier, exact path) -> rows order[k] of `dst` (the caller's order)
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ order, long long n_rows, int n_items, float* __restrict__ dst)
+{
+    const long long total = n_rows * n_items;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long k = e / n_items;
+        dst[(size_t)__ldg(order + k) * n_items + (e - k * n_items)] = src[e];
+    }
+}
+
+cudaError_t launch_scatter_rows(const float* src, const int64_t* order, long long n_rows, int n_items, float* dst, cudaStream_t st)
+{
+    scatter_rows_kernel<<<148 * 8, 256, 0, st>>>(src, order, n_rows, n_items, dst);
+    return cudaGetLastError();
+}
+
 }  // namespace rfm
