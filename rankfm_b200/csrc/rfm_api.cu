@@ -1157,10 +1157,20 @@ static int scatter_rows(rfm_session* s, float* d_rec, const float* src, const st
     return RFM_OK;
 }
 
+// Where a top-level recommend_tc call may put finished rows while later batches still compute: the caller's host buffer,
+// filled batch by batch on a copy stream (a 1 M x 100 result is 400 MB: copied after the last kernel it cost 110 ms on
+// top of 290 ms of GPU work).  Rows rewritten afterwards (second servings, exact path) are listed in `dirty`.
+struct HostSink {
+    float* out = nullptr;               // [n_users, n_items], rows in the order of the call's device rows
+    cudaStream_t cs = nullptr;
+    std::vector<int64_t> dirty;
+    bool whole = false;                 // nothing was copied row-exactly: the caller copies everything
+};
+
 // tensor-core path (rfm_gemm.cu): pass 1 block bounds -> per-row threshold -> pass 2 candidates -> shortlist (n' best by
 // bf16 score, exact fp32 re-score) -> top-n.  `top_level`: the caller's rows (counted in tc_rows), not a redo.
 static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h_users, int64_t n_users, int32_t n_items, int32_t filter_previous,
-                        float* d_rec, float* gemm_ms, int cand_cap, int tau_mode, bool top_level = true)
+                        float* d_rec, float* gemm_ms, int cand_cap, int tau_mode, bool top_level = true, HostSink* sink = nullptr)
 {
     const Tables& T = s->T;
     if (n_users <= 0) return RFM_OK;
@@ -1217,6 +1227,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         }
     CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), ntgt.size() * 4, cudaMemcpyHostToDevice, s->st));
     std::vector<int> flag_h((size_t)n_users);
+    struct PooledEvents : std::vector<cudaEvent_t> { int dev; explicit PooledEvents(int d) : dev(d) {} ~PooledEvents() { pool_return(dev, nullptr, *this); } } batch_done(s->device);
     int64_t served = n_users;                                        // rows this invocation's loop handles
     for (int64_t bi = 0; bi < n_batches; ++bi) {
         const int64_t off = bi * rows_alloc;
@@ -1246,6 +1257,12 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
                              n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, 2 * cand_cap, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
         s->launches += 5;
+        if (sink) {
+            cudaEvent_t done;
+            CU(pool_event(s->device, &done));
+            batch_done.push_back(done);                              // back to the pool when this call returns
+            CU(cudaEventRecord(done, s->st));
+        }
         if (tau_mode && bi == 0 && n_batches > 1 && !s->tau_spec_ok) {      // does the speculation work on this catalogue?
             CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->st));
             CU(cudaStreamSynchronize(s->st));
@@ -1254,6 +1271,15 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
             if (missed * 32 > nb) { s->tau_spec_off = true; served = off + nb; break; }
             s->tau_spec_ok = true;
         }
+    }
+    if (sink) {                                                      // every batch is enqueued: drain finished ones while the rest compute
+        for (size_t bi = 0; bi < batch_done.size(); ++bi) {
+            const int64_t off = (int64_t)bi * rows_alloc;
+            const int64_t nb = std::min<int64_t>(rows_alloc, n_users - off);
+            CU(cudaStreamWaitEvent(sink->cs, batch_done[bi], 0));
+            CU(cudaMemcpyAsync(sink->out + (size_t)off * n_items, d_rec + (size_t)off * n_items, (size_t)nb * n_items * 4, cudaMemcpyDeviceToHost, sink->cs));
+        }
+        CU(cudaStreamSynchronize(sink->cs));
     }
     CU(cudaStreamSynchronize(s->st));
     if (gemm_ms)
@@ -1273,6 +1299,11 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     }
     if (top_level) s->tc_rows += n_users;
     s->tc_redo += (int64_t)redo_users.size(); s->tc_retry += (int64_t)retry_users.size();
+    if (sink) {
+        if (served < n_users) sink->whole = true;
+        sink->dirty.insert(sink->dirty.end(), retry_rows.begin(), retry_rows.end());
+        sink->dirty.insert(sink->dirty.end(), redo_rows.begin(), redo_rows.end());
+    }
     if (tau_mode && n_batches == 1 && top_level) {
         if ((int64_t)retry_users.size() * 32 > n_users) { s->tau_spec_off = true; s->tau_spec_ok = false; }
         else if (n_users >= 1024) s->tau_spec_ok = true;
@@ -1342,11 +1373,11 @@ static RecommendPlan recommend_plan(rfm_session* s, const std::vector<int32_t>& 
 }
 
 static int recommend_dev(rfm_session* s, const int32_t* d_users, const int32_t* h_users, const RecommendPlan& plan, int64_t n_users, int32_t n_items,
-                         int32_t filter_previous, float* d_rec, float* gemm_ms)
+                         int32_t filter_previous, float* d_rec, float* gemm_ms, HostSink* sink = nullptr)
 {
     if (gemm_ms) *gemm_ms = 0.f;
     const int tau_mode = s->tau_spec_off ? 0 : tau_mode_default();
-    int rc = recommend_tc(s, d_users, h_users, plan.n_narrow, n_items, filter_previous, d_rec, gemm_ms, kCandCap, tau_mode);
+    int rc = recommend_tc(s, d_users, h_users, plan.n_narrow, n_items, filter_previous, d_rec, gemm_ms, kCandCap, tau_mode, true, sink);
     if (rc) return rc;
     const int64_t o1 = plan.n_narrow, o2 = plan.n_narrow + plan.n_wide;
     rc = recommend_tc(s, d_users + o1, h_users + o1, plan.n_wide, n_items, filter_previous, d_rec + (size_t)o1 * n_items, gemm_ms, kCandCapWide, tau_mode);
@@ -1381,7 +1412,26 @@ extern "C" int rfm_session_recommend(rfm_session* s, const float* users, int64_t
     if ((rc = d_users.alloc((size_t)n_users))) return rc;
     if ((rc = d_rec.alloc((size_t)n_users * n_items))) return rc;
     CU(cudaMemcpyAsync(d_users, hp.data(), (size_t)n_users * 4, cudaMemcpyHostToDevice, s->st));
-    if ((rc = recommend_dev(s, d_users, hp.data(), plan, n_users, n_items, filter_previous, d_rec, nullptr))) return rc;
+    // the common large call -- every user in the narrow tensor-core tier, hence already in the caller's order -- streams
+    // finished batches into the caller's buffer while later ones compute
+    HostSink sink;
+    // (from 64 MB of results: below that one copy after the last kernel measured no slower; RANKFM_B200_STREAM_MIN = floats)
+    const char* smin = getenv("RANKFM_B200_STREAM_MIN");
+    const bool stream_out = plan.n_narrow == n_users && (int64_t)n_users * n_items >= (smin ? atoll(smin) : ((int64_t)1 << 24));
+    if (stream_out) { sink.out = rec_items; CU(pool_stream(s->device, &sink.cs)); }
+    rc = recommend_dev(s, d_users, hp.data(), plan, n_users, n_items, filter_previous, d_rec, nullptr, stream_out ? &sink : nullptr);
+    if (stream_out) {
+        std::vector<cudaEvent_t> none;
+        cudaStreamSynchronize(sink.cs);
+        pool_return(s->device, sink.cs, none);
+    }
+    if (rc) return rc;
+    if (stream_out && !sink.whole && (int64_t)sink.dirty.size() * 64 <= n_users) {      // few rewritten rows: copy just those again
+        for (int64_t r : sink.dirty)
+            CU(cudaMemcpyAsync(rec_items + (size_t)r * n_items, d_rec + (size_t)r * n_items, (size_t)n_items * 4, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        return RFM_OK;
+    }
     // back to the caller's order on the device (nothing to do when every user took the same path), then ONE copy straight
     // into the caller's buffer: a host staging vector + row-wise memcpy cost more than the GPU work at 1 M users x 100
     bool identity = true;

@@ -775,6 +775,38 @@ def test_recommend_estimated_threshold_is_switched_off_when_it_fails(gpu_lib, mo
     assert second == first                                           # the next call started with the provable threshold
 
 
+def test_recommend_streams_finished_batches_to_the_host(gpu_lib, monkeypatch):
+    """a large all-tensor-core call copies each finished batch into the caller's buffer while later batches compute
+    (rfm_api.cu HostSink); rows rewritten afterwards (second servings) are copied again.  Same rows as small calls, which
+    take the single-copy path."""
+    U, n = 45000, 100
+    monkeypatch.setenv("RANKFM_B200_STREAM_MIN", str(1 << 20))      # default: from 16 M result floats
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    monkeypatch.setenv("RANKFM_B200_TAU_TAIL", "2")
+    sess, ui = _sparse_scoring_session(U, 33000, 16, seed=13)
+    users = np.arange(U, dtype=np.float32)
+    users[[7, 20000, 44999]] = np.nan
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "safe")
+    parts = np.concatenate([sess.recommend(users[a:a + 9000], n, True) for a in range(0, U, 9000)])
+    full = sess.recommend(users, n, True)
+    assert np.array_equal(full, parts, equal_nan=True)
+    # estimated threshold, verified once with head room, then with less: the first-batch check is off, some rows of every
+    # batch fall short, are served again after the batch copies and must be copied again (a few: row by row; many: everything)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "estimate")
+    monkeypatch.setenv("RANKFM_B200_TAU_Z", "6")
+    assert np.array_equal(sess.recommend(users, n, True), parts, equal_nan=True)
+    before = sess.recommend_retried()
+    seen = []
+    for z in ("2.0", "1.0", "0.001"):
+        monkeypatch.setenv("RANKFM_B200_TAU_Z", z)
+        again = sess.recommend(users, n, True)
+        seen.append(sess.recommend_retried() - before)
+        before = sess.recommend_retried()
+        assert np.array_equal(again, parts, equal_nan=True), z
+    sess.close()
+    assert seen[-1] > U // 10, seen
+
+
 def test_recommend_tensor_core_many_batches(gpu_lib, monkeypatch):
     """more users than one wave of CTAs holds: several batches back to back (targets uploaded once, redo flags read once);
     rows from every batch must match the exact path"""
