@@ -1197,6 +1197,12 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         while (w < 16384 && w < expect) w *= 2;
         width = w;
     }
+    // The shortlist kernel stages a row's candidates in shared memory; sized for every slot's capacity that is 32 KB per block at
+    // width 4096 and caps it at 5 blocks per SM.  The speculative modes stage only what they expect -- 2,048 entries in the
+    // narrow tier, 16 KB, so that the kernel's 6 blocks per SM fit (rows with more take the second serving like an
+    // overflowing slot).
+    const char* stg = getenv("RANKFM_B200_TC_STAGE");
+    const int stage_cap = tau_mode ? (stg ? std::max(256, atoi(stg)) : std::min(width, std::max(2048, 4 * cand_cap))) : 0;
     // one wave: at most n_sm CTAs (one resident per SM), user tiles x item splits; >= 2 splits keep a partial last batch balanced
     int64_t max_rows = (int64_t)std::max(1, s->n_sm / 2) * MT;
     max_rows = std::min<int64_t>(max_rows, std::max<int64_t>(MT, (((int64_t)4 << 30) / ((int64_t)n_sub1 * 4)) / MT * MT));
@@ -1254,7 +1260,7 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e));
         if (gemm_ms) CU(cudaEventRecord(ev.back(), s->st));
         e = launch_shortlist(T, d_users + off, nb, cand, cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
-                             n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, 2 * cand_cap, s->st);
+                             n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, 2 * cand_cap, stage_cap, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
         s->launches += 5;
         if (sink) {

@@ -454,17 +454,24 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kShortThreads = 256;
 
+// Blocks per SM: the kernel is latency-bound (block-wide barriers between the select passes, the compaction and the sort
+// stages), so residency is what it needs.  Unconstrained it took 64 registers = 4 blocks per SM; the common variant (no side
+// features, one quad per lane, narrow tier) fits 40 registers (8 B of spills) = 6 blocks per SM: -8 % on a whole recommend
+// call (round 2 A/B on one box: 8.10 -> 7.42 ms per 65,536 users together with the 2,048-entry staging below).
+#ifndef RFM_SHORT_MINB
+#define RFM_SHORT_MINB 6
+#endif
 template <int G, int QPL, bool FEAT, int SW>
-__global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T, const int32_t* __restrict__ users, const float2* __restrict__ cand,
+__global__ void __launch_bounds__(kShortThreads, (!FEAT && QPL == 1 && SW <= 512) ? RFM_SHORT_MINB : 4) shortlist_kernel(const Tables T, const int32_t* __restrict__ users, const float2* __restrict__ cand,
                                                                   const int* __restrict__ cand_cnt, int slots, int cap, const float* __restrict__ bias,
                                                                   const int32_t* __restrict__ order, const int* __restrict__ n_target,
                                                                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                                                   int filter_previous, int n_items, float* __restrict__ rec, int* __restrict__ flag,
-                                                                  const float* __restrict__ tau, int I_pad, int guard)
+                                                                  const float* __restrict__ tau, int I_pad, int guard, int stage_cap)
 {
     extern __shared__ __align__(16) unsigned char short_smem[];
     __shared__ float s_norm2;
-    uint2* ent = reinterpret_cast<uint2*>(short_smem);               // [slots * cap] (ordered key of the bf16 score, position)
+    uint2* ent = reinterpret_cast<uint2*>(short_smem);               // [min(slots * cap, stage_cap)] (ordered key of the bf16 score, position)
     __shared__ int32_t kept[SW];                            // item ids of the shortlist, in position order
     __shared__ unsigned long long sel[SW];                  // (ordered key of the exact score << 32) | item index
     __shared__ uint32_t hist[256];
@@ -484,7 +491,7 @@ __global__ void __launch_bounds__(kShortThreads) shortlist_kernel(const Tables T
     }
     __syncthreads();
     const int total = s_off[slots], want = n_target[b];
-    if (!known || s_over) {                                           // overflow: the caller redoes the row on the exact path
+    if (!known || s_over || total > stage_cap) {                      // overflow (of a slot, or of this kernel's staging): the caller redoes the row
         if (!known) for (int k = tid; k < n_items; k += kShortThreads) out[k] = __int_as_float(0x7fc00000);
         if (tid == 0) flag[b] = known ? 1 : 0;
         return;
@@ -640,17 +647,17 @@ static bool shortlist_guard()
 template <int G, int QPL, int SW>
 static cudaError_t shortlist_launch(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                                     const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                                    int* flag, const float* tau, int I_pad, int guard, size_t smem, cudaStream_t st)
+                                    int* flag, const float* tau, int I_pad, int guard, int stage_cap, size_t smem, cudaStream_t st)
 {
     cudaError_t e;
     if (T.x_uf_any || T.x_if_any) {
         e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, true, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, true, SW><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
+        shortlist_kernel<G, QPL, true, SW><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, stage_cap);
     } else {
         e = cudaFuncSetAttribute(shortlist_kernel<G, QPL, false, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        shortlist_kernel<G, QPL, false, SW><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard);
+        shortlist_kernel<G, QPL, false, SW><<<n_users, kShortThreads, smem, st>>>(T, users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, stage_cap);
     }
     return cudaGetLastError();
 }
@@ -658,23 +665,24 @@ static cudaError_t shortlist_launch(const Tables& T, const int32_t* users, int n
 template <int G, int QPL>
 static cudaError_t shortlist_gq(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                                 const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                                int* flag, const float* tau, int I_pad, int short_width, cudaStream_t st)
+                                int* flag, const float* tau, int I_pad, int short_width, int stage_cap, cudaStream_t st)
 {
-    const size_t smem = (size_t)slots * cap * sizeof(uint2);
+    stage_cap = stage_cap > 0 ? min(stage_cap, slots * cap) : slots * cap;
+    const size_t smem = (size_t)stage_cap * sizeof(uint2);
     const int guard = shortlist_guard() ? 1 : 0;
-    if (short_width > kShortWidth) return shortlist_launch<G, QPL, kShortWidthWide>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, smem, st);
-    return shortlist_launch<G, QPL, kShortWidth>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, smem, st);
+    if (short_width > kShortWidth) return shortlist_launch<G, QPL, kShortWidthWide>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, stage_cap, smem, st);
+    return shortlist_launch<G, QPL, kShortWidth>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, guard, stage_cap, smem, st);
 }
 
 // rec [n_users, n_items]: final rows (float item indexes, NaN-padded like topn_select_kernel); flag [n_users]
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                             int* flag, const float* tau, int I_pad, int short_width, cudaStream_t st)
+                             int* flag, const float* tau, int I_pad, int short_width, int stage_cap, cudaStream_t st)
 {
     int qpl = 1;
     const int G = train_group_size(T, &qpl);
     if (max(T.Pp, T.Qp) > 4 * G || qpl > 4 || slots > 64 || (size_t)slots * cap * sizeof(uint2) > 160 * 1024) return cudaErrorInvalidValue;
-#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, short_width, st)
+#define RFM_SHORT(GG, QQ) return shortlist_gq<GG, QQ>(T, users, n_users, cand, cnt, slots, cap, bias, order, n_target, indptr, indices, filt, n_items, rec, flag, tau, I_pad, short_width, stage_cap, st)
     switch (G) {
         case 4:  RFM_SHORT(4, 1);
         case 8:  RFM_SHORT(8, 1);

@@ -101,7 +101,7 @@ constexpr int kShortWidth = 512;               // shortlist entries per row, nar
 constexpr int kShortWidthWide = 2048;          // wide tier (n' <= 1024: users with long histories under filter_previous)
 cudaError_t launch_shortlist(const Tables& T, const int32_t* users, int n_users, const float2* cand, const int* cnt, int slots, int cap, const float* bias,
                              const int32_t* order, const int* n_target, const int64_t* indptr, const int32_t* indices, int filt, int n_items, float* rec,
-                             int* flag, const float* tau, int I_pad, int short_width, cudaStream_t st);
+                             int* flag, const float* tau, int I_pad, int short_width, int stage_cap /* candidates staged per row; 0 = every slot's capacity */, cudaStream_t st);
 cudaError_t launch_eval_topk(const float* rec, const int64_t* order, int n_users, int k, const int64_t* test_indptr, const int32_t* test_items,
                              const int32_t* n_test, double* out5, uint8_t* hits_out, cudaStream_t st);
 cudaError_t launch_scatter_rows(const float* src, const int64_t* order, long long n_rows, int n_items, float* dst, cudaStream_t st);

@@ -725,6 +725,24 @@ def test_recommend_speculative_thresholds_equal_the_conservative_one(gpu_lib, mo
     assert np.mean(spec[~np.isnan(exact)] == exact[~np.isnan(exact)]) >= 0.99
 
 
+def test_recommend_rows_beyond_the_shortlist_staging_are_served_again(gpu_lib, monkeypatch):
+    """speculative modes stage only the candidates they expect per row (RANKFM_B200_TC_STAGE, default 2,048); a row with
+    more is flagged like an overflowing slot and served again conservatively -- same rows either way"""
+    U = 600
+    monkeypatch.setenv("RANKFM_B200_RECOMMEND", "tc")
+    sess, ui = _sparse_scoring_session(U, 130000, 24, seed=8)
+    users = np.arange(U, dtype=np.float32)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "safe")
+    safe = sess.recommend(users, 50, True)
+    monkeypatch.setenv("RANKFM_B200_TAU_MODE", "head")
+    monkeypatch.setenv("RANKFM_B200_TC_STAGE", "256")               # below the ~n' = 126 + candidates most rows collect
+    head = sess.recommend(users, 50, True)
+    retried = sess.recommend_retried()
+    sess.close()
+    assert np.array_equal(head, safe)
+    assert retried > 0, retried
+
+
 def test_recommend_head_threshold_falls_back_on_a_catalogue_without_bias_signal(gpu_lib, monkeypatch):
     """every item bias equal: the head subset is an arbitrary 1/16 of the catalogue, its threshold is loose, rows collect
     ~16 n' candidates and slots overflow -- those rows are served again conservatively, the results are the conservative
