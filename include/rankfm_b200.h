@@ -220,7 +220,7 @@ int rfm_session_recommend_stats(rfm_session *s, int64_t *tc_rows, int64_t *tc_re
  * 1-in-k sample of the item tiles, see rfm_api.cu "ESTIMATED") came out too high for them; results never depend on it */
 int rfm_session_recommend_retried(rfm_session *s, int64_t *tc_retried);
 /* the library keeps freed device blocks for the next call of the same shape (one-shot calls create and destroy a session
- * each; see rfm_api.cu "Device block cache"; limit RANKFM_B200_CACHE_MB, default 4096): give them back to the driver */
+ * each; see rfm_api.cu "Device block cache"; limit RANKFM_B200_CACHE_MB, default 16384): give them back to the driver */
 int rfm_trim_device_cache(void);
 int rfm_session_flush_l2(rfm_session *s);                                    /* overwrite a >L2-sized scratch buffer */
 int rfm_session_launch_count(rfm_session *s, int64_t *launches);             /* kernels launched by this session */

@@ -57,7 +57,8 @@ extern "C" int rfm_device_count(void)
 // `_fit` / `_predict` / `_recommend`) create and destroy a session per call; cudaMalloc + cudaFree of its ~15 buffers cost
 // 6-40 ms per call on the cfg2 workload and cudaFree stalled for 100-230 ms every few calls (profiles/: e2e probe,
 // RANKFM_B200_TIMING=1) -- against 22 ms of training.  Freed blocks are therefore kept (exact size classes, up to
-// RANKFM_B200_CACHE_MB, default 4096 MiB per process) and handed back to the next call of the same shape.
+// RANKFM_B200_CACHE_MB, default 16384 MiB per process -- a tenth of a B200's HBM; a cfg4-sized shard needs ~4 GB and
+// releasing its blocks to the driver cost 0.5 s per call) and handed back to the next call of the same shape.
 // dev_free() synchronises the device like cudaFree does, so a cached block is never still in use by queued work.
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
@@ -68,7 +69,7 @@ struct BlockCache {
     size_t idle_bytes = 0;
     size_t limit() const
     {
-        static const size_t v = [] { const char* e = getenv("RANKFM_B200_CACHE_MB"); return (size_t)(e ? atoll(e) : 4096) << 20; }();
+        static const size_t v = [] { const char* e = getenv("RANKFM_B200_CACHE_MB"); return (size_t)(e ? atoll(e) : 16384) << 20; }();
         return v;
     }
 };
@@ -210,6 +211,7 @@ struct rfm_session {
     Tables T{};
     int device = 0, n_sm = 148;
     cudaStream_t st = nullptr;
+    cudaStream_t st_side = nullptr;     // lower-priority helper stream of the tensor-core recommend pipeline (created on first use)
     // data
     int2* d_inter = nullptr; float* d_sw = nullptr; int64_t* d_indptr = nullptr; int32_t* d_indices = nullptr;
     int64_t N = 0, nnz = 0;
@@ -331,7 +333,11 @@ static cudaError_t pool_stream(int dev, cudaStream_t* out)
         for (size_t k = 0; k < g_pool.streams.size(); ++k)
             if (g_pool.streams[k].first == dev) { *out = g_pool.streams[k].second; g_pool.streams.erase(g_pool.streams.begin() + (long)k); return cudaSuccess; }
     }
-    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+    // one step above the default (= lowest) priority: helper streams created with the default priority (the threshold select
+    // of the recommend pipeline) then only fill what the kernels of a session's main stream leave free
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { least = 0; greatest = 0; }
+    return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, greatest < least ? least - 1 : least);
 }
 static cudaError_t pool_event(int dev, cudaEvent_t* out)
 {
@@ -385,6 +391,7 @@ extern "C" int rfm_session_destroy(rfm_session* s)
     for (void* q : s->scratch) dev_free(q);
     if (s->t0) s->ev.push_back(s->t0);
     if (s->t1) s->ev.push_back(s->t1);
+    if (s->st_side) cudaStreamDestroy(s->st_side);
     pool_return(s->device, s->st, s->ev);               // the stream is idle: every dev_free above synchronised the device
     delete s;
     return RFM_OK;
@@ -1210,18 +1217,24 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
     const int split_cap = std::max(1, std::min(n_tiles1, width / (cand_cap * SPS)));
     // The user batches run back to back on the session's stream; targets of all batches are uploaded once and the redo
     // flags of all rows are read once, so the loop never synchronises with the host (except once after the first batch of
-    // an estimated-threshold call, to see whether the estimate works on this catalogue).  (Running the shortlist kernel of
-    // batch b on a second stream next to the GEMM of batch b+1 was measured and bought nothing: a GEMM CTA holds ~200 KB
-    // of an SM's shared memory, so shortlist blocks cannot co-reside with it and only delay the next wave -- GEMM + filter
-    // 6.2 -> 8.3 ms per 65,536 users for the same 9.0 ms total.)
+    // a speculative-threshold call, to see whether the speculation works on this catalogue).
+    // Software pipeline over the batches: the FRONT of batch b+1 (pack the user operand, pass 1, threshold select) is
+    // issued before pass 2 of batch b, with the threshold select on a second, lower-priority stream -- it needs ~5 KB of
+    // shared memory per block and co-resides with the pass-2 CTAs (which leave ~28 KB per SM and 70 % of the issue slots
+    // free), so its 0.054 ms per batch disappear under pass 2.  A, the block bounds and tau are double-buffered.
+    // (The same trick does NOT work for the shortlist kernel: its blocks cannot co-reside with a GEMM CTA that holds
+    // ~200 KB of an SM's shared memory and only delay the next wave -- measured in round 2: GEMM + filter 6.2 -> 8.3 ms
+    // per 65,536 users for the same 9.0 ms total.)
     __nv_bfloat16_raw* d_A = nullptr; int* d_ntgt = nullptr; float2* d_cand = nullptr; int* d_cnt = nullptr;
     float *d_rowmax = nullptr, *d_tau = nullptr; int* d_flag = nullptr;
     const int64_t n_batches = (n_users + rows_alloc - 1) / rows_alloc;
-    struct Events : std::vector<cudaEvent_t> { ~Events() { for (auto e : *this) cudaEventDestroy(e); } } ev;    // timing pairs (GEMM + filter of each batch)
-    if ((rc = scratch_get(s, 1, (size_t)rows_alloc * Kp, &d_A))) return rc;
+    const bool piped = n_batches > 1 && !(getenv("RANKFM_B200_TC_PIPE") && !strcmp(getenv("RANKFM_B200_TC_PIPE"), "0"));
+    const size_t nbuf = piped ? 2 : 1;
+    struct Events : std::vector<cudaEvent_t> { ~Events() { for (auto e : *this) cudaEventDestroy(e); } } ev;    // timing pairs (GEMM + filter kernels)
+    if ((rc = scratch_get(s, 1, nbuf * rows_alloc * Kp, &d_A))) return rc;
     if ((rc = scratch_get(s, 2, (size_t)n_batches * rows_alloc, &d_ntgt))) return rc;
-    if ((rc = scratch_get(s, 3, (size_t)rows_alloc, &d_tau))) return rc;
-    if ((rc = scratch_get(s, 4, (size_t)rows_alloc * n_sub1, &d_rowmax))) return rc;
+    if ((rc = scratch_get(s, 3, nbuf * rows_alloc, &d_tau))) return rc;
+    if ((rc = scratch_get(s, 4, nbuf * rows_alloc * n_sub1, &d_rowmax))) return rc;
     if ((rc = scratch_get(s, 5, (size_t)rows_alloc * width, &d_cand))) return rc;
     if ((rc = scratch_get(s, 6, (size_t)rows_alloc * split_cap * SPS, &d_cnt))) return rc;
     if ((rc = scratch_get(s, 9, (size_t)n_users, &d_flag))) return rc;
@@ -1233,34 +1246,85 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         }
     CU(cudaMemcpyAsync(d_ntgt, ntgt.data(), ntgt.size() * 4, cudaMemcpyHostToDevice, s->st));
     std::vector<int> flag_h((size_t)n_users);
-    struct PooledEvents : std::vector<cudaEvent_t> { int dev; explicit PooledEvents(int d) : dev(d) {} ~PooledEvents() { pool_return(dev, nullptr, *this); } } batch_done(s->device);
-    int64_t served = n_users;                                        // rows this invocation's loop handles
-    for (int64_t bi = 0; bi < n_batches; ++bi) {
-        const int64_t off = bi * rows_alloc;
-        const int nb = (int)std::min<int64_t>(rows_alloc, n_users - off);
-        const int M_pad = (nb + MT - 1) / MT * MT;
-        const int n_splits = std::max(1, std::min(split_cap, s->n_sm / (M_pad / MT)));
-        const int slots = n_splits * SPS, cap = width / slots;
-        float2* cand = d_cand;
-        int* cnt = d_cnt;
-        const int* tgt = d_ntgt + (size_t)off;
-        CU(launch_pack_gemm_users(T, d_users + off, nb, M_pad, Kp, d_A, s->st));
-        if (gemm_ms) {
-            cudaEvent_t ta, tb;
-            if (cudaEventCreate(&ta) != cudaSuccess || cudaEventCreate(&tb) != cudaSuccess) return fail(RFM_ERR_CUDA, "cudaEventCreate failed");
-            ev.push_back(ta); ev.push_back(tb);
-            CU(cudaEventRecord(ta, s->st));
-        }
+    struct PooledEvents : std::vector<cudaEvent_t> { int dev; explicit PooledEvents(int d) : dev(d) {} ~PooledEvents() { pool_return(dev, nullptr, *this); } };
+    PooledEvents batch_done(s->device), order_ev(s->device);
+    std::vector<cudaEvent_t> thr_done((size_t)n_batches, nullptr);
+    cudaStream_t side = s->st;
+    if (piped) {
+        if (!s->st_side) CU(cudaStreamCreateWithFlags(&s->st_side, cudaStreamNonBlocking));      // default (= lowest) priority; pooled streams run above it
+        side = s->st_side;
+    }
+    struct SideSync { cudaStream_t st; ~SideSync() { if (st) cudaStreamSynchronize(st); } } side_sync{piped ? side : nullptr};   // nothing of this call outlives it
+    struct Geom { int64_t off; int nb, M_pad, n_splits, slots, cap; };
+    auto geom = [&](int64_t bi) {
+        Geom g;
+        g.off = bi * rows_alloc;
+        g.nb = (int)std::min<int64_t>(rows_alloc, n_users - g.off);
+        g.M_pad = (g.nb + MT - 1) / MT * MT;
+        g.n_splits = std::max(1, std::min(split_cap, s->n_sm / (g.M_pad / MT)));
+        g.slots = g.n_splits * SPS; g.cap = width / g.slots;
+        return g;
+    };
+    auto timed = [&](bool begin) -> int {                            // open / close a timing bracket on the main stream
+        if (!gemm_ms) return RFM_OK;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return fail(RFM_ERR_CUDA, "cudaEventCreate failed");
+        ev.push_back(e);
+        (void)begin;
+        CU(cudaEventRecord(e, s->st));
+        return RFM_OK;
+    };
+    // front of a batch: user operand, pass 1 (block bounds), threshold select.  In the pipelined loop pass 1 is bracketed by
+    // itself and the select runs on the side stream; otherwise the caller's bracket spans pass 1 .. pass 2.
+    auto front = [&](int64_t bi) -> int {
+        const Geom g = geom(bi);
+        const size_t par = piped ? (size_t)(bi & 1) : 0;
+        __nv_bfloat16_raw* A = d_A + par * rows_alloc * Kp;
+        float* rowmax = d_rowmax + par * rows_alloc * n_sub1;
+        float* tau = d_tau + par * rows_alloc;
+        CU(launch_pack_gemm_users(T, d_users + g.off, g.nb, g.M_pad, Kp, A, s->st));
+        int r = timed(true);
+        if (r) return r;
         const int subset = (tau_mode == 1 || (tau_mode == 0 && !tau_subset_head())) ? stride : -stride;
-        cudaError_t e = launch_score_filter(T, 1, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, subset, nullptr, nullptr, nullptr, 0, d_rowmax, nullptr, s->st);
+        cudaError_t e = launch_score_filter(T, 1, A, s->d_gemm_B, s->d_gemm_bias, g.nb, g.M_pad, I_pad, g.n_splits, subset, nullptr, nullptr, nullptr, 0, rowmax, nullptr, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e));
-        e = launch_row_threshold(d_rowmax, M_pad, n_sub1, tgt, d_tau, tau_mode == 1 ? stride : 1, tau_mode == 1 ? z : 0.f, s->st);
+        if (piped) {
+            if ((r = timed(false))) return r;
+            cudaEvent_t p1;
+            CU(pool_event(s->device, &p1)); order_ev.push_back(p1);
+            CU(cudaEventRecord(p1, s->st));
+            CU(cudaStreamWaitEvent(side, p1, 0));
+        }
+        e = launch_row_threshold(rowmax, g.M_pad, n_sub1, d_ntgt + (size_t)g.off, tau, tau_mode == 1 ? stride : 1, tau_mode == 1 ? z : 0.f, side);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "row_threshold launch failed: %s", cudaGetErrorString(e));
-        e = launch_score_filter(T, 2, d_A, s->d_gemm_B, s->d_gemm_bias, nb, M_pad, I_pad, n_splits, 1, cand, cnt, d_tau, cap, nullptr, nullptr, s->st);
+        if (piped) {
+            cudaEvent_t td;
+            CU(pool_event(s->device, &td)); order_ev.push_back(td);
+            CU(cudaEventRecord(td, side));
+            thr_done[(size_t)bi] = td;
+        }
+        return RFM_OK;
+    };
+    int64_t served = n_users;                                        // rows this invocation's loop handles
+    if ((rc = front(0))) return rc;
+    for (int64_t bi = 0; bi < n_batches; ++bi) {
+        const Geom g = geom(bi);
+        const int64_t off = g.off;
+        const int nb = g.nb;
+        const size_t par = piped ? (size_t)(bi & 1) : 0;
+        const __nv_bfloat16_raw* A = d_A + par * rows_alloc * Kp;
+        const float* tau = d_tau + par * rows_alloc;
+        const int* tgt = d_ntgt + (size_t)off;
+        if (piped) {
+            if (bi + 1 < n_batches && (rc = front(bi + 1))) return rc;
+            if ((rc = timed(true))) return rc;                       // a select that is not done yet stalls inside this bracket
+            CU(cudaStreamWaitEvent(s->st, thr_done[(size_t)bi], 0));
+        }
+        cudaError_t e = launch_score_filter(T, 2, A, s->d_gemm_B, s->d_gemm_bias, nb, g.M_pad, I_pad, g.n_splits, 1, d_cand, d_cnt, tau, g.cap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e));
-        if (gemm_ms) CU(cudaEventRecord(ev.back(), s->st));
-        e = launch_shortlist(T, d_users + off, nb, cand, cnt, slots, cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
-                             n_items, d_rec + (size_t)off * n_items, d_flag + off, d_tau, I_pad, 2 * cand_cap, stage_cap, s->st);
+        if ((rc = timed(false))) return rc;
+        e = launch_shortlist(T, d_users + off, nb, d_cand, d_cnt, g.slots, g.cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
+                             n_items, d_rec + (size_t)off * n_items, d_flag + off, tau, I_pad, 2 * cand_cap, stage_cap, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
         s->launches += 5;
         if (sink) {
@@ -1269,12 +1333,13 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
             batch_done.push_back(done);                              // back to the pool when this call returns
             CU(cudaEventRecord(done, s->st));
         }
+        if (!piped && bi + 1 < n_batches && (rc = front(bi + 1))) return rc;
         if (tau_mode && bi == 0 && n_batches > 1 && !s->tau_spec_ok) {      // does the speculation work on this catalogue?
             CU(cudaMemcpyAsync(flag_h.data(), d_flag, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->st));
             CU(cudaStreamSynchronize(s->st));
             int64_t missed = 0;
             for (int r = 0; r < nb; ++r) missed += flag_h[(size_t)r] != 0;
-            if (missed * 32 > nb) { s->tau_spec_off = true; served = off + nb; break; }
+            if (missed * 32 > nb) { s->tau_spec_off = true; served = off + nb; if (piped) cudaStreamSynchronize(side); break; }
             s->tau_spec_ok = true;
         }
     }

@@ -733,10 +733,10 @@ def test_recommend_rows_beyond_the_shortlist_staging_are_served_again(gpu_lib, m
     sess, ui = _sparse_scoring_session(U, 130000, 24, seed=8)
     users = np.arange(U, dtype=np.float32)
     monkeypatch.setenv("RANKFM_B200_TAU_MODE", "safe")
-    safe = sess.recommend(users, 50, True)
+    safe = sess.recommend(users, 100, True)
     monkeypatch.setenv("RANKFM_B200_TAU_MODE", "head")
-    monkeypatch.setenv("RANKFM_B200_TC_STAGE", "256")               # below the ~n' = 126 + candidates most rows collect
-    head = sess.recommend(users, 50, True)
+    monkeypatch.setenv("RANKFM_B200_TC_STAGE", "256")               # every row collects at least its n' = 216 + (items seen) candidates
+    head = sess.recommend(users, 100, True)
     retried = sess.recommend_retried()
     sess.close()
     assert np.array_equal(head, safe)
