@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
+#include "rfm_host.h"
 #include "rfm_kernels.h"
 #include "rfm_pair.cuh"
 
@@ -773,14 +774,16 @@ __global__ void item_norm_max_kernel(const __nv_bfloat16* __restrict__ B, int I_
 // bias[I_pad] (sorted, descending; bias[I_pad] = largest operand-row norm), order[I_pad] (position -> item), B[I_pad, Kp]; once per weight state
 cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, float* bias, int32_t* order, cudaStream_t st)
 {
+    // scratch from the library's device block cache (rfm_host.h): a one-shot `_recommend` creates a session per call and
+    // would otherwise pay three cudaMalloc/cudaFree pairs (each a device synchronisation) per weight state
     float* raw = nullptr; int32_t* iota = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
-    cudaError_t e = cudaMalloc(&raw, (size_t)T.I * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&iota, (size_t)T.I * 4);
+    cudaError_t e = rfmh::dev_malloc(reinterpret_cast<void**>(&raw), (size_t)T.I * 4);
+    if (e == cudaSuccess) e = rfmh::dev_malloc(reinterpret_cast<void**>(&iota), (size_t)T.I * 4);
     if (e == cudaSuccess) {
         item_bias_kernel<<<148 * 4, 256, 0, st>>>(T, raw, iota);
         e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, raw, bias, iota, order, T.I, 0, 32, st);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    if (e == cudaSuccess) e = rfmh::dev_malloc(&tmp, tmp_bytes ? tmp_bytes : 16);
     if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, raw, bias, iota, order, T.I, 0, 32, st);   // stable: ties stay in item order
     if (e == cudaSuccess) e = cudaMemsetAsync(order + T.I, 0xff, (size_t)(I_pad - T.I) * 4, st);
     if (e == cudaSuccess) {
@@ -789,8 +792,8 @@ cudaError_t launch_pack_gemm_items(const Tables& T, int Kp, int I_pad, void* B, 
         item_norm_max_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(B), I_pad, Kp, bias + I_pad);
         e = cudaGetLastError();
     }
-    cudaStreamSynchronize(st);
-    cudaFree(raw); cudaFree(iota); cudaFree(tmp);
+    cudaStreamSynchronize(st);                  // the scratch goes back to the cache: nothing queued may still use it
+    rfmh::dev_free(raw); rfmh::dev_free(iota); rfmh::dev_free(tmp);
     return e;
 }
 cudaError_t launch_pack_gemm_users(const Tables& T, const int32_t* users, int n_users, int M_pad, int Kp, void* A, cudaStream_t st)
