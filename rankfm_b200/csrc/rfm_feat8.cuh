@@ -214,4 +214,68 @@ __device__ __forceinline__ void feat8_update_chains(const Tables& T, float* gp, 
     }
 }
 
+// One chain per warp (TrainParams::gp_race): the chain advances by ONE group's update per warp step.  With racing plain
+// stores every group computes and stores its update and all but the last writer's are lost -- G/32 of the work lands.
+// Here the warp picks the winner up front (the highest valid group) and applies ITS update with all 32 lanes: lane l takes
+// parameter row (l >> 2) of v_uf and of v_if and the quads (l & 3) + 4 j of that row.  The winner's scalars and vectors
+// arrive by shuffle (2 + 1 + 4 for the scalars and the w_if quad, 8 per quad pair for dij_new / vu_new).  Same result as
+// the race would give when that group wrote last; ~half the instructions (rows at a 256-byte stride cost a two-way bank
+// conflict per quarter warp, still half the shared-memory wavefronts).  Needs 8 <= G < 32.  Every lane must call.
+template <int G, int QPL>
+__device__ __forceinline__ void feat8_update_chains_warp(const Tables& T, float* gp, bool upd, int sub, const Feat8& f, const float4& dxq, float ec, float eta_rb,
+                                                         const float4 (&vu_new)[QPL], const float4 (&dij_new)[QPL])
+{
+    static_assert(G >= 8 && G < 32, "a warp-wide winner update needs several groups of at least 8 lanes");
+    const int lane = threadIdx.x & 31;
+    const unsigned lead = __ballot_sync(0xffffffffu, upd && sub == 0);
+    if (lead == 0u) return;                                                 // warp-uniform: no group has an update
+    const int L = (31 - __clz(lead)) / G * G;                               // first lane of the winner group
+    // the winner's x_uf[u, row] / dx[row] for this lane's row: lane s of a group offers value s, this lane fetches value `row`
+    float su = f.xu[0], sd = f.dx[0];
+#pragma unroll
+    for (int t = 1; t < kFeat8; ++t) { if ((sub & 7) == t) { su = f.xu[t]; sd = f.dx[t]; } }
+    const int row = lane >> 2, qsub = lane & 3;
+    const float xu_r = __shfl_sync(0xffffffffu, su, L + row), dx_r = __shfl_sync(0xffffffffu, sd, L + row);
+    const float ec_w = __shfl_sync(0xffffffffu, ec, L);
+    const float keep = 1.0f - eta_rb;
+    {                                                                       // w_if, every q (:283-286): lanes 0, 1 take the two quads
+        float4 d;
+        d.x = __shfl_sync(0xffffffffu, dxq.x, L + (lane & 1)); d.y = __shfl_sync(0xffffffffu, dxq.y, L + (lane & 1));
+        d.z = __shfl_sync(0xffffffffu, dxq.z, L + (lane & 1)); d.w = __shfl_sync(0xffffffffu, dxq.w, L + (lane & 1));
+        if (T.x_if_any && lane < 2 && 4 * lane < T.Qp) {
+            float4* wp = reinterpret_cast<float4*>(gp + 4 * lane);
+            const float4 w = *wp;
+            *wp = make_float4(fmaf(ec_w, d.x, w.x * keep), fmaf(ec_w, d.y, w.y * keep), fmaf(ec_w, d.z, w.z * keep), fmaf(ec_w, d.w, w.w * keep));
+        }
+    }
+    const float cu = ec_w * xu_r, cd = ec_w * dx_r;
+    const bool do_u = T.x_uf_any && row < T.P && xu_r != 0.0f;               // v_uf[p] for x_uf[u,p] != 0 (:313-318)
+    const bool do_d = T.x_if_any && row < T.Q && dx_r != 0.0f;               // v_if[q] for dx[q] != 0 (:321-326)
+    float* base_u = gp + T.gp_vuf + (size_t)row * T.Fp;
+    float* base_d = gp + T.gp_vif + (size_t)row * T.Fp;
+    constexpr int J = G * QPL / 4;                                          // quads per lane and row
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = (4 * j) / G;                                          // compile-time after unrolling: which of the winner's quads-per-lane
+        const int src = L + qsub + (4 * j) % G;                             // ... held by which of its lanes
+        const int q = qsub + 4 * j;                                         // quad of the row
+        float4 dj, vn;
+        dj.x = __shfl_sync(0xffffffffu, dij_new[k].x, src); dj.y = __shfl_sync(0xffffffffu, dij_new[k].y, src);
+        dj.z = __shfl_sync(0xffffffffu, dij_new[k].z, src); dj.w = __shfl_sync(0xffffffffu, dij_new[k].w, src);
+        vn.x = __shfl_sync(0xffffffffu, vu_new[k].x, src); vn.y = __shfl_sync(0xffffffffu, vu_new[k].y, src);
+        vn.z = __shfl_sync(0xffffffffu, vu_new[k].z, src); vn.w = __shfl_sync(0xffffffffu, vu_new[k].w, src);
+        if (do_u && q < T.NQ) {
+            float4* wp = reinterpret_cast<float4*>(base_u + 4 * q);
+            const float4 w = *wp;
+            *wp = make_float4(fmaf(cu, dj.x, w.x * keep), fmaf(cu, dj.y, w.y * keep), fmaf(cu, dj.z, w.z * keep), fmaf(cu, dj.w, w.w * keep));
+        }
+        if (do_d && q < T.NQ) {
+            float4* wp = reinterpret_cast<float4*>(base_d + 4 * q);
+            const float4 w = *wp;
+            *wp = make_float4(fmaf(cd, vn.x, w.x * keep), fmaf(cd, vn.y, w.y * keep), fmaf(cd, vn.z, w.z * keep), fmaf(cd, vn.w, w.w * keep));
+        }
+    }
+    __syncwarp();                                                           // the next step's lanes read rows other lanes wrote
+}
+
 }  // namespace rfm

@@ -43,7 +43,7 @@ struct TrainParams {
     float gp_gain;           // weight of each warp's delta when the chains are folded (see rfm_session_train)
     int32_t gp_floats;
     int32_t gp_private;      // 1: one feature-parameter chain per lane group (plain RMW), 0: one per warp (atomics)
-    int32_t gp_race;         // 1: one chain per warp, the lane groups' plain stores race (one update lands per step)
+    int32_t gp_race;         // one chain per warp, one update lands per step: 1 = the lane groups' plain stores race, 2 = the warp applies the winner group's update with all lanes
     uint32_t k0, k1, epoch_key;
     MtState* mt;             // non-null -> MT19937 sampler (serial only)
     EpochAcc* acc;

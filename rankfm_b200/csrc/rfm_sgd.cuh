@@ -375,7 +375,12 @@ __device__ __forceinline__ void apply_update(const TrainParams& p, float* gp, co
         }
     }
     if constexpr (F8) {
-        feat8_update_chains<G, QPL>(T, gp, upd, sub, *f8, dx, ec, eta * rb, vu_new, dij_new);
+        if constexpr (G >= 8 && G < 32) {
+            if (p.gp_race == 2) feat8_update_chains_warp<G, QPL>(T, gp, upd, sub, *f8, dx, ec, eta * rb, vu_new, dij_new);   // warp-uniform
+            else feat8_update_chains<G, QPL>(T, gp, upd, sub, *f8, dx, ec, eta * rb, vu_new, dij_new);
+        } else {
+            feat8_update_chains<G, QPL>(T, gp, upd, sub, *f8, dx, ec, eta * rb, vu_new, dij_new);
+        }
     } else if (FEAT) {
         const float rb_or_ra = rb;
         if (T.x_if_any) {

@@ -551,7 +551,10 @@ static cudaError_t launch_gq(const TrainParams& p0, int grid, cudaStream_t st)
     p.depth = pipe_depth(p.T, G);
     p.gp_floats = (int)gp_floats_of(p.T);
     p.gp_private = gp_private_of(p.T, G, p.depth);
-    p.gp_race = chain_per_warp(p.T, G) ? 1 : 0;
+    {
+        const char* e = getenv("RANKFM_B200_CHAIN");                        // group | race | winner (default)
+        p.gp_race = chain_per_warp(p.T, G) ? ((e && !strcmp(e, "race")) ? 1 : 2) : 0;
+    }
     const size_t smem = pipe_smem_bytes(p.T, G, p.depth);
     return launch_pipe<G, QPL>(p, feat, grid, smem, st);
 }
@@ -631,6 +634,16 @@ __global__ void __launch_bounds__(32) feat8_selftest_kernel(const Tables T, int 
         if (o >= T.F || (e < T.gp_vuf && e >= T.Q)) v = 0.f;
         gpa[e] = v; gpb[e] = v;
     }
+    // warp-shared chain copy for the winner-update path: starts as the LAST group's chain (the winner = highest valid group)
+    float* gpc = sm + (size_t)GPW * (3 * rows + 2 * gp_floats);
+    if (G < 32) {
+        for (int e = lane; e < gp_floats; e += 32) {
+            float v = 0.3f * selftest_value(seed * 7u + (GPW - 1), e);
+            const int o = e >= T.gp_vif ? (e - T.gp_vif) % T.Fp : (e >= T.gp_vuf ? (e - T.gp_vuf) % T.Fp : 0);
+            if (o >= T.F || (e < T.gp_vuf && e >= T.Q)) v = 0.f;
+            gpc[e] = v;
+        }
+    }
     __syncwarp();
     UserCtx<QPL> ua, ub;
     ItemRow<QPL> pos, neg;
@@ -664,12 +677,27 @@ __global__ void __launch_bounds__(32) feat8_selftest_kernel(const Tables T, int 
     float d_gp = 0.f, d_rows = 0.f, moved = 0.f;
     for (int e = sub; e < gp_floats; e += G) { d_gp = fmaxf(d_gp, fabsf(gpa[e] - gpb[e])); moved = fmaxf(moved, fabsf(gpa[e] - 0.3f * selftest_value(seed * 7u + gw, e))); }
     for (int e = sub; e < rows; e += G) d_rows = fmaxf(d_rows, fabsf(da[e] - db[e]));
+    if constexpr (G >= 8 && G < 32) {
+        // the warp-wide winner update (feat8_update_chains_warp) on the shared copy must leave exactly what the last group's
+        // own feat8 update left on its private copy
+        TrainParams p2 = p;
+        p2.gp_private = 0; p2.gp_race = 2;
+        __syncwarp();
+        for (int e = sub; e < rows; e += G) da[e] = 0.f;                    // scratch sink
+        __syncwarp();
+        apply_update<G, QPL, true, false, true, SmemSink, true>(p2, gpc, ua, pos, neg, 1, 1.3f, 1, pu, true, 0, sub, acc_b, sa, &f8);
+        __syncwarp();
+        const float* win = sm + (size_t)(GPW - 1) * (3 * rows + 2 * gp_floats) + rows + gp_floats;      // gpb of the last group
+        for (int e = lane; e < gp_floats; e += 32) d_gp = fmaxf(d_gp, fabsf(gpc[e] - win[e]));
+    }
     for (int off = 16; off > 0; off >>= 1) {
         d_a = fmaxf(d_a, __shfl_xor_sync(0xffffffffu, d_a, off)); d_b = fmaxf(d_b, __shfl_xor_sync(0xffffffffu, d_b, off));
         d_gp = fmaxf(d_gp, __shfl_xor_sync(0xffffffffu, d_gp, off)); d_rows = fmaxf(d_rows, __shfl_xor_sync(0xffffffffu, d_rows, off));
         moved = fmaxf(moved, __shfl_xor_sync(0xffffffffu, moved, off));
     }
-    if (lane == 0) { out[0] = d_a; out[1] = d_b; out[2] = d_gp; out[3] = d_rows; out[4] = moved; }
+    if (lane == 0) {                                          // max with what an earlier launch (another group shape) left
+        out[0] = fmaxf(out[0], d_a); out[1] = fmaxf(out[1], d_b); out[2] = fmaxf(out[2], d_gp); out[3] = fmaxf(out[3], d_rows); out[4] = fmaxf(out[4], moved);
+    }
     (void)GPW;
 }
 
@@ -677,7 +705,7 @@ template <int G, int QPL>
 static cudaError_t feat8_selftest_gq(const Tables& T, int gp_floats, uint32_t seed, float eta, float reg_b, float* out, cudaStream_t st)
 {
     if constexpr (G >= 8) {
-        const size_t smem = (size_t)(32 / G) * (3 * (T.ldu + 2 * T.ldi) + 2 * gp_floats) * sizeof(float);
+        const size_t smem = ((size_t)(32 / G) * (3 * (T.ldu + 2 * T.ldi) + 2 * gp_floats) + (size_t)gp_floats) * sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(feat8_selftest_kernel<G, QPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         feat8_selftest_kernel<G, QPL><<<1, 32, smem, st>>>(T, gp_floats, seed, eta, reg_b, out);
@@ -693,6 +721,16 @@ cudaError_t launch_feat8_selftest(const Tables& T, uint32_t seed, float eta, flo
     const int G = train_group_size(T, &qpl);
     const int gpf = (int)gp_floats_of(T);
     if (T.P > kFeat8 || T.Q > kFeat8 || G < 8) return cudaErrorInvalidValue;
+    {   // the production kernel's half-width shape (sgd_group_size), when it differs: same checks, results folded by max
+        int hq = 1;
+        const int hg = sgd_group_size(T, &hq);
+        if (hg != G || hq != qpl) {
+            cudaError_t e = cudaSuccess;
+            if (hg == 8 && hq == 2) e = feat8_selftest_gq<8, 2>(T, gpf, seed, eta, reg_b, out5, st);
+            else if (hg == 16 && hq == 2) e = feat8_selftest_gq<16, 2>(T, gpf, seed, eta, reg_b, out5, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
     switch (G) {
         case 8:  return feat8_selftest_gq<8, 1>(T, gpf, seed, eta, reg_b, out5, st);
         case 16: return feat8_selftest_gq<16, 1>(T, gpf, seed, eta, reg_b, out5, st);

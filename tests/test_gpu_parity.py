@@ -295,11 +295,13 @@ def test_feat8_side_feature_code_matches_the_generic_code(gpu_lib, F, P, Q):
 
 
 @pytest.mark.parametrize("F,P,Q,feat8,chain", [(12, 5, 6, "1", "warp"), (64, 8, 8, "1", "warp"), (64, 8, 8, "1", "group"), (64, 8, 8, "0", "warp"),
-                                               (40, 3, 8, "1", "warp"), (128, 8, 8, "1", "warp")])
+                                               (40, 3, 8, "1", "warp"), (128, 8, 8, "1", "warp"), (64, 8, 8, "1", "race")])
 def test_parallel_fit_with_features_statistical_parity(gpu_lib, F, P, Q, feat8, chain, monkeypatch):
     """(64, 8, 8) is BASELINE.json configs[2]'s row shape.  Default: the feat8 code path on half-width lane groups (G = 8, two
-    quads per lane) with ONE racing chain per warp; chain = "group": wide groups, one chain per lane group (round-2 first
-    version); feat8 = "0": the generic run-time loops with group-private chains"""
+    quads per lane) with ONE chain per warp that advances by the winner group's update, applied by all 32 lanes; chain =
+    "race": the same chain with every group storing its update (the last writer wins; round-2 second version); chain =
+    "group": wide groups, one chain per lane group (round-2 first version); feat8 = "0": the generic run-time loops with
+    group-private chains"""
     monkeypatch.setenv("RANKFM_B200_FEAT8", feat8)
     monkeypatch.setenv("RANKFM_B200_CHAIN", chain)
     U, I = 1500, 800
