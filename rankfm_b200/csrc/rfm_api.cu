@@ -1265,12 +1265,11 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         g.slots = g.n_splits * SPS; g.cap = width / g.slots;
         return g;
     };
-    auto timed = [&](bool begin) -> int {                            // open / close a timing bracket on the main stream
+    auto mark = [&]() -> int {                                       // opens / closes a timing bracket on the main stream (events pair up in order)
         if (!gemm_ms) return RFM_OK;
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return fail(RFM_ERR_CUDA, "cudaEventCreate failed");
         ev.push_back(e);
-        (void)begin;
         CU(cudaEventRecord(e, s->st));
         return RFM_OK;
     };
@@ -1283,13 +1282,13 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         float* rowmax = d_rowmax + par * rows_alloc * n_sub1;
         float* tau = d_tau + par * rows_alloc;
         CU(launch_pack_gemm_users(T, d_users + g.off, g.nb, g.M_pad, Kp, A, s->st));
-        int r = timed(true);
+        int r = mark();
         if (r) return r;
         const int subset = (tau_mode == 1 || (tau_mode == 0 && !tau_subset_head())) ? stride : -stride;
         cudaError_t e = launch_score_filter(T, 1, A, s->d_gemm_B, s->d_gemm_bias, g.nb, g.M_pad, I_pad, g.n_splits, subset, nullptr, nullptr, nullptr, 0, rowmax, nullptr, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 1 (tcgen05) launch failed: %s", cudaGetErrorString(e));
         if (piped) {
-            if ((r = timed(false))) return r;
+            if ((r = mark())) return r;
             cudaEvent_t p1;
             CU(pool_event(s->device, &p1)); order_ev.push_back(p1);
             CU(cudaEventRecord(p1, s->st));
@@ -1317,12 +1316,12 @@ static int recommend_tc(rfm_session* s, const int32_t* d_users, const int32_t* h
         const int* tgt = d_ntgt + (size_t)off;
         if (piped) {
             if (bi + 1 < n_batches && (rc = front(bi + 1))) return rc;
-            if ((rc = timed(true))) return rc;                       // a select that is not done yet stalls inside this bracket
+            if ((rc = mark())) return rc;                       // a select that is not done yet stalls inside this bracket
             CU(cudaStreamWaitEvent(s->st, thr_done[(size_t)bi], 0));
         }
         cudaError_t e = launch_score_filter(T, 2, A, s->d_gemm_B, s->d_gemm_bias, nb, g.M_pad, I_pad, g.n_splits, 1, d_cand, d_cnt, tau, g.cap, nullptr, nullptr, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "score_filter pass 2 (tcgen05) launch failed: %s", cudaGetErrorString(e));
-        if ((rc = timed(false))) return rc;
+        if ((rc = mark())) return rc;
         e = launch_shortlist(T, d_users + off, nb, d_cand, d_cnt, g.slots, g.cap, s->d_gemm_bias, s->d_gemm_order, tgt, s->d_indptr, s->d_indices, filter_previous,
                              n_items, d_rec + (size_t)off * n_items, d_flag + off, tau, I_pad, 2 * cand_cap, stage_cap, s->st);
         if (e != cudaSuccess) return fail(RFM_ERR_CUDA, "shortlist launch failed: %s", cudaGetErrorString(e));
