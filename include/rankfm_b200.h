@@ -125,6 +125,10 @@ int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_t r0, int64
  * (`_rankfm.pyx:67-87`), of the feature parameters after one gradient step (`:283-326`), of the row deltas, and the largest
  * parameter movement of that step (so a caller can see the step was not a no-op).  P or Q = 0: that block is inactive. */
 int rfm_debug_feat8(int32_t F, int32_t P, int32_t Q, uint32_t seed, float *out5);
+/* host arithmetic of the estimated row threshold of the tensor-core recommend path (`RANKFM_B200_TAU_MODE=estimate`): which
+ * block bound of a 1-in-k sample of the item tiles estimates the n'-th best score of the catalogue with z sigma of head room
+ * (z = 0 or k = 1: the n'-th itself).  No GPU needed. */
+int rfm_debug_tau_rank(int32_t want, int32_t sample_k, float z);
 
 /* ---- data preparation on the device: what `RankFM._init_all` / `_init_interactions` do with pandas on
  * the host (`rankfm.py:114-177`) and `_fit` with a Python loop (`_rankfm.pyx:201-212`), as device radix sorts ---- */

@@ -18,7 +18,7 @@ SAMPLER_PHILOX, SAMPLER_MT = 0, 1
 SCHED_PARALLEL, SCHED_SERIAL = 0, 1
 
 EXPORTS = [
-    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_comm_release_all", "rfm_host_register", "rfm_host_unregister", "rfm_debug_philox", "rfm_debug_feistel", "rfm_debug_feat8", "rfm_trim_device_cache",
+    "rfm_version", "rfm_last_error", "rfm_device_count", "rfm_nccl_unique_id", "rfm_comm_release_all", "rfm_host_register", "rfm_host_unregister", "rfm_debug_philox", "rfm_debug_feistel", "rfm_debug_feat8", "rfm_debug_tau_rank", "rfm_trim_device_cache",
     "rfm_prep_index_ids", "rfm_prep_user_items", "rfm_synth_zipf",
     "rfm_fit", "rfm_last_fit_phases", "rfm_predict", "rfm_recommend", "rfm_similar",
     "rfm_session_create", "rfm_session_train", "rfm_session_set_epoch_callback", "rfm_session_set_weights", "rfm_session_download",
@@ -79,6 +79,7 @@ def lib():
     L.rfm_debug_philox.argtypes = [C.c_uint32] * 6 + [vp]
     L.rfm_debug_feistel.argtypes = [i64, C.c_uint64, i32, i64, i64, vp]
     L.rfm_debug_feat8.argtypes = [i32, i32, i32, C.c_uint32, vp]
+    L.rfm_debug_tau_rank.argtypes = [i32, i32, C.c_float]
     L.rfm_prep_index_ids.argtypes = [vp, i64, i32, vp, vp, vp]
     L.rfm_prep_user_items.argtypes = [vp, i64, i32, i32, i32, vp, vp]
     L.rfm_synth_zipf.argtypes = [i32, i32, i64, C.c_double, C.c_double, C.c_uint64, C.c_uint64, i32, i32, i32, vp, vp, vp, vp]

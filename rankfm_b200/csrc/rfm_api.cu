@@ -193,6 +193,9 @@ extern "C" int rfm_debug_feat8(int32_t F, int32_t P, int32_t Q, uint32_t seed, f
     return RFM_OK;
 }
 
+// rank of the block bound that becomes the row threshold of the tensor-core recommend path (rfm_kernels.h: tau_rank)
+extern "C" int rfm_debug_tau_rank(int32_t want, int32_t sample_k, float z) { return rfm::tau_rank(want, sample_k, z); }
+
 extern "C" int rfm_debug_feistel(int64_t n, uint64_t seed, int32_t epoch, int64_t r0, int64_t count, int64_t* out)
 {
     if (!out || n < 1 || r0 < 0 || r0 + count > n) return fail(RFM_ERR_ARG, "bad feistel range");

@@ -76,6 +76,24 @@ def test_rng_contract_with_oracle(lib):
         assert np.array_equal(out, oracle.feistel_perm(n, seed, epoch))
 
 
+def test_estimated_threshold_rank_rule(lib):
+    """`tau_rank` (rfm_kernels.h): the m-th largest of a 1-in-k sample estimates the n'-th best of the whole catalogue;
+    m solves k m - z k sqrt(m) = n' (negative-binomial head room), never exceeds n', and degenerates to n' without a sample"""
+    rank = lib.rfm_debug_tau_rank
+    for want in (20, 56, 216, 1024):
+        assert rank(want, 1, 4.5) == want and rank(want, 8, 0.0) == want
+        prev = want
+        for k in (2, 4, 8, 16):
+            m = rank(want, k, 4.5)
+            assert 1 <= m <= prev                                   # a sparser sample looks at a smaller rank
+            assert k * m >= want                                    # expected number of catalogue items above the threshold
+            if m < want:                                            # not clamped: z sigma (k sqrt(m)) below the expectation still reaches n'
+                assert k * m - 4.5 * k * np.sqrt(m) >= want - k
+            assert rank(want, k, 0.001) <= m <= rank(want, k, 9.0)
+            prev = m
+    assert rank(216, 8, 4.5) == 64 and rank(216, 16, 4.5) == 45     # the values DESIGN.md / the simulation quote
+
+
 def test_user_items_csr_view():
     X = np.array([[0, 3], [2, 1], [0, 1], [2, 5], [2, 1]], np.int32)
     ui = _rankfm.UserItems.from_interactions(X, 3)
